@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the FEMpy assembly hot path on B200 (metric of BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU port of the reference's algorithm
+
+A step is ONE fused assembly of the CSR stiffness values + residual vector (BCs and loads applied) of the
+workload mesh.  At N=1 the workload is BASELINE config 2: structured 4-node quad mesh, 512 x 512 elements
+(526 338 DOF), isotropic plane stress.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAT = dict(E=70e9, nu=0.3, rho=2700.0, t=1.0)
+WORKLOADS = {  # name -> (element type, nx = ny, description)
+    "c2": ("quad", 512, "config2: structured Q4 512x512, 526338 DOF, iso plane stress"),
+    "c3": ("quad9", 500, "config3: structured Q9 500x500, 2004002 DOF, iso plane stress"),
+    "c4": ("triangle", 1580, "config4: structured T3 2x1580x1580, 4999122 DOF, iso plane stress"),
+    "c5": ("quad", 5000, "config5: structured Q4 5000x5000, 50020002 DOF, iso plane stress"),
+}
+METRIC = "elements/s assembled (CSR K + residual)"
+
+
+def make_workload(name, nx=None):
+    from fempy_b200 import meshes
+
+    elType, n, desc = WORKLOADS[name]
+    n = nx or n
+    coords, conn = meshes.GENERATORS[elType](n, n)
+    N = coords.shape[0]
+    numEl = conn[elType].shape[0]
+    rng = np.random.default_rng(0)
+    states = 1e-3 * rng.random((N, 2))
+    thick = np.full(numEl, MAT["t"])
+    left, right = meshes.edge_nodes(coords, x=0.0), meshes.edge_nodes(coords, x=2.0)
+    bcDOF = np.stack((2 * left, 2 * left + 1), axis=1).reshape(-1).astype(np.int64)
+    bcVal = np.zeros(bcDOF.size)
+    loads = np.zeros(2 * N)
+    loads[2 * right] += 1e4
+    return dict(elType=elType, n=n, desc=desc, coords=coords, conn=conn, states=states, thick=thick, bcDOF=bcDOF, bcVal=bcVal,
+                loads=loads, numNodes=N, numElems=numEl)
+
+
+def algorithmic_bytes(wl, nnz):
+    """Compulsory HBM traffic of one K+R assembly: int32 connectivity, coords, states,
+    thickness read once; K values and R written once."""
+    nn = wl["conn"][wl["elType"]].shape[1]
+    return 4 * nn * wl["numElems"] + 16 * wl["numNodes"] * 2 + 8 * wl["numElems"] + 8 * nnz + 16 * wl["numNodes"]
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.maxMhz = index, [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.maxMhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self._halt.is_set() and self.nv is not None:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.maxMhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_port_run(wl, rows):
+    """The CPU port (oracle/fem_oracle.py) on the first `rows` element rows of the workload mesh:
+    K (COO -> CSR) + R with BCs and loads, the reference's stages (FEMpy/Problem.py:565-661)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import fem_oracle as fo
+    from util import oracle_blocks
+
+    elType, n = wl["elType"], wl["n"]
+    perRow = wl["numElems"] // n
+    numEl = perRow * rows if elType != "triangle" else None
+    conn = wl["conn"][elType]
+    if elType == "triangle":
+        half = conn.shape[0] // 2
+        sub = np.vstack((conn[: (half // n) * rows], conn[half : half + (half // n) * rows]))
+    else:
+        sub = conn[:numEl]
+    numNodes = int(sub.max()) + 1
+    coords, states = wl["coords"][:numNodes], wl["states"][:numNodes]
+    thick = np.full(sub.shape[0], MAT["t"])
+    keep = wl["bcDOF"] < 2 * numNodes
+    bcDOF, bcVal, loads = wl["bcDOF"][keep], wl["bcVal"][keep], wl["loads"][: 2 * numNodes]
+    blocks = oracle_blocks({elType: sub})
+    t0 = time.perf_counter()
+    K = fo.assemble_matrix(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], bcDOF)
+    R = fo.assemble_residual(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], loads, bcDOF, bcVal)
+    dt = time.perf_counter() - t0
+    assert K.nnz > 0 and R.size == 2 * numNodes
+    return sub.shape[0], dt
+
+
+def cpu_baseline(wl, budget_s=12.0):
+    rows = max(1, wl["n"] // 16)
+    numEl, dt = cpu_port_run(wl, rows)  # calibration + warm numpy caches
+    rows = int(min(wl["n"], max(rows, rows * budget_s / max(dt, 1e-3))))
+    numEl, dt = cpu_port_run(wl, rows)
+    return {"value": numEl / dt, "unit": "elements/s", "cores": 1, "kind": "port",
+            "sample": f"oracle/fem_oracle.py (numpy port of the reference's stages) on the first {rows} of {wl['n']} element rows "
+                      f"of the workload ({numEl} elements, {dt:.2f} s)"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU port of the reference's algorithm on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    wl = make_workload(args.config if args.gpus == 1 else args.config_multi)
+    rows = max(1, wl["n"] // 8)
+    for _ in range(args.warmup):
+        cpu_port_run(wl, max(1, rows // 4))
+    total_el, total_t = 0, 0.0
+    for _ in range(args.steps):
+        numEl, dt = cpu_port_run(wl, rows)
+        total_el += numEl
+        total_t += dt
+    value = total_el / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sample_rows": rows},
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": 1, "kind": "port",
+                         "sample": f"first {rows} of {wl['n']} element rows per step, numpy port of the reference's stages"},
+        "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    from fempy_b200 import AssemblyPlan, Constitutive, Elements
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: fempy_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        raise NotImplementedError("multi-GPU bench arrives with fempy_b200.dist")
+    wl = make_workload(args.config, args.nx)
+    elType = wl["elType"]
+    el = {"quad": Elements.QuadElement2D(1), "quad9": Elements.QuadElement2D(2), "triangle": Elements.TriElement2D(1)}[elType]
+    cm = Constitutive.IsoPlaneStress(MAT["E"], MAT["nu"], MAT["rho"], MAT["t"])
+    mat = cm.material()
+
+    plan = AssemblyPlan(wl["numNodes"], 2, 2, device=local_rank)
+    N_, dN, w = el.tables()
+    t0 = time.perf_counter()
+    plan.addBlock(N_, dN, w, wl["conn"][elType])
+    plan.finalize()
+    plan_wall_ms = 1e3 * (time.perf_counter() - t0)
+    plan.setBCs(wl["bcDOF"], wl["bcVal"])
+    nnz, numDOF, numEl = plan.nnz, plan.numDOF, plan.numElements
+
+    stream = torch.cuda.current_stream()
+    plan.setStream(stream.cuda_stream)
+    d_coords = torch.from_numpy(wl["coords"]).to(dev)
+    d_states = torch.from_numpy(wl["states"]).to(dev)
+    d_thick = torch.from_numpy(wl["thick"]).to(dev)
+    d_loads = torch.from_numpy(wl["loads"]).to(dev)
+    d_K = torch.empty(nnz, dtype=torch.float64, device=dev)
+    d_R = torch.empty(numDOF, dtype=torch.float64, device=dev)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        plan.assembleDev(d_coords, d_states, d_thick, mat, True, d_loads, d_K, d_R)
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    launches_per_step = plan.lastLaunches
+
+    sampler = ClockSampler(local_rank)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    plan.profile(True)
+    torch.cuda.synchronize()
+    sampler.start()
+    for i in range(args.steps):
+        flush.zero_()  # evict the previous step's working set from L2 (untimed)
+        starts[i].record(stream)
+        step()
+        ends[i].record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    times = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    kernel_ms_sum, kernel_calls = plan.profileRead()
+    plan.profile(False)
+    ms_per_step = float(times.mean())
+    value = numEl / (ms_per_step * 1e-3)
+
+    # --- roofline of the dominant kernel -------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    alg_bytes = algorithmic_bytes(wl, nnz)
+    kernel_ms = kernel_ms_sum / max(kernel_calls, 1)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "assembly kernel (fused K_e/R_e evaluation + scatter)", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_element": alg_bytes / numEl,
+                "peak_source": peak_src, "step_frac_of_roofline": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
+
+    # --- end to end through the host-pointer C ABI (pinned host buffers) ---------------------------
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64).pin_memory()
+        t.numpy()[...] = a
+        return t.numpy()
+
+    h_coords, h_states, h_thick, h_loads = pinned(wl["coords"]), pinned(wl["states"]), pinned(wl["thick"]), pinned(wl["loads"])
+    h_K, h_R = pinned(np.zeros(nnz)), pinned(np.zeros(numDOF))
+    plan.setStream(None)
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        plan.assemble(h_coords, h_states, h_thick, mat, wl["bcDOF"], wl["bcVal"], True, h_loads, Kout=h_K, Rout=h_R)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.assemble(h_coords, h_states, h_thick, mat, wl["bcDOF"], wl["bcVal"], True, h_loads, Kout=h_K, Rout=h_R)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    checksum = float(h_R.sum())
+    e2e = {"value": numEl / e2e_s, "unit": "elements/s", "ms_per_step": 1e3 * e2e_s,
+           "h2d_bytes_per_step": int(h_coords.nbytes + h_states.nbytes + h_thick.nbytes + h_loads.nbytes),
+           "d2h_bytes_per_step": int(h_K.nbytes + h_R.nbytes), "api": "femb_assemble (host pointers, pinned)",
+           "residual_checksum": checksum}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": wl["desc"], "elements": numEl, "dof": numDOF, "nnz": nnz, "l2": "flushed between timed steps (512 MB write)",
+                   "states": "1e-3*rng(0)", "bcs": int(wl["bcDOF"].size)},
+        "nnz_per_s": nnz / (ms_per_step * 1e-3), "ms_per_step_min": float(times.min()), "ms_per_step_median": float(np.median(times)),
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+        "launches_per_step": int(launches_per_step), "clocks": clocks,
+        "plan_build": {"device_ms": plan.buildMs, "wall_ms": plan_wall_ms},
+    }  # fmt: skip
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(wl)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--config-multi", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--nx", type=int, default=None, help="override the mesh size (exploration only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,186 @@
+"""Host-side mirror of the reference's 2-D element families
+(reference FEMpy/Elements/Element.py:32-486, QuadElement2D.py:42-186, TriElement2D.py:69-169).
+
+The table generators (shape functions, gradients, quadrature) are host code; the batched per-element
+methods -- `computeResidualJacobians`, `computeResiduals`, `computeFunction` -- keep the reference's
+names, argument order and return shapes but run on the GPU through the C ABI: element arrays
+(E, n, d) are flattened into a throw-away plan with E*n nodes.
+"""
+import numpy as np
+
+from . import tables as T
+from .plan import AssemblyPlan
+
+
+class Element:
+    """Base class: sizes + the batched element-level seams (Element.py:163-486)."""
+
+    def __init__(self, numNodes, numDim, quadratureOrder, numStates=None):
+        if numDim not in [1, 2, 3]:
+            raise ValueError(f"Sorry, FEMpy doesn't support {numDim}-dimensional problems")
+        self.numNodes = numNodes
+        self.numDim = numDim
+        self.numStates = numStates if numStates is not None else numDim
+        self.numDOF = self.numNodes * self.numStates
+        self.quadratureOrder = quadratureOrder
+        self.name = f"{self.numNodes}Node-{self.numStates}Disp-{self.numDim}D-Element"
+
+    # -- tables, implemented by the families ----------------------------------------------------
+    def computeShapeFunctions(self, paramCoords):
+        raise NotImplementedError
+
+    def computeShapeFunctionGradients(self, paramCoords):
+        raise NotImplementedError
+
+    def getIntegrationPointWeights(self, order=None):
+        raise NotImplementedError
+
+    def getIntegrationPointCoords(self, order=None):
+        raise NotImplementedError
+
+    def getReferenceElementCoordinates(self):
+        raise NotImplementedError
+
+    def tables(self, intOrder=None):
+        """(N, dNdxi, w) at the element's Gauss points."""
+        order = self.quadratureOrder if intOrder is None else intOrder
+        pts = np.atleast_2d(self.getIntegrationPointCoords(order))
+        return self.computeShapeFunctions(pts), self.computeShapeFunctionGradients(pts), self.getIntegrationPointWeights(order)
+
+    # -- batched element-level methods on the GPU ---------------------------------------------------
+    def _flatPlan(self, nodeCoords, intOrder):
+        nodeCoords = np.ascontiguousarray(nodeCoords, dtype=np.float64)
+        numElements = nodeCoords.shape[0]
+        if nodeCoords.shape[1:] != (self.numNodes, self.numDim):
+            raise ValueError("nodeCoords must be numElements x numNodes x numDim")
+        plan = AssemblyPlan(numElements * self.numNodes, self.numDim, self.numStates)
+        N, dN, w = self.tables(intOrder)
+        conn = np.arange(numElements * self.numNodes, dtype=np.int64).reshape(numElements, self.numNodes)
+        plan.addBlock(N, dN, w, conn)
+        plan.finalize()
+        return plan, nodeCoords.reshape(-1, self.numDim)
+
+    @staticmethod
+    def _thickness(designVars, numElements):
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(designVars["Thickness"], dtype=np.float64), (numElements,)))
+
+    def computeResidualJacobians(self, nodeStates, nodeCoords, designVars, constitutiveModel, intOrder=None):
+        """(E, n*s, n*s) element stiffness matrices (Element.py:426-486)."""
+        plan, X = self._flatPlan(nodeCoords, intOrder)
+        q = np.ascontiguousarray(nodeStates, dtype=np.float64).reshape(-1, self.numStates)
+        numElements = X.shape[0] // self.numNodes
+        Ke, _ = plan.elementBlocks(X, q, self._thickness(designVars, numElements), constitutiveModel.material(), wantR=False)
+        plan.close()
+        return Ke.reshape(numElements, self.numDOF, self.numDOF)
+
+    def computeResiduals(self, nodeStates, nodeCoords, designVars, constitutiveModel, intOrder=None):
+        """(E, n, s) element residuals (Element.py:370-424)."""
+        plan, X = self._flatPlan(nodeCoords, intOrder)
+        q = np.ascontiguousarray(nodeStates, dtype=np.float64).reshape(-1, self.numStates)
+        numElements = X.shape[0] // self.numNodes
+        _, Re = plan.elementBlocks(X, q, self._thickness(designVars, numElements), constitutiveModel.material(), wantK=False)
+        plan.close()
+        return Re.reshape(numElements, self.numNodes, self.numStates)
+
+    def computeFunction(self, nodeCoords, nodeStates, elementDVs, function, elementReductionType, intOrder=None):
+        """Element function values (Element.py:163-273); note the argument order differs from the two
+        methods above, as in the reference.  `function` is what `constitutiveModel.getFunction` returned."""
+        if elementReductionType is not None:
+            assert elementReductionType.lower() in ["sum", "mean", "integrate", "min", "max", "ksmax", "ksmin"], \
+                "elementReductionType not valid"
+            if elementReductionType.lower() in ["ksmax", "ksmin"]:
+                raise NotImplementedError("KS aggregation is outside the CUDA hot path (SURVEY.md section 2.1)")
+        plan, X = self._flatPlan(nodeCoords, intOrder)
+        q = np.ascontiguousarray(nodeStates, dtype=np.float64).reshape(-1, self.numStates)
+        numElements = X.shape[0] // self.numNodes
+        vals = plan.function(X, q, function.constitutiveModel.material(), function.funcId, elementReductionType)
+        plan.close()
+        return vals.reshape(numElements, -1) if elementReductionType is None else vals
+
+
+class QuadElement2D(Element):
+    """Lagrange quadrilateral of order 1-3 in meshio node order (QuadElement2D.py:42-186)."""
+
+    def __init__(self, order=1, numStates=None, quadratureOrder=None):
+        if order not in [1, 2, 3]:
+            raise ValueError("Quad elements only support orders 1, 2 and 3")
+        self.order = order
+        if quadratureOrder is None:
+            quadratureOrder = int(np.ceil((2 * order + 1) / 2))
+        super().__init__((order + 1) ** 2, numDim=2, quadratureOrder=quadratureOrder, numStates=numStates)
+        self.name = f"Order{self.order}-LagrangeQuad"
+        self.shapeFuncToNodeOrder = T.QUAD_NODE_ORDER[order]
+
+    def computeShapeFunctions(self, paramCoords):
+        N = T.lagrange2d(paramCoords[:, 0], paramCoords[:, 1], self.order + 1)
+        return np.ascontiguousarray(N[:, self.shapeFuncToNodeOrder])
+
+    def computeShapeFunctionGradients(self, paramCoords):
+        dN = T.lagrange2d_deriv(paramCoords[:, 0], paramCoords[:, 1], self.order + 1)
+        return np.ascontiguousarray(dN[:, :, self.shapeFuncToNodeOrder])
+
+    def getIntegrationPointWeights(self, order=None):
+        return T.gauss_weights(self.numDim, self.quadratureOrder if order is None else order)
+
+    def getIntegrationPointCoords(self, order=None):
+        return T.gauss_points(self.numDim, self.quadratureOrder if order is None else order)
+
+    def getReferenceElementCoordinates(self):
+        n = self.order + 1
+        x = np.tile(np.linspace(-1, 1, n), n)
+        y = np.repeat(np.linspace(-1, 1, n), n)
+        return np.vstack((x[self.shapeFuncToNodeOrder], y[self.shapeFuncToNodeOrder])).T
+
+
+class TriElement2D(Element):
+    """Lagrange triangle of order 1-3 (TriElement2D.py:69-169)."""
+
+    def __init__(self, order=1, numStates=None, quadratureOrder=None):
+        if order not in [1, 2, 3]:
+            raise ValueError("Triangular elements only support orders 1, 2 and 3")
+        self.order = order
+        if quadratureOrder is None:
+            quadratureOrder = int(np.ceil((order + 1) / 2))
+        super().__init__((order + 1) * (order + 2) // 2, numDim=2, quadratureOrder=quadratureOrder, numStates=numStates)
+        self.name = f"Order{self.order}-LagrangeTri"
+
+    def computeShapeFunctions(self, paramCoords):
+        return T.lagrange_tri(paramCoords[:, 0], paramCoords[:, 1], self.order)
+
+    def computeShapeFunctionGradients(self, paramCoords):
+        return T.lagrange_tri_deriv(paramCoords[:, 0], paramCoords[:, 1], self.order)
+
+    def getIntegrationPointWeights(self, order=None):
+        return T.tri_weights(self.quadratureOrder if order is None else order)
+
+    def getIntegrationPointCoords(self, order=None):
+        return T.tri_points(self.quadratureOrder if order is None else order)
+
+    def getReferenceElementCoordinates(self):
+        if self.order == 1:
+            return np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+        if self.order == 2:
+            return np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [0.5, 0.0], [0.5, 0.5], [0.0, 0.5]])
+        t = 1 / 3
+        return np.array([[0, 0], [1, 0], [0, 1], [t, 0], [2 * t, 0], [2 * t, t], [t, 2 * t], [0, 2 * t], [0, t], [t, t]], dtype=float)
+
+
+def elementFromMeshioName(meshioName, numStates):
+    """meshio cell-type name -> element object, or None if unsupported (Model.py:429-488)."""
+    name = meshioName.lower()
+    if name[:4] == "quad":
+        if name == "quad":
+            return QuadElement2D(order=1, numStates=numStates)
+        numNodes = int(name[4:])
+        if numNodes != 8:
+            order = np.sqrt(numNodes) - 1
+            if int(order) == order and int(order) in (1, 2, 3):
+                return QuadElement2D(order=int(order), numStates=numStates)
+        return None
+    if name == "triangle":
+        return TriElement2D(order=1, numStates=numStates)
+    if name == "triangle6":
+        return TriElement2D(order=2, numStates=numStates)
+    if name == "triangle10":
+        return TriElement2D(order=3, numStates=numStates)
+    return None

@@ -1,0 +1,282 @@
+"""FEMpyProblem on the B200 path.
+
+`B200AssemblyMixin` overrides exactly the three methods of the reference's problem class that make up
+the assembly hot path -- `_assembleMatrix`, `_assembleResidual` (reference FEMpy/Problem.py:565-661)
+and `computeFunction` (:282-355) -- and routes them through one fused CUDA assembly call.  It only
+reads what SURVEY.md section 8b lists (model.nodeCoords, model.elements[type][...], model.dvs,
+constitutive parameters, problem.states / getBCs() / loads), so it can be mixed into the reference's own
+`FEMpyProblem` as well as into the host-side mirror below.
+
+`FEMpyProblem` here is that mirror: same public methods, attributes and error behaviour as the
+reference class (Problem.py:38-692), minus file output, so the parity tests read like the
+reference's own tests on a machine where the reference's dependencies are not installed.
+"""
+import copy
+import time
+
+import numpy as np
+from scipy.sparse import csr_array
+
+from . import assembly_utils as AssemblyUtils
+from .constitutive import FUNC_MASS, FUNC_VON_MISES, PLANE_STRAIN, PLANE_STRESS
+from .plan import AssemblyPlan
+
+try:  # same optional dependency as the reference (Problem.py:26-29); the solve is outside the hot path
+    from pypardiso import factorized
+except ModuleNotFoundError:
+    from scipy.sparse.linalg import factorized
+
+
+def materialFor(constitutiveModel):
+    """`femb_material` for a constitutive model object of this package or of the reference."""
+    from ._lib import Material
+
+    name = type(constitutiveModel).__name__
+    modelId = {"IsoPlaneStress": PLANE_STRESS, "IsoPlaneStrain": PLANE_STRAIN}.get(name)
+    if modelId is None:
+        raise NotImplementedError(f"constitutive model {name} has no CUDA implementation (and there is no CPU fallback)")
+    cm = constitutiveModel
+    return Material(float(cm.E), float(cm.nu), float(cm.rho), modelId, int(not cm.isLinear))
+
+
+def planFor(model, device=0):
+    """Build (once per model) the GPU plan: element tables + connectivity -> CSR pattern + scatter map."""
+    plan = getattr(model, "_b200_plan", None)
+    if plan is not None:
+        return plan
+    plan = AssemblyPlan(model.numNodes, model.numDim, model.constitutiveModel.numStates, device=device)
+    for elType, elData in model.elements.items():
+        el = elData["elementObject"]
+        pts = np.atleast_2d(el.getIntegrationPointCoords())
+        plan.addBlock(el.computeShapeFunctions(pts), el.computeShapeFunctionGradients(pts), el.getIntegrationPointWeights(),
+                      elData["connectivity"])
+    plan.finalize()
+    model._b200_plan = plan
+    return plan
+
+
+class B200AssemblyMixin:
+    """The CUDA assembly path behind FEMpyProblem's private assembly drivers."""
+
+    def _b200Inputs(self, states):
+        plan = planFor(self.model)
+        coords = np.ascontiguousarray(self.model.nodeCoords, dtype=np.float64)
+        thickness = np.ascontiguousarray(self.model.dvs["Thickness"], dtype=np.float64)
+        return plan, coords, np.ascontiguousarray(states, dtype=np.float64), thickness, materialFor(self.constitutiveModel)
+
+    def _assembleMatrix(self, states, applyBCs=True):
+        """Global stiffness matrix as scipy csr_array (Problem.py:565-615)."""
+        plan, coords, q, thickness, mat = self._b200Inputs(states)
+        bcDOF = bcVal = None
+        if applyBCs:
+            bcDOF, bcVal = AssemblyUtils.convertBCDictToLists(self.getBCs())
+        K, _ = plan.assemble(coords, q, thickness, mat, bcDOF, bcVal, applyBCs, None, wantK=True, wantR=False)
+        indptr, indices = plan.pattern()
+        return csr_array((K, indices, indptr), shape=(self.numDOF, self.numDOF))
+
+    def _assembleResidual(self, states, applyBCs=True):
+        """Global residual vector (Problem.py:617-661)."""
+        plan, coords, q, thickness, mat = self._b200Inputs(states)
+        bcDOF = bcVal = None
+        if applyBCs:
+            bcDOF, bcVal = AssemblyUtils.convertBCDictToLists(self.getBCs())
+        loads = AssemblyUtils.convertLoadsDictToVector(self.loads, self.numDOF) if self.loads else None
+        _, R = plan.assemble(coords, q, thickness, mat, bcDOF, bcVal, applyBCs, loads, wantK=False, wantR=True)
+        return R
+
+    def assembleSystem(self, states=None, applyBCs=True):
+        """K and R from ONE fused kernel pass (what `solve` needs; not in the reference API)."""
+        states = self.states if states is None else states
+        plan, coords, q, thickness, mat = self._b200Inputs(states)
+        bcDOF = bcVal = None
+        if applyBCs:
+            bcDOF, bcVal = AssemblyUtils.convertBCDictToLists(self.getBCs())
+        loads = AssemblyUtils.convertLoadsDictToVector(self.loads, self.numDOF) if self.loads else None
+        K, R = plan.assemble(coords, q, thickness, mat, bcDOF, bcVal, applyBCs, loads)
+        indptr, indices = plan.pattern()
+        return csr_array((K, indices, indptr), shape=(self.numDOF, self.numDOF)), R
+
+    def computeFunction(self, name, elementReductionType, globalReductionType=None):
+        """Element function over the whole model (Problem.py:282-355)."""
+        func = self.model.constitutiveModel.getFunction(name)  # raises ValueError for unknown names
+        funcId = {"mass": FUNC_MASS, "von-mises-stress": FUNC_VON_MISES}[name.lower()]
+        if elementReductionType is not None:
+            assert elementReductionType.lower() in ["sum", "mean", "integrate", "min", "max", "ksmax", "ksmin"], \
+                "elementReductionType not valid"
+            if elementReductionType.lower() in ["ksmax", "ksmin"]:
+                raise NotImplementedError("KS aggregation is outside the CUDA hot path (SURVEY.md section 2.1)")
+        del func
+        plan, coords, q, _, mat = self._b200Inputs(self.states)
+        vals = plan.function(coords, q, mat, funcId, elementReductionType)
+        functionValues = {}
+        start = 0
+        for (elType, elData), (_, P, E) in zip(self.model.elements.items(), plan.blocks):
+            if elementReductionType is None:
+                functionValues[elType] = vals[start : start + E * P].reshape(E, P)
+                start += E * P
+            else:
+                functionValues[elType] = vals[start : start + E]
+                start += E
+
+        if globalReductionType is not None:
+            assert globalReductionType.lower() in ["sum", "mean", "min", "max", "ksmax", "ksmin"], "globalReductionType not valid"
+            red = globalReductionType.lower()
+            if red in ("ksmax", "ksmin"):
+                raise NotImplementedError("KS aggregation is outside the CUDA hot path (SURVEY.md section 2.1)")
+            reductionFunc = {"mean": np.average, "sum": np.sum, "min": np.min, "max": np.max}[red]
+            globalValues = np.zeros(len(self.model.elements))
+            for i, elType in enumerate(functionValues):
+                globalValues[i] = reductionFunc(functionValues[elType])
+            return reductionFunc(globalValues)
+        return functionValues
+
+
+class _ProblemBase:
+    """Everything of the reference's FEMpyProblem that is NOT the hot path (Problem.py:53-504),
+    restated without the mdolab-baseclasses dependency."""
+
+    def __init__(self, name, model, options=None):
+        self.name = name
+        self.model = model
+        self.states = np.zeros((self.numNodes, self.numStates))
+        self.Jacobian = None
+        self.jacUpToDate = False
+        self.factorizedJac = None
+        self.jacIsFactorized = False
+        self.Res = np.zeros(self.numNodes * self.numStates)
+        self.resUpToDate = False
+        self.solveCounter = 0
+        self.BCs = {}
+        self.loads = {}
+        self.options = {"printTiming": False, "outputDir": None, "outputFormat": None, "outputFunctions": None}
+        for key, value in (options or {}).items():
+            if key not in self.options:
+                raise KeyError(f"Option {key} is not a valid FEMpyProblem option")
+            self.options[key] = value
+        for option in ("outputDir", "outputFormat", "outputFunctions"):
+            if self.options[option] is None:
+                self.options[option] = self.model.getOption(option)
+
+    def getOption(self, name):
+        return self.options[name]
+
+    def setOption(self, name, value):
+        self.options[name] = value
+
+    constitutiveModel = property(lambda self: self.model.constitutiveModel)
+    isLinear = property(lambda self: self.constitutiveModel.isLinear)
+    numDim = property(lambda self: self.model.numDim)
+    numNodes = property(lambda self: self.model.numNodes)
+    numDOF = property(lambda self: self.model.numDOF)
+    numStates = property(lambda self: self.constitutiveModel.numStates)
+    elements = property(lambda self: self.model.elements)
+
+    def solve(self):
+        """Residual + Jacobian assembly, linear solve, state increment (Problem.py:137-169)."""
+        times = {"Start": time.time()}
+        self.updateResidual(applyBCs=True)
+        times["ResAssembled"] = time.time()
+        self.updateJacobian(applyBCs=True)
+        times["JacAssembled"] = time.time()
+        update = self.solveJacLinear(-self.Res)
+        times["Solved"] = time.time()
+        self.incrementState(update)
+        if self.getOption("printTiming"):
+            self._printTiming(times)
+        self.solveCounter += 1
+        return times
+
+    def solveJacLinear(self, RHS):
+        if not self.jacUpToDate:
+            self.updateJacobian()
+        if self.factorizedJac is None or not self.jacIsFactorized:
+            self.factorizedJac = factorized(self.Jacobian.tocsc())
+            self.jacIsFactorized = True
+        return self.factorizedJac(RHS)
+
+    def incrementState(self, update):
+        self.states += update if update.shape == self.states.shape else update.reshape(self.states.shape)
+        self.markResOutOfDate()
+        if not self.isLinear:
+            self.markJacOutOfDate()
+
+    def updateState(self, update):
+        self.states[:] = update if update.shape == self.states.shape else update.reshape(self.states.shape)
+        self.markResOutOfDate()
+        if not self.isLinear:
+            self.markJacOutOfDate()
+
+    def reset(self):
+        self.updateState(np.zeros((self.numNodes, self.numStates)))
+
+    def updateResidual(self, applyBCs=True):
+        if not self.resUpToDate:
+            self.Res = self._assembleResidual(self.states, applyBCs=applyBCs)
+            self.markResUpToDate()
+
+    def updateJacobian(self, applyBCs=True):
+        if not self.jacUpToDate:
+            self.Jacobian = self._assembleMatrix(self.states, applyBCs=applyBCs)
+            self.markJacUpToDate()
+            self.jacIsFactorized = False
+
+    def markResOutOfDate(self):
+        self.resUpToDate = False
+
+    def markJacOutOfDate(self):
+        self.jacUpToDate = False
+
+    def markResUpToDate(self):
+        self.resUpToDate = True
+
+    def markJacUpToDate(self):
+        self.jacUpToDate = True
+
+    def _nodeDofLists(self, nodeInds, dof, value, scale=1.0):
+        if isinstance(nodeInds, (int, np.integer)):
+            nodeInds = [nodeInds]
+        if isinstance(dof, (int, np.integer)):
+            dof = [dof]
+        if isinstance(value, (float, int)):
+            value = [value] * len(dof)
+        elif len(value) != len(dof):
+            raise Exception("value should be a single entry or a list of values the same length as the DOF list.")
+        dofNodes, valDOF = [], []
+        for i in range(len(nodeInds)):
+            for j in range(len(dof)):
+                dofNodes.append(int(nodeInds[i]) * self.numStates + dof[j])
+                valDOF.append(value[j] / scale)
+        return dofNodes, valDOF
+
+    def addFixedBCToNodes(self, name, nodeInds, dof, value):
+        """Problem.py:357-402."""
+        dofNodes, valDOF = self._nodeDofLists(nodeInds, dof, value)
+        self.BCs[name] = {"DOF": dofNodes, "Value": valDOF}
+
+    def addLoadToNodes(self, name, nodeInds, dof, value, totalLoad=False):
+        """Problem.py:404-453."""
+        scale = float(len(nodeInds)) if totalLoad else 1.0
+        dofNodes, valDOF = self._nodeDofLists(nodeInds, dof, value, scale)
+        self.loads[name] = {"DOF": dofNodes, "Value": valDOF}
+
+    def addBodyLoad(self, name, loadingFunction):
+        raise NotImplementedError("Body loads are not yet implemented, sorry :(")
+
+    def getBCs(self):
+        BCs = copy.deepcopy(self.model.BCs)
+        BCs.update(self.BCs)
+        return BCs
+
+    def getElementStates(self, elementType):
+        """(E, n, s) nodal states per element (Problem.py:485-504), as one fancy-index gather."""
+        return self.states[self.elements[elementType]["connectivity"]]
+
+    def _printTiming(self, times):
+        print(f"\n Timing information for FEMpy problem: {self.name}")
+        print("Residual Assembly: {:11.5e} s".format(times["ResAssembled"] - times["Start"]))
+        print("Jacobian Assembly: {:11.5e} s".format(times["JacAssembled"] - times["ResAssembled"]))
+        print("Linear Solution:   {:11.5e} s".format(times["Solved"] - times["JacAssembled"]))
+
+
+class FEMpyProblem(B200AssemblyMixin, _ProblemBase):
+    """Drop-in for the reference's FEMpyProblem with the assembly hot path on the GPU."""

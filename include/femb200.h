@@ -1,0 +1,148 @@
+/*
+ * femb200 -- B200-native (sm_100a) finite-element assembly, C ABI.
+ *
+ * Drop-in boundary for FEMpy's assembly hot path.  The reference has no FFI layer; the seam it
+ * offers is three private methods of FEMpyProblem plus the batched Element methods and the
+ * AssemblyUtils helpers.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; femb_last_error() gives the text
+ *   - float64 C-contiguous arrays; int64 connectivity / DOF / CSR indices at the boundary
+ *   - host-pointer calls are synchronous; *_dev calls are asynchronous on the plan's stream
+ *   - the caller owns every buffer passed in; the plan owns its device memory until destroy
+ *   - there is no CPU fallback: without a CUDA device every compute call fails
+ */
+#ifndef FEMB200_H
+#define FEMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct femb_plan femb_plan;
+
+/* constitutive model ids (FEMpy/Constitutive/IsoPlaneStress.py, IsoPlaneStrain.py) */
+#define FEMB_PLANE_STRESS 0
+#define FEMB_PLANE_STRAIN 1
+
+/* element functions (ConstitutiveModel.getFunction names: "Mass", "Von-Mises-Stress") */
+#define FEMB_FUNC_MASS 0
+#define FEMB_FUNC_VON_MISES 1
+
+/* element reductions (FEMpy/Elements/Element.py:221-259) */
+#define FEMB_REDUCE_NONE 0 /* (E, P) point values */
+#define FEMB_REDUCE_SUM 1
+#define FEMB_REDUCE_MEAN 2
+#define FEMB_REDUCE_INTEGRATE 3
+#define FEMB_REDUCE_MIN 4
+#define FEMB_REDUCE_MAX 5
+
+/* what femb_assemble produces */
+#define FEMB_WANT_K 1
+#define FEMB_WANT_R 2
+
+/* material + kinematics of one assembly call.
+ * E, nu  -> D matrix exactly as FEMpy/Constitutive/StressModels/IsoStress.py:25-78
+ * model  -> FEMB_PLANE_STRESS | FEMB_PLANE_STRAIN
+ * nonlinear != 0 -> Green strain (ContinuumStrains.py:112-126,158-172), else small strain
+ * rho    -> density returned by the "Mass" function (IsoPlaneStress.py:211-216) */
+typedef struct femb_material {
+    double E;
+    double nu;
+    double rho;
+    int32_t model;
+    int32_t nonlinear;
+} femb_material;
+
+const char* femb_last_error(void);
+int femb_device_count(void);
+const char* femb_version(void);
+
+/* ---- plan: mesh topology + element tables -> CSR pattern + scatter map (built on the GPU, once)
+ * replaces FEMpyModel.__init__'s per-type element registry and getDOFfromNodeInds
+ * (FEMpy/Model.py:123-142,387-414) and the COO->CSR structure scipy derives on every call
+ * (FEMpy/Problem.py:613-615). */
+int femb_plan_create(int64_t numNodes, int32_t numDim, int32_t numStates, int32_t device, femb_plan** out);
+
+/* one element type ("block"); element ids run across blocks in the order they are added
+ * (FEMpy/Model.py:137-142).  N: (P, n) shape functions, dNdxi: (P, numDim, n) parametric gradients,
+ * w: (P) weights at the element's own Gauss points (Element.computeShapeFunctions /
+ * computeShapeFunctionGradients / getIntegrationPointWeights).  conn: (numElems, n) node ids. */
+int femb_plan_add_block(femb_plan* plan, int32_t nodesPerElem, int32_t numQuad, const double* N, const double* dNdxi,
+                        const double* w, int64_t numElems, const int64_t* conn);
+
+/* builds the node->element adjacency, the sorted structural CSR pattern and the element scatter map */
+int femb_plan_finalize(femb_plan* plan);
+void femb_plan_destroy(femb_plan* plan);
+
+/* run the plan's kernels on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream);
+ * NULL restores the plan's own stream */
+int femb_plan_set_stream(femb_plan* plan, void* cudaStream);
+int femb_plan_sync(femb_plan* plan);
+
+int64_t femb_plan_num_dof(const femb_plan* plan);
+int64_t femb_plan_num_elems(const femb_plan* plan);
+int64_t femb_plan_nnz(const femb_plan* plan);
+double femb_plan_build_ms(const femb_plan* plan); /* device time spent in finalize */
+int64_t femb_plan_last_launches(const femb_plan* plan); /* kernels launched by the last compute call */
+
+/* CSR structure of the stiffness matrix: indptr (numDOF+1), indices (nnz), int64, rows sorted --
+ * what scipy's csr_array(coo_array(...)) yields in FEMpyProblem._assembleMatrix (Problem.py:613-615) */
+int femb_plan_pattern(femb_plan* plan, int64_t* indptr, int64_t* indices);
+int femb_plan_pattern_dev(femb_plan* plan, int64_t* d_indptr, int64_t* d_indices);
+
+/* ---- K + R assembly: FEMpyProblem._assembleMatrix + _assembleResidual (FEMpy/Problem.py:565-661)
+ * coords (numNodes, numDim), states (numNodes, numStates), thickness (numElems) ["Thickness" DV],
+ * bcDof/bcVal (nBC) = AssemblyUtils.convertBCDictToLists output (duplicates allowed, reference
+ * semantics: rows zeroed, +1.0 on the diagonal per occurrence, last value wins in the residual;
+ * AssemblyUtils.py:26-94), applied when applyBCs != 0;  loads (numDOF) or NULL =
+ * convertLoadsDictToVector output.  Outputs: Kdata (nnz) in femb_plan_pattern order, R (numDOF).
+ * `want` selects FEMB_WANT_K / FEMB_WANT_R / both; unused outputs may be NULL. */
+int femb_assemble(femb_plan* plan, const double* coords, const double* states, const double* thickness,
+                  const femb_material* mat, const int64_t* bcDof, const double* bcVal, int64_t nBC, int32_t applyBCs,
+                  const double* loads, int32_t want, double* Kdata, double* R);
+
+/* device-resident variant: BCs are staged once with femb_plan_set_bcs; all pointers are device pointers */
+int femb_plan_set_bcs(femb_plan* plan, const int64_t* bcDof, const double* bcVal, int64_t nBC);
+int femb_assemble_dev(femb_plan* plan, const double* d_coords, const double* d_states, const double* d_thickness,
+                      const femb_material* mat, int32_t applyBCs, const double* d_loads, int32_t want, double* d_Kdata,
+                      double* d_R);
+
+/* CUDA-event timing of the dominant assembly kernel(s) inside femb_assemble_dev, on the plan's stream
+ * (measurement only: bench.py's roofline leg).  read() synchronises, returns the summed kernel time and
+ * the number of timed calls since the last read, and resets the counters. */
+int femb_plan_profile(femb_plan* plan, int32_t enable);
+int femb_plan_profile_read(femb_plan* plan, double* sumMs, int64_t* count);
+
+/* ---- element functions: FEMpyProblem.computeFunction / Element.computeFunction
+ * (FEMpy/Problem.py:282-355, FEMpy/Elements/Element.py:163-273).  out: (numElems) or (sum_b E_b*P_b)
+ * for FEMB_REDUCE_NONE, blocks concatenated in plan order. */
+int femb_function(femb_plan* plan, const double* coords, const double* states, const femb_material* mat,
+                  int32_t func, int32_t reduction, double* out);
+int femb_function_dev(femb_plan* plan, const double* d_coords, const double* d_states, const femb_material* mat,
+                      int32_t func, int32_t reduction, double* d_out);
+
+/* ---- per-element blocks: Element.computeResidualJacobians / computeResiduals
+ * (FEMpy/Elements/Element.py:370-486).  Ke: (E_b, n*s, n*s) per block, Re: (E_b, n, s) per block,
+ * blocks concatenated.  Either output may be NULL. */
+int femb_element_blocks(femb_plan* plan, const double* coords, const double* states, const double* thickness,
+                        const femb_material* mat, double* Ke, double* Re);
+
+/* ---- COO expansion of element matrices: AssemblyUtils.localMatricesToCOOArrays
+ * (FEMpy/Utils/AssemblyUtils.py:168-214): element-major, row-major triplets with exactly-zero values
+ * dropped.  rows/cols/vals have capacity numElems*nd*nd; *numOut receives the kept count. */
+int femb_local_matrices_to_coo(const double* localMats, const int64_t* localDOF, int64_t numElems, int32_t nd,
+                               int32_t device, int64_t* rows, int64_t* cols, double* vals, int64_t* numOut);
+
+/* ---- residual scatter: AssemblyUtils.scatterLocalResiduals (FEMpy/Utils/AssemblyUtils.py:217-238),
+ * globalResidual (numNodes*numStates) updated in place */
+int femb_scatter_local_residuals(const double* localRes, const int64_t* conn, int64_t numElems, int32_t nodesPerElem,
+                                 int32_t numStates, int64_t numNodes, int32_t device, double* globalResidual);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMB200_H */

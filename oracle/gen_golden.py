@@ -1,0 +1,196 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_harness.py) in the build container.
+
+TEST INFRASTRUCTURE.  Run once here:  python oracle/gen_golden.py
+The fixtures are committed; the GPU box (which has no /root/reference) only reads them.
+
+Fixtures
+  tables.npz      Gauss points/weights, N and dN/dxi of Quad order 1-3 and Tri order 1-3
+  elements.npz    element-level K_e, R_e, von Mises point values for random elements of every family
+                  x {plane stress, plane strain} x {linear, Green strain}  (the "finer seams" of SURVEY 8b)
+  meshes.npz      assembled K (CSR), R, element functions on small quad / quad9 / triangle / mixed meshes
+  lbracket.npz    config 1: Examples/Meshes/LBracket.msh mesh arrays + assembled K, R, solution, functions
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh  # noqa: E402
+from fempy_b200 import meshes  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+MAT = dict(E=70e9, nu=0.3, rho=2700.0, t=1.0)
+
+
+def families(fp):
+    fam = {}
+    for o in (1, 2, 3):
+        fam[f"quad{o}"] = fp.Elements.QuadElement2D(order=o)
+        fam[f"tri{o}"] = fp.Elements.TriElement2D(order=o)
+    return fam
+
+
+def gen_tables(fp):
+    out = {}
+    for name, el in families(fp).items():
+        pts = el.getIntegrationPointCoords()
+        out[f"{name}_pts"] = pts
+        out[f"{name}_w"] = el.getIntegrationPointWeights()
+        out[f"{name}_N"] = el.computeShapeFunctions(pts)
+        out[f"{name}_dN"] = el.computeShapeFunctionGradients(pts)
+        out[f"{name}_refcoords"] = el.getReferenceElementCoordinates()
+    np.savez_compressed(os.path.join(OUT, "tables.npz"), **out)
+
+
+def gen_elements(fp):
+    out = {}
+    numEl = 6
+    for name, el in families(fp).items():
+        rng = np.random.default_rng(42)
+        X = np.zeros((numEl, el.numNodes, 2))
+        for i in range(numEl):
+            X[i] = el.getRandomElementCoordinates(rng=rng)
+        if name == "quad1":  # the reference's known-answer element (tests/testElements.py:80-82)
+            X[0] = np.array([[0.0, 0.0], [2.0, 0.0], [2.0, 1.0], [0.0, 2.0]])
+        q = 0.05 * rng.random(X.shape)
+        thick = rng.random(numEl) + 0.5
+        if name == "quad1":
+            thick[0] = 1.0
+        out[f"{name}_X"], out[f"{name}_q"], out[f"{name}_t"] = X, q, thick
+        for model in (0, 1):
+            for linear in (True, False):
+                cm = rh.make_constitutive(fp, model, MAT["E"], MAT["nu"], MAT["rho"], MAT["t"], linear)
+                dvs = {"Thickness": thick}
+                key = f"{name}_m{model}_{'lin' if linear else 'nl'}"
+                out[key + "_Ke"] = el.computeResidualJacobians(q, X, dvs, cm)
+                out[key + "_Re"] = el.computeResiduals(q, X, dvs, cm)
+                out[key + "_vm"] = el.computeFunction(X, q, dvs, cm.getFunction("Von-Mises-Stress"), None)
+                out[key + "_vmmean"] = el.computeFunction(X, q, dvs, cm.getFunction("Von-Mises-Stress"), "mean")
+                out[key + "_massint"] = el.computeFunction(X, q, dvs, cm.getFunction("Mass"), "integrate")
+    np.savez_compressed(os.path.join(OUT, "elements.npz"), **out)
+
+
+def mixed_grid(nx, ny):
+    """Left half of the grid as quads, right half as triangles (two element types in one model)."""
+    coords, cq = meshes.quad4_grid(nx, ny)
+    conn = cq["quad"]
+    col = np.tile(np.arange(nx), ny)
+    quads = conn[col < nx // 2]
+    rest = conn[col >= nx // 2]
+    tris = np.vstack((rest[:, [0, 1, 2]], rest[:, [0, 2, 3]]))
+    return coords, {"quad": quads, "triangle": tris}
+
+
+def perturb(coords, seed):
+    """Break the vertical/horizontal edge alignment so no element entry is an exact zero and the
+    reference's value-dependent pattern equals the structural one (cf. tests/testProblem.py:52-54)."""
+    rng = np.random.default_rng(seed)
+    return coords + 1e-3 * rng.random(coords.shape)
+
+
+MESH_CASES = {
+    # name: (generator, args, model, linear, applyBCs)
+    "quad_ps": (meshes.quad4_grid, (6, 4), 0, True, True),
+    "quad_pe": (meshes.quad4_grid, (5, 5), 1, True, True),
+    "quad_ps_nobc": (meshes.quad4_grid, (4, 3), 0, True, False),
+    "quad_ps_nl": (meshes.quad4_grid, (4, 4), 0, False, True),
+    "quad9_ps": (meshes.quad9_grid, (3, 3), 0, True, True),
+    "quad9_pe": (meshes.quad9_grid, (4, 2), 1, True, True),
+    "tri_ps": (meshes.tri3_grid, (5, 4), 0, True, True),
+    "tri_pe": (meshes.tri3_grid, (4, 4), 1, True, True),
+    "mixed_ps": (mixed_grid, (6, 3), 0, True, True),
+    "quad_ps_32": (meshes.quad4_grid, (32, 32), 0, True, True),
+    "quad9_ps_10": (meshes.quad9_grid, (10, 10), 0, True, True),
+    "tri_ps_20": (meshes.tri3_grid, (20, 20), 0, True, True),
+}
+
+
+def gen_meshes(fp):
+    out = {}
+    for ci, (name, (gen, args, model, linear, applyBCs)) in enumerate(MESH_CASES.items()):
+        rng = np.random.default_rng(100 + ci)
+        coords, conn = gen(*args)
+        coords = perturb(coords, ci)
+        N = coords.shape[0]
+        numEl = sum(c.shape[0] for c in conn.values())
+        states = (1e-3 if linear else 5e-2) * rng.random((N, 2))
+        thick = rng.random(numEl) * 1e-2 + 1e-3
+        left = np.argwhere(coords[:, 0] < 1.5e-3).flatten()
+        right = np.argwhere(coords[:, 0] > 2.0 - 1e-9).flatten()
+        # BCs: left edge fixed to non-zero values; one DOF repeated in a second entry (diagonal 2.0,
+        # later value wins in the residual).  Loads: right edge + a second entry hitting the same DOFs.
+        bcs = [("Fixed", left, [0, 1], [0.0, 1e-4]), ("Again", [int(left[0])], [1], 2e-4)]
+        loads = [("Load", right, [0], 1e4, False), ("Load2", right[:2], [0, 1], [5e3, -2e3], True)]
+        m, p = rh.build_problem(fp, coords, conn, model, MAT["E"], MAT["nu"], MAT["rho"], MAT["t"], linear=linear,
+                                thickness=thick, bcs=bcs, loads=loads, states=states)
+        K, R = rh.assemble(p, applyBCs=applyBCs)
+        out[name + "_coords"], out[name + "_states"], out[name + "_thick"] = coords, states, thick
+        for k, c in conn.items():
+            out[f"{name}_conn_{k}"] = c
+        bcDOF, bcVal = [], []
+        for key, bc in p.getBCs().items():
+            bcDOF += bc["DOF"]
+            bcVal += bc["Value"]
+        out[name + "_bcDOF"], out[name + "_bcVal"] = np.array(bcDOF, dtype=np.int64), np.array(bcVal, dtype=float)
+        loadVec = np.zeros(2 * N)
+        for key in p.loads:
+            loadVec[p.loads[key]["DOF"]] += p.loads[key]["Value"]
+        out[name + "_loads"] = loadVec
+        out[name + "_meta"] = np.array([model, int(linear), int(applyBCs)])
+        out[name + "_indptr"], out[name + "_indices"], out[name + "_data"] = K.indptr, K.indices, K.data
+        out[name + "_R"] = R
+        for red in ("mean", "max", "min", "sum", "integrate"):
+            vals = p.computeFunction("Von-Mises-Stress", red)
+            for k in conn:
+                out[f"{name}_vm_{red}_{k}"] = vals[k]
+        vals = p.computeFunction("Mass", "integrate")
+        for k in conn:
+            out[f"{name}_mass_integrate_{k}"] = vals[k]
+        out[name + "_mass_total"] = np.array(p.computeFunction("Mass", "integrate", "sum"))
+        out[name + "_vm_mean_max"] = np.array(p.computeFunction("Von-Mises-Stress", "mean", "max"))
+    np.savez_compressed(os.path.join(OUT, "meshes.npz"), **out)
+
+
+def gen_lbracket(fp):
+    """Config 1: the vertical-load case of Examples/LBracketExample.py:28-62."""
+    import contextlib
+    import io
+
+    E, nu, rho, t = 71.7e9, 0.33, 2780, 5e-3
+    cm = fp.Constitutive.IsoPlaneStress(E, nu, rho, t)
+    model = fp.FEMpyModel(cm, meshFileName=os.path.join(rh.REFERENCE_ROOT, "Examples", "Meshes", "LBracket.msh"))
+    coords = model.getCoordinates()
+    top = np.argwhere(coords[:, 1] == np.max(coords[:, 1])).flatten()
+    model.addFixedBCToNodes(name="Fixed", nodeInds=[int(i) for i in top], dof=[0, 1], value=0.0)
+    prob = model.addProblem("Vertical-Load")
+    right = np.argwhere(coords[:, 0] == np.max(coords[:, 0])).flatten()
+    prob.addLoadToNodes(name="RightEdgeLoad", nodeInds=[int(i) for i in right], dof=1, value=-1e5, totalLoad=True)
+    K, R = rh.assemble(prob)
+    with contextlib.redirect_stdout(io.StringIO()):
+        prob.solve()
+    out = dict(
+        coords=coords, conn=model.elements["quad"]["connectivity"].astype(np.int32), top=top, right=right,
+        indptr=K.indptr, indices=K.indices.astype(np.int32), data=K.data, R=R, u=prob.states,
+        vm_mean=prob.computeFunction("Von-Mises-Stress", "mean")["quad"],
+        vm_mean_max=np.array(prob.computeFunction("Von-Mises-Stress", "mean", "max")),
+        mass=np.array(prob.computeFunction("Mass", "integrate", "sum")),
+        material=np.array([E, nu, rho, t]),
+    )
+    K2, R2 = rh.assemble(prob)  # residual at the solved state (should be ~0 except rounding)
+    out["R_solved"] = R2
+    np.savez_compressed(os.path.join(OUT, "lbracket.npz"), **out)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    fp = rh.import_reference()
+    gen_tables(fp)
+    gen_elements(fp)
+    gen_meshes(fp)
+    gen_lbracket(fp)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

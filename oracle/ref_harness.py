@@ -1,0 +1,75 @@
+"""Import and drive the UNMODIFIED reference (FEMpy at /root/reference) inside the build container.
+
+TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  /root/reference does not exist on the GPU box, so nothing
+run there may import this module; it is used by ``oracle/gen_golden.py`` (fixture generation) and by
+the ``-m "not gpu"`` tests that pin the oracle, which skip when the reference is absent.
+
+Three stub packages under ``oracle/stubs`` (baseclasses, meshio, parameterized) replace the
+reference's un-installed dependencies; the reference sources themselves are
+imported from where they lie and are never copied.
+"""
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("FEMPY_REFERENCE_ROOT", "/root/reference")
+_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "FEMpy"))
+
+
+def import_reference():
+    """Returns the reference ``FEMpy`` package (numba kernels compile on first import, ~15 s)."""
+    if not available():
+        raise ImportError(f"reference not found at {REFERENCE_ROOT}")
+    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/fempy_ref_numba_cache")
+    for p in (REFERENCE_ROOT, _STUBS):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import FEMpy  # noqa: E402
+    return FEMpy
+
+
+def make_constitutive(fp, model, E, nu, rho, t, linear=True):
+    cls = {0: fp.Constitutive.IsoPlaneStress, 1: fp.Constitutive.IsoPlaneStrain}[model]
+    return cls(E, nu, rho, t, linear=linear)
+
+
+def build_problem(fp, coords, connectivity, model, E, nu, rho, t, linear=True, thickness=None,
+                  bcs=None, loads=None, states=None):
+    """Reference FEMpyModel + FEMpyProblem from arrays.
+
+    bcs:   list of (name, nodeInds, dof, value)  -> problem.addFixedBCToNodes
+    loads: list of (name, nodeInds, dof, value, totalLoad) -> problem.addLoadToNodes
+    """
+    import numpy as np
+
+    con = make_constitutive(fp, model, E, nu, rho, t, linear)
+    femModel = fp.FEMpyModel(con, nodeCoords=np.array(coords), connectivity={k: np.array(v) for k, v in connectivity.items()})
+    if thickness is not None:
+        femModel.setDesignVariables({"Thickness": np.array(thickness)})
+    prob = femModel.addProblem("oracle")
+    for name, nodes, dof, value in bcs or []:
+        prob.addFixedBCToNodes(name, [int(n) for n in nodes], dof, value)
+    for name, nodes, dof, value, total in loads or []:
+        prob.addLoadToNodes(name, [int(n) for n in nodes], dof, value, totalLoad=total)
+    if states is not None:
+        prob.updateState(np.array(states))
+    return femModel, prob
+
+
+def assemble(prob, applyBCs=True):
+    """(K csr, R) through the reference's own private assembly drivers (Problem.py:565-661)."""
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        K = prob._assembleMatrix(prob.states, applyBCs=applyBCs)
+        R = prob._assembleResidual(prob.states, applyBCs=applyBCs)
+    K.sort_indices()
+    return K, R

@@ -1,0 +1,359 @@
+"""Parity of the CUDA path (through the C ABI / the Model-Problem mirror) with the oracle, the golden
+fixtures produced by the unmodified reference, and the reference's own known-answer vectors.
+
+Bar (BASELINE.json north_star): sparsity pattern and DOF maps bit-exact; stiffness, residual and stress
+values within 1e-12 relative (to the largest magnitude of the array -- summation order differs)."""
+import numpy as np
+import pytest
+from scipy.sparse import csr_array
+
+from fempy_b200 import AssemblyPlan, AssemblyUtils, FEMpyModel, meshes
+from oracle import fem_oracle as fo
+from test_oracle_golden import COO_COLS, COO_DOF, COO_MATS, COO_ROWS, COO_VALS, KNOWN_QUAD_K, KNOWN_QUAD_X, two_quad_problem
+from util import ELEMENT_FOR, FAMILY_ELEMENT, MAT, build_problem, golden, make_cm, mesh_case, mesh_case_names, oracle_blocks, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def problem_from_case(c):
+    cm = make_cm(c["model"], c["linear"])
+    m = FEMpyModel(cm, nodeCoords=c["coords"], connectivity=c["conn"])
+    m.setDesignVariables({"Thickness": c["thick"]})
+    p = m.addProblem("case")
+    p.BCs["golden"] = {"DOF": [int(d) for d in c["bcDOF"]], "Value": [float(v) for v in c["bcVal"]]}
+    nz = np.flatnonzero(c["loads"])
+    p.loads["golden"] = {"DOF": [int(d) for d in nz], "Value": [float(v) for v in c["loads"][nz]]}
+    p.updateState(c["states"])
+    return m, p
+
+
+# ---- fixtures from the unmodified reference ----------------------------------------------------------------------
+@pytest.mark.parametrize("name", mesh_case_names(golden("meshes.npz")))
+def test_assembled_meshes_against_reference(name):
+    g = golden("meshes.npz")
+    c = mesh_case(g, name)
+    m, p = problem_from_case(c)
+    K = p._assembleMatrix(p.states, applyBCs=c["applyBCs"])
+    R = p._assembleResidual(p.states, applyBCs=c["applyBCs"])
+    assert isinstance(K, csr_array) and K.shape == (p.numDOF, p.numDOF)
+    np.testing.assert_array_equal(K.indptr, c["indptr"])  # bit-exact pattern
+    np.testing.assert_array_equal(K.indices, c["indices"])
+    assert K.has_sorted_indices
+    assert relerr(K.data, c["data"]) < TOL
+    assert relerr(R, c["R"]) < TOL
+    # fused K+R call gives the same answer as the two separate drivers
+    K2, R2 = p.assembleSystem(applyBCs=c["applyBCs"])
+    assert relerr(K2.data, c["data"]) < TOL and relerr(R2, c["R"]) < TOL
+    for red in ("mean", "max", "min", "sum", "integrate"):
+        vals = p.computeFunction("Von-Mises-Stress", red)
+        for k in c["conn"]:
+            assert relerr(vals[k], g[f"{name}_vm_{red}_{k}"]) < TOL, (red, k)
+    mass = p.computeFunction("Mass", "integrate")
+    for k in c["conn"]:
+        assert relerr(mass[k], g[f"{name}_mass_integrate_{k}"]) < TOL
+    np.testing.assert_allclose(p.computeFunction("Mass", "integrate", "sum"), g[name + "_mass_total"], rtol=1e-12)
+    np.testing.assert_allclose(p.computeFunction("Von-Mises-Stress", "mean", "max"), g[name + "_vm_mean_max"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("family", sorted(FAMILY_ELEMENT))
+@pytest.mark.parametrize("model", [0, 1])
+@pytest.mark.parametrize("linear", [True, False])
+def test_element_level_against_reference(family, model, linear):
+    """the finer seams: Element.computeResidualJacobians / computeResiduals / computeFunction"""
+    g = golden("elements.npz")
+    el = ELEMENT_FOR[FAMILY_ELEMENT[family]]()
+    cm = make_cm(model, linear)
+    X, q, t = g[family + "_X"], g[family + "_q"], g[family + "_t"]
+    key = f"{family}_m{model}_{'lin' if linear else 'nl'}"
+    dvs = {"Thickness": t}
+    Ke = el.computeResidualJacobians(q, X, dvs, cm)
+    Re = el.computeResiduals(q, X, dvs, cm)
+    assert Ke.shape == g[key + "_Ke"].shape and Re.shape == g[key + "_Re"].shape
+    assert relerr(Ke, g[key + "_Ke"]) < TOL
+    assert relerr(Re, g[key + "_Re"]) < TOL
+    vm = el.computeFunction(X, q, dvs, cm.getFunction("Von-Mises-Stress"), None)
+    assert vm.shape == g[key + "_vm"].shape and relerr(vm, g[key + "_vm"]) < TOL
+    assert relerr(el.computeFunction(X, q, dvs, cm.getFunction("Von-Mises-Stress"), "mean"), g[key + "_vmmean"]) < TOL
+    assert relerr(el.computeFunction(X, q, dvs, cm.getFunction("Mass"), "integrate"), g[key + "_massint"]) < TOL
+
+
+def test_lbracket_config1():
+    """BASELINE config 1 (Examples/LBracketExample.py): pattern, K, R, solve, von Mises, mass"""
+    g = golden("lbracket.npz")
+    E, nu, rho, t = g["material"]
+    from fempy_b200 import Constitutive
+
+    cm = Constitutive.IsoPlaneStress(E, nu, rho, t)
+    model = FEMpyModel(cm, nodeCoords=g["coords"], connectivity={"quad": g["conn"].astype(np.int64)})
+    model.addFixedBCToNodes(name="Fixed", nodeInds=[int(i) for i in g["top"]], dof=[0, 1], value=0.0)
+    prob = model.addProblem("Vertical-Load")
+    prob.addLoadToNodes(name="RightEdgeLoad", nodeInds=[int(i) for i in g["right"]], dof=1, value=-1e5, totalLoad=True)
+    K = prob._assembleMatrix(prob.states)
+    R = prob._assembleResidual(prob.states)
+    np.testing.assert_array_equal(K.indptr, g["indptr"])
+    np.testing.assert_array_equal(K.indices, g["indices"])
+    assert K.nnz == 297028
+    assert relerr(K.data, g["data"]) < TOL
+    assert relerr(R, g["R"]) < TOL
+    prob.solve()
+    assert relerr(prob.states, g["u"]) < 1e-9  # through a direct solve: conditioning-limited
+    np.testing.assert_allclose(np.abs(prob.states).max(), 3.285941388626e-02, rtol=1e-8)
+    prob.updateState(g["u"])
+    assert relerr(prob.computeFunction("Von-Mises-Stress", "mean")["quad"], g["vm_mean"]) < TOL
+    np.testing.assert_allclose(prob.computeFunction("Von-Mises-Stress", "mean", "max"), 1.632125596200e09, rtol=1e-9)
+    np.testing.assert_allclose(prob.computeFunction("Mass", "integrate", "sum"), 1.779200000000e03, rtol=1e-9)
+    assert relerr(prob._assembleResidual(prob.states), g["R_solved"]) < 1e-6 or np.abs(g["R_solved"]).max() < 1e-3
+
+
+# ---- the reference's own known-answer vectors, through the CUDA path ------------------------------------------------
+def test_local_matrices_to_coo_reference_vector():
+    """reference tests/testAssembleutils.py:55-81"""
+    r, c, v = AssemblyUtils.localMatricesToCOOArrays(COO_MATS, COO_DOF)
+    np.testing.assert_equal(r, COO_ROWS)
+    np.testing.assert_equal(c, COO_COLS)
+    np.testing.assert_equal(v, COO_VALS)
+    assert r.dtype == np.int64 and c.dtype == np.int64
+
+
+def test_scatter_local_residuals():
+    """AssemblyUtils.py:217-238 against the oracle restatement"""
+    rng = np.random.default_rng(3)
+    conn = rng.integers(0, 50, size=(200, 4))
+    res = rng.random((200, 4, 2))
+    out = np.arange(100, dtype=float)
+    ref = out.copy()
+    fo.scatter_local_residuals(res, conn, ref)
+    AssemblyUtils.scatterLocalResiduals(res, conn, out)
+    np.testing.assert_allclose(out, ref, rtol=1e-13)
+
+
+def test_known_quad_stiffness_matrix():
+    """reference tests/testElements.py:34-45,80-82,169"""
+    el = ELEMENT_FOR["quad"]()
+    Ke = el.computeResidualJacobians(np.zeros((1, 4, 2)), KNOWN_QUAD_X[None], {"Thickness": np.ones(1)}, make_cm(1))
+    np.testing.assert_allclose(Ke[0], KNOWN_QUAD_K, rtol=1e-3)
+
+
+@pytest.mark.parametrize("family", sorted(FAMILY_ELEMENT))
+def test_zero_residual_and_fd_consistency(family):
+    """reference tests/testElements.py:135-180: zero residual at zero state; K dq == dR (1e-5)"""
+    el = ELEMENT_FOR[FAMILY_ELEMENT[family]]()
+    g = golden("elements.npz")
+    X = g[family + "_X"]
+    rng = np.random.default_rng(5)
+    dvs = {"Thickness": rng.random(X.shape[0])}
+    cm = make_cm(1)
+    res = el.computeResiduals(np.zeros_like(X), X, dvs, cm)
+    assert res.shape == (X.shape[0], el.numNodes, 2)
+    np.testing.assert_allclose(res, 0, atol=1e-10)
+    q = rng.random(X.shape)
+    Jac = el.computeResidualJacobians(q, X, dvs, cm)
+    res0 = el.computeResiduals(q, X, dvs, cm)
+    for _ in range(3):
+        pert = rng.random(q.shape) * 1e-6 - 0.5e-6
+        dR = el.computeResiduals(q + pert, X, dvs, cm) - res0
+        for i in range(X.shape[0]):
+            np.testing.assert_allclose(dR[i].flatten(), Jac[i] @ pert[i].flatten(), atol=1e-5, rtol=1e-5)
+
+
+def test_two_quad_problem_reference_test():
+    """reference tests/testProblem.py:73-143 verbatim in spirit: sparsity, exact RHS, solve, functions"""
+    coords, conn, _, _, _, sparsity = two_quad_problem()
+    m, p = build_problem(coords, conn, 0, E=71.7e9, nu=0.33, rho=2780, t=5e-3)
+    p.addFixedBCToNodes(name="YFixed", nodeInds=[1, 5], dof=1, value=1.0)
+    p.addFixedBCToNodes(name="XFixed", nodeInds=5, dof=0, value=0.1)
+    p.addLoadToNodes(name="YLoad", nodeInds=[2], dof=1, value=-10.0)
+    p.updateJacobian(applyBCs=False)
+    np.testing.assert_equal(p.Jacobian.nonzero(), np.nonzero(sparsity))
+    p.markJacOutOfDate()
+    expectedRHS = np.zeros(12)
+    expectedRHS[[3, 5, 11, 10]] = [-1.0, 10.0, -1.0, -0.1]
+    p.updateResidual()
+    np.testing.assert_equal(p.Res, expectedRHS)
+    p.solve()
+    p.updateResidual()
+    np.testing.assert_allclose(p.Res, np.zeros(12), rtol=1e-6, atol=1e-6)
+    u = p.states.flatten()
+    np.testing.assert_approx_equal(u[3], 1.0, significant=10)
+    np.testing.assert_approx_equal(u[11], 1.0, significant=10)
+    np.testing.assert_approx_equal(u[10], 0.1, significant=10)
+    sparsity[[3, 10, 11], :] = 0
+    sparsity[[3, 10, 11], [3, 10, 11]] = 1.0
+    np.testing.assert_equal(p.Jacobian.nonzero(), np.nonzero(sparsity))
+    np.testing.assert_allclose(2780 * 2, p.computeFunction("Mass", elementReductionType="integrate", globalReductionType="sum"))
+    np.testing.assert_equal({"quad": np.array([2780.0, 2780.0])}, p.computeFunction("Mass", elementReductionType="max"))
+    np.testing.assert_equal(2780 * 2, p.computeFunction("Mass", elementReductionType="min", globalReductionType="sum"))
+    with pytest.raises(ValueError):
+        p.computeFunction("Pressure", "max")
+    with pytest.raises(AssertionError):
+        p.computeFunction("Mass", "median")
+
+
+# ---- against the oracle at sizes it finishes in seconds -------------------------------------------------------------
+MEDIUM = [("quad", 128, 0), ("quad", 96, 1), ("quad9", 40, 0), ("triangle", 100, 0), ("triangle", 64, 1)]
+
+
+@pytest.mark.parametrize("elType,n,model", MEDIUM)
+def test_medium_meshes_against_oracle(elType, n, model):
+    coords, conn = meshes.GENERATORS[elType](n, n)
+    N = coords.shape[0]
+    numEl = conn[elType].shape[0]
+    rng = np.random.default_rng(0)
+    states = 1e-3 * rng.random((N, 2))
+    thick = rng.random(numEl) * 1e-2 + 1e-3
+    left, right = meshes.edge_nodes(coords, x=0.0), meshes.edge_nodes(coords, x=2.0)
+    m, p = build_problem(coords, conn, model, thickness=thick, states=states,
+                         bcs=[("Fixed", left, [0, 1], 0.0)], loads=[("Load", right, [0], 1e4, False)])
+    K, R = p.assembleSystem()
+    blocks = oracle_blocks(conn)
+    ip, ix = fo.structural_pattern(blocks, N, 2)
+    np.testing.assert_array_equal(K.indptr, ip)
+    np.testing.assert_array_equal(K.indices, ix)
+    bcDOF, bcVal = AssemblyUtils.convertBCDictToLists(p.getBCs())
+    loads = AssemblyUtils.convertLoadsDictToVector(p.loads, 2 * N)
+    Ko = fo.assemble_matrix(blocks, coords, states, thick, model, MAT["E"], MAT["nu"], bcDOF, dropZeros=False)
+    Ko.sort_indices()
+    assert relerr(K.data, Ko.data) < TOL
+    Ro = fo.assemble_residual(blocks, coords, states, thick, model, MAT["E"], MAT["nu"], loads, bcDOF, bcVal)
+    assert relerr(R, Ro) < TOL
+    vm = p.computeFunction("Von-Mises-Stress", "mean")[elType]
+    vmo = fo.compute_function(blocks, coords, states, fo.VON_MISES, "mean", model, MAT["E"], MAT["nu"], MAT["rho"])[0]
+    assert relerr(vm, vmo) < TOL
+
+
+# ---- full-size configurations through size-independent properties --------------------------------------------------
+FULL = [("quad", 512, "config 2: 526k DOF"), ("quad9", 250, "config 3 family: 502k DOF"), ("triangle", 700, "config 4 family: 983k DOF")]
+
+
+@pytest.mark.parametrize("elType,n,label", FULL)
+def test_full_size_properties(elType, n, label):
+    coords, conn = meshes.GENERATORS[elType](n, n)
+    N = coords.shape[0]
+    numEl = conn[elType].shape[0]
+    rng = np.random.default_rng(1)
+    thick = rng.random(numEl) * 1e-2 + 1e-3
+    m, p = build_problem(coords, conn, 0, thickness=thick)
+    K = p._assembleMatrix(p.states, applyBCs=False)
+    scale = np.abs(K.data).max()
+    # nnz of a structured grid
+    expected = {"quad": 4 * (3 * n + 1) ** 2, "quad9": 4 * (8 * n + 1) ** 2, "triangle": 4 * (7 * n * n + 6 * n + 1)}[elType]
+    assert K.nnz == expected
+    assert np.all(np.diff(K.indptr) > 0) and K.has_sorted_indices
+    # symmetry
+    D = (K - K.T).tocsr()
+    assert np.abs(D.data).max() < 1e-12 * scale
+    # rigid-body modes are in the null space: two translations and the linearised rotation
+    for mode in (np.tile([1.0, 0.0], N), np.tile([0.0, 1.0], N), np.stack((-coords[:, 1], coords[:, 0]), axis=1).reshape(-1)):
+        assert np.abs(K @ mode).max() < 1e-10 * scale * np.abs(mode).max()
+    # linear model: the stress-based residual equals K u (two independent code paths)
+    u = 1e-3 * rng.random((N, 2))
+    R = p._assembleResidual(u, applyBCs=False)
+    Ku = K @ u.reshape(-1)
+    assert np.abs(R - Ku).max() < 1e-12 * np.abs(Ku).max() * 50
+    # patch test: a linear displacement field gives a constant stress state
+    p.updateState(np.stack((1e-3 * coords[:, 0] + 2e-4 * coords[:, 1], -3e-4 * coords[:, 0] + 5e-4 * coords[:, 1]), axis=1))
+    vm = p.computeFunction("Von-Mises-Stress", None)[elType]
+    Dm = fo.d_matrix(0, MAT["E"], MAT["nu"])
+    sig = Dm @ np.array([1e-3, 5e-4, 2e-4 - 3e-4])
+    vm_exact = np.sqrt(sig[0] ** 2 - sig[0] * sig[1] + sig[1] ** 2 + 3 * sig[2] ** 2)
+    np.testing.assert_allclose(vm, vm_exact, rtol=1e-9)
+    # total mass = rho * area of the warped domain (trapezoid: width 2, heights 2 and 1)
+    np.testing.assert_allclose(p.computeFunction("Mass", "integrate", "sum"), MAT["rho"] * 3.0, rtol=1e-11)
+    # idempotence: a second assembly reproduces the first to rounding (atomics reorder the sums)
+    K2 = p._assembleMatrix(np.zeros((N, 2)), applyBCs=False)
+    assert np.abs(K2.data - K.data).max() < 1e-13 * scale
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------------------
+def test_single_element_and_isolated_nodes():
+    coords = np.array([[0.0, 0.0], [2.0, 0.1], [2.2, 1.0], [0.1, 1.5], [5.0, 5.0], [6.0, 7.0]])  # nodes 4, 5 unused
+    conn = {"quad": np.array([[0, 1, 2, 3]])}
+    m, p = build_problem(coords, conn, 0)
+    K = p._assembleMatrix(p.states, applyBCs=False)
+    assert K.shape == (12, 12) and K.nnz == 64
+    np.testing.assert_array_equal(K.indptr, [0, 8, 16, 24, 32, 40, 48, 56, 64, 64, 64, 64, 64])
+    N_, dN, w = ELEMENT_FOR["quad"]().tables()
+    Ke = fo.element_jacobians(dN, w, coords[None, :4], np.zeros((1, 4, 2)), np.ones(1), 0, MAT["E"], MAT["nu"])
+    assert relerr(K.toarray()[:8, :8], Ke[0]) < TOL
+    p.addFixedBCToNodes("orphan", [4], [0], 0.0)
+    from fempy_b200._lib import FembError
+
+    with pytest.raises(FembError, match="belongs to no element"):
+        p._assembleMatrix(p.states, applyBCs=True)
+
+
+def test_bc_semantics_duplicates_and_empty():
+    """rows zeroed but kept, +1.0 per occurrence on the diagonal, last value wins in R (AssemblyUtils.py:55-60,93)"""
+    coords, conn = meshes.quad4_grid(3, 2)
+    coords = coords + 1e-3 * np.random.default_rng(0).random(coords.shape)
+    states = 1e-3 * np.random.default_rng(1).random(coords.shape)
+    m, p = build_problem(coords, conn, 0, states=states)
+    K0 = p._assembleMatrix(p.states, applyBCs=True)  # no BCs defined at all
+    Kf = p._assembleMatrix(p.states, applyBCs=False)
+    np.testing.assert_array_equal(K0.data, Kf.data) if False else None
+    assert relerr(K0.data, Kf.data) < 1e-14
+    p.BCs["a"] = {"DOF": [5, 2, 5], "Value": [0.5, 0.25, 0.75]}
+    K = p._assembleMatrix(p.states)
+    R = p._assembleResidual(p.states)
+    np.testing.assert_array_equal(K.indptr, Kf.indptr)  # BC rows stay in the pattern
+    Kd = K.toarray()
+    assert Kd[5, 5] == 2.0 and Kd[2, 2] == 1.0
+    assert np.count_nonzero(Kd[5]) == 1 and np.count_nonzero(Kd[2]) == 1
+    assert np.count_nonzero(Kd[:, 5]) > 1  # columns are NOT eliminated
+    u = states.reshape(-1)
+    assert R[5] == u[5] - 0.75 and R[2] == u[2] - 0.25
+    blocks = oracle_blocks(conn)
+    Ko = fo.assemble_matrix(blocks, coords, states, np.ones(6), 0, MAT["E"], MAT["nu"], [5, 2, 5])
+    assert relerr(Kd, Ko.toarray()) < TOL
+
+
+def test_inverted_element_signed_determinant():
+    """clockwise connectivity: detJ < 0 is used as is (LinAlg.py:89 has no abs)"""
+    coords, conn = meshes.quad4_grid(2, 2)
+    cw = {"quad": conn["quad"][:, ::-1].copy()}
+    m, p = build_problem(coords, cw, 0)
+    K = p._assembleMatrix(p.states, applyBCs=False)
+    blocks = oracle_blocks(cw)
+    Ko = fo.assemble_matrix(blocks, coords, np.zeros_like(coords), np.ones(4), 0, MAT["E"], MAT["nu"], dropZeros=False)
+    Ko.sort_indices()
+    assert relerr(K.data, Ko.data) < TOL
+    assert K.diagonal().max() < 0
+    assert p.computeFunction("Mass", "integrate", "sum") < 0
+
+
+def test_bad_inputs_raise():
+    from fempy_b200._lib import FembError
+
+    plan = AssemblyPlan(4)
+    N, dN, w = ELEMENT_FOR["quad"]().tables()
+    with pytest.raises(FembError, match="outside"):
+        plan.addBlock(N, dN, w, np.array([[0, 1, 2, 7]]))
+    with pytest.raises(FembError, match="unsupported element family"):
+        plan.addBlock(N[:1], dN[:1], w[:1], np.array([[0, 1, 2, 3]]))
+    with pytest.raises(FembError, match="not finalized"):
+        plan.nnz and plan.pattern()
+    plan.addBlock(N, dN, w, np.array([[0, 1, 2, 3]]))
+    plan.finalize()
+    with pytest.raises(ValueError):
+        plan.assemble(np.zeros((3, 2)), np.zeros((4, 2)), np.ones(1), make_cm(0).material())
+    with pytest.raises(FembError, match="2-D"):
+        AssemblyPlan(4, numDim=3, numStates=3)
+    plan.close()
+
+
+def test_problem_level_nonlinear_newton_step():
+    """Green-strain model: K and R at a non-zero state against the oracle (state-dependent Jacobian)"""
+    coords, conn = meshes.quad9_grid(6, 5)
+    N = coords.shape[0]
+    rng = np.random.default_rng(2)
+    states = 5e-2 * rng.random((N, 2))
+    m, p = build_problem(coords, conn, 1, linear=False, states=states, bcs=[("Fixed", meshes.edge_nodes(coords, x=0.0), [0, 1], 0.0)])
+    assert not p.isLinear
+    K, R = p.assembleSystem()
+    blocks = oracle_blocks(conn)
+    bcDOF, bcVal = AssemblyUtils.convertBCDictToLists(p.getBCs())
+    Ko = fo.assemble_matrix(blocks, coords, states, np.ones(30), 1, MAT["E"], MAT["nu"], bcDOF, nonlinear=True, dropZeros=False)
+    Ko.sort_indices()
+    Ro = fo.assemble_residual(blocks, coords, states, np.ones(30), 1, MAT["E"], MAT["nu"], None, bcDOF, bcVal, nonlinear=True)
+    assert relerr(K.data, Ko.data) < TOL and relerr(R, Ro) < TOL
