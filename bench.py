@@ -190,13 +190,18 @@ def run_ours(args, rank, world, local_rank):
     plan = AssemblyPlan(wl["numNodes"], 2, 2, device=local_rank)
     N_, dN, w = el.tables()
     t0 = time.perf_counter()
+    plan.setLocalityHint(wl["coords"])
+    if args.patch_nodes:
+        plan.setOption("patch_nodes", args.patch_nodes)
     plan.addBlock(N_, dN, w, wl["conn"][elType])
     plan.finalize()
     plan_wall_ms = 1e3 * (time.perf_counter() - t0)
+    plan.setOption("use_patches", 0 if args.scatter else 1)
     plan.setBCs(wl["bcDOF"], wl["bcVal"])
     nnz, numDOF, numEl = plan.nnz, plan.numDOF, plan.numElements
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     plan.setStream(stream.cuda_stream)
     d_coords = torch.from_numpy(wl["coords"]).to(dev)
     d_states = torch.from_numpy(wl["states"]).to(dev)
@@ -240,7 +245,7 @@ def run_ours(args, rank, world, local_rank):
     kernel_ms = kernel_ms_sum / max(kernel_calls, 1)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "assembly kernel (fused K_e/R_e evaluation + scatter)", "kernel_ms": kernel_ms,
+                "traffic": None, "kernel": "k_assemble_patch (fused K_e/R_e evaluation + write-once gather, BCs, loads)" if plan.info("patch_path") else "k_assemble_sym (fused K_e/R_e evaluation + RED.F64 scatter)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_element": alg_bytes / numEl,
                 "peak_source": peak_src, "step_frac_of_roofline": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
 
@@ -276,6 +281,9 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step), "clocks": clocks,
         "plan_build": {"device_ms": plan.buildMs, "wall_ms": plan_wall_ms},
+        "path": {"write_once_patches": plan.info("patch_path"), "patch_nodes": plan.info("patch_nodes"), "num_patches": plan.info("num_patches"),
+                 "patch_elems_total": plan.info("patch_elems_total"), "patch_elems_max": plan.info("patch_elems_max"),
+                 "patch_sources_total": plan.info("patch_sources_total")},
     }  # fmt: skip
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(wl)
@@ -292,6 +300,8 @@ def main():
     ap.add_argument("--config-multi", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--nx", type=int, default=None, help="override the mesh size (exploration only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--patch-nodes", type=int, default=0, help="owned nodes per patch (0 = library default)")
+    ap.add_argument("--scatter", action="store_true", help="use the slot-map scatter kernels (FP64 atomics) instead of patches")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -6,12 +6,12 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libfemb200.so")
-SOURCES = ["femb200.cu"]
-HEADERS = ["elem_math.cuh", os.path.join("..", "..", "include", "femb200.h")]
+SOURCES = ["common.cu", "plan.cu", "plan_patch.cu", "assemble.cu", "functions.cu"]
+HEADERS = ["elem_math.cuh", "femb_internal.h", os.path.join("..", "..", "include", "femb200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+    "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
 ]  # fmt: skip
 
 
@@ -33,14 +33,37 @@ def build(force=False, verbose=False):
     """Build fempy_b200/csrc/libfemb200.so if missing or older than its sources."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    nvcc = find_nvcc()
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headerTime = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        srcPath = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(srcPath), headerTime):
+            return obj, ""
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas=-v"] if verbose else []) + ["-c", "-o", obj, srcPath]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+        with open(os.path.join(objdir, "ptxas.log"), "w") as f:
+            f.write("\n".join(log for _, log in results))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + [o for o, _ in results]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 
 if __name__ == "__main__":
-    print(build(force=True))
+    import sys
+
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -32,7 +32,10 @@ _SIGNATURES = {
     "femb_plan_add_block": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, c_double_p, C.c_int64, c_int64_p]),
     "femb_plan_finalize": (C.c_int, [C.c_void_p]),
     "femb_plan_destroy": (None, [C.c_void_p]),
-    "femb_plan_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "femb_plan_set_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "femb_plan_set_locality_hint": (C.c_int, [C.c_void_p, c_double_p]),
+    "femb_plan_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "femb_plan_get_info": (C.c_int64, [C.c_void_p, C.c_char_p]),
     "femb_plan_sync": (C.c_int, [C.c_void_p]),
     "femb_plan_num_dof": (C.c_int64, [C.c_void_p]),
     "femb_plan_num_elems": (C.c_int64, [C.c_void_p]),

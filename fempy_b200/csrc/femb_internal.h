@@ -1,0 +1,227 @@
+// Internal declarations shared by the translation units of libfemb200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../../include/femb200.h"
+#include "elem_math.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------------
+int femb_fail(const char* fmt, ...);
+#define fail femb_fail
+
+#define CUDA_TRY(expr)                                                                                                  \
+    do {                                                                                                                \
+        cudaError_t _e = (expr);                                                                                        \
+        if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define TRY(expr)          \
+    do {                   \
+        int _r = (expr);   \
+        if (_r) return _r; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+static constexpr int MAX_BLOCKS = 8;
+
+// Gather program of one element block over the plan's node patches ("write-once" assembly):
+// a CTA owns a patch of nodes, evaluates every element touching them into shared memory and then
+// sums, for each (owned node, neighbour node) block of the global matrix, its element contributions.
+struct PatchProgram {
+    bool built = false;
+    int maxElems = 0;             // largest patch element count (shared-memory sizing)
+    int64_t totalElems = 0;       // sum over patches (includes elements evaluated by several patches)
+    int64_t totalSources = 0;
+    int* d_pePtr = nullptr;       // (numPatches+1) patch -> range of patch elements
+    int* d_peElem = nullptr;      // block-local element id of each patch element (sorted within a patch)
+    int* d_peConn = nullptr;      // patch-contiguous, node-major connectivity: base nn*pePtr[p], [a*ne + t]
+    int* d_srcBase = nullptr;     // (numPatches+1) patch -> first source
+    uint16_t* d_srcPtr = nullptr; // (nnzNode + numPatches) patch-relative source offsets, one extra per patch
+    uint16_t* d_src = nullptr;    // sources: elemLocal << (blkBits+1) | blk << 1 | transpose
+};
+
+struct BlockData {
+    int nn = 0, nq = 0;
+    int64_t numElems = 0;
+    int64_t elemOffset = 0;   // first global element id
+    int64_t pointOffset = 0;  // first global Gauss point (for FEMB_REDUCE_NONE output)
+    int64_t keOffset = 0, reOffset = 0;
+    std::vector<double> N, dN, w;
+    int* d_conn = nullptr;  // node-major int32: conn[a * E + e]
+    int* d_slot = nullptr;  // [(a*nn + b) * E + e] -> position of (node_a, node_b) in the node-level CSR
+    PatchProgram prog;
+};
+
+struct BlockTable {  // kernel-side view of all blocks (pattern build)
+    int numBlocks;
+    int nn[MAX_BLOCKS];
+    long long numElems[MAX_BLOCKS];
+    long long elemOffset[MAX_BLOCKS];
+    const int* conn[MAX_BLOCKS];
+};
+
+struct femb_plan {
+    int device = 0;
+    int64_t numNodes = 0;
+    int numDim = 2, numStates = 2;
+    std::vector<BlockData> blocks;
+    int64_t numElems = 0, numPoints = 0, keTotal = 0, reTotal = 0;
+    bool finalized = false;
+    int* d_nrowptr = nullptr;  // node-level CSR row pointers (numNodes + 1)
+    int* d_ncols = nullptr;    // node-level CSR column nodes, sorted within a row
+    int64_t nnzNode = 0;
+    int* d_adjPtr = nullptr;   // node -> adjacent elements (global element ids), kept for the patch programs
+    int* d_adj = nullptr;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    float buildMs = 0.f;
+    int64_t launches = 0;
+    // node patches (shared by all blocks)
+    bool patchesBuilt = false;
+    int patchNodes = 0;          // owned nodes per patch
+    int64_t numPatches = 0;
+    double* d_hintCoords = nullptr;  // optional locality hint (node coordinates at plan time)
+    int* d_order = nullptr;      // patch order: owned nodes of patch p = order[p*patchNodes ...]
+    int* d_nbStart = nullptr;    // (numNodes+1) prefix of node degrees in patch order = first node-block of a node
+    uint16_t* d_nbRow = nullptr; // (nnzNode) patch-local owned-node index of each node-block, patch order
+    int usePatch = 1;            // assembly path selection (1: write-once patches where available)
+    // boundary conditions, de-duplicated on the host with the reference's semantics
+    int64_t nBC = 0;
+    int* d_bcDof = nullptr;       // sorted ascending
+    double* d_bcVal = nullptr;    // last value given for the DOF
+    double* d_bcCount = nullptr;  // number of occurrences (diagonal value)
+    unsigned char* d_bcMask = nullptr;  // (numNodes) bit r set when DOF 2*node + r is constrained
+    // scratch for the host-pointer API
+    double *s_coords = nullptr, *s_states = nullptr, *s_thick = nullptr, *s_loads = nullptr, *s_K = nullptr,
+           *s_R = nullptr, *s_out = nullptr;
+    size_t s_outCap = 0;
+    int* d_flag = nullptr;
+    // optional CUDA-event timing of the dominant assembly kernel(s) (bench.py roofline leg)
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;
+    size_t profUsed = 0;
+};
+
+template <typename T>
+static inline int dalloc(T** p, size_t n) {
+    if (*p) return 0;
+    CUDA_TRY(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
+template <typename T>
+static inline void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+static inline int use_device(const femb_plan* p) {
+    CUDA_TRY(cudaSetDevice(p->device));
+    return 0;
+}
+
+static inline int need_final(const femb_plan* p, const char* who) {
+    if (!p) return fail("%s: plan is NULL", who);
+    if (!p->finalized) return fail("%s: plan is not finalized", who);
+    return 0;
+}
+
+// out[0..n) = exclusive prefix sums of in[0..n); out[n] = total.  in and out must not alias.  Synchronises.
+int exclusive_scan(const int* d_in, int* d_out, int64_t n, cudaStream_t st, int64_t& launches);
+
+// patch programs (plan_patch.cu)
+int build_patches(femb_plan* p, int64_t& launches);
+void free_patches(femb_plan* p);
+bool patch_family_supported(int nn, int nq);
+
+// ---------------------------------------------------------------------------------------------
+// kernel argument blocks
+// ---------------------------------------------------------------------------------------------
+struct AsmArgs {
+    long long E;
+    long long elemOffset;
+    const int* conn;
+    const int* slot;
+    const int* nrowptr;
+    const double2* coords;
+    const double2* states;
+    const double* thick;  // indexed by global element id
+    double* K;
+    double* R;
+};
+
+struct FuncArgs {
+    long long E;
+    const int* conn;
+    const double2* coords;
+    const double2* states;
+    double* out;  // E or E*NQ values
+};
+
+// ---------------------------------------------------------------------------------------------
+// element families
+// ---------------------------------------------------------------------------------------------
+template <int NN, int NQ>
+static inline femb::Tables<NN, NQ> make_tables(const BlockData& b) {
+    femb::Tables<NN, NQ> t;
+    for (int p = 0; p < NQ; ++p) {
+        for (int d = 0; d < 2; ++d)
+            for (int a = 0; a < NN; ++a) t.dN[p][d][a] = b.dN[(p * 2 + d) * NN + a];
+        for (int a = 0; a < NN; ++a) t.N[p][a] = b.N[p * NN + a];
+        t.w[p] = b.w[p];
+    }
+    return t;
+}
+
+static inline femb::DMat make_dmat(const femb_material& m) {
+    femb::DMat D;
+    if (m.model == FEMB_PLANE_STRESS) {  // IsoStress.py:25-50
+        const double f = m.E / (1.0 - m.nu * m.nu);
+        D.d00 = f * 1.0;
+        D.d01 = f * m.nu;
+        D.d11 = f * 1.0;
+        D.d22 = f * ((1.0 - m.nu) / 2.0);
+    } else {  // IsoStress.py:53-78
+        const double f = m.E / ((1.0 + m.nu) * (1.0 - 2.0 * m.nu));
+        D.d00 = f * (1.0 - m.nu);
+        D.d01 = f * m.nu;
+        D.d11 = f * (1.0 - m.nu);
+        D.d22 = f * ((1.0 - 2.0 * m.nu) / 2.0);
+    }
+    D.nu = m.nu;
+    D.rho = m.rho;
+    D.model = m.model;
+    D.nonlinear = m.nonlinear;
+    return D;
+}
+
+static inline bool family_supported(int nn, int nq) {
+    return (nn == 3 && nq == 1) || (nn == 6 && nq == 3) || (nn == 10 && nq == 3) || (nn == 4 && nq == 4) ||
+           (nn == 9 && nq == 9) || (nn == 16 && nq == 16);
+}
+
+// body sees constexpr NN, NQ and ROW (row-split kernels for the families that do not fit one thread)
+#define FEMB_DISPATCH_FAMILY(nn, nq, BODY)                                                                                 \
+    do {                                                                                                                   \
+        if ((nn) == 3 && (nq) == 1) { constexpr int NN = 3, NQ = 1; constexpr bool ROW = false; (void)ROW; BODY; }         \
+        else if ((nn) == 4 && (nq) == 4) { constexpr int NN = 4, NQ = 4; constexpr bool ROW = false; (void)ROW; BODY; }    \
+        else if ((nn) == 6 && (nq) == 3) { constexpr int NN = 6, NQ = 3; constexpr bool ROW = true; (void)ROW; BODY; }     \
+        else if ((nn) == 9 && (nq) == 9) { constexpr int NN = 9, NQ = 9; constexpr bool ROW = true; (void)ROW; BODY; }     \
+        else if ((nn) == 10 && (nq) == 3) { constexpr int NN = 10, NQ = 3; constexpr bool ROW = true; (void)ROW; BODY; }   \
+        else if ((nn) == 16 && (nq) == 16) { constexpr int NN = 16, NQ = 16; constexpr bool ROW = true; (void)ROW; BODY; } \
+        else return fail("unsupported element family: %d nodes, %d quadrature points", (nn), (nq));                        \
+    } while (0)

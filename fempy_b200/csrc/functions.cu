@@ -1,0 +1,319 @@
+// Element functions (von Mises, mass), per-element blocks and the AssemblyUtils equivalents.
+#include "femb_internal.h"
+
+using namespace femb;
+
+template <int NN>
+__device__ __forceinline__ void load_element(const AsmArgs& A, long long e, int (&node)[NN], double (&x)[NN],
+                                             double (&y)[NN], double (&ux)[NN], double (&uy)[NN]) {
+#pragma unroll
+    for (int a = 0; a < NN; ++a) node[a] = __ldg(A.conn + (long long)a * A.E + e);
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+        const double2 c = __ldg(A.coords + node[a]);
+        const double2 q = __ldg(A.states + node[a]);
+        x[a] = c.x;
+        y[a] = c.y;
+        ux[a] = q.x;
+        uy[a] = q.y;
+    }
+}
+
+static int stage(double** buf, const double* host, size_t n, cudaStream_t st) {
+    TRY(dalloc(buf, n));
+    CUDA_TRY(cudaMemcpyAsync(*buf, host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+// =============================================================================================
+// element function kernel
+// =============================================================================================
+template <int NN, int NQ, bool NL>
+__global__ void __launch_bounds__(128) k_function(const __grid_constant__ Tables<NN, NQ> tb, const DMat D,
+                                                  const FuncArgs F, const int func, const int reduction) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= F.E) return;
+    double x[NN], y[NN], ux[NN], uy[NN];
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+        const int node = __ldg(F.conn + (long long)a * F.E + e);
+        const double2 c = __ldg(F.coords + node);
+        const double2 q = __ldg(F.states + node);
+        x[a] = c.x;
+        y[a] = c.y;
+        ux[a] = q.x;
+        uy[a] = q.y;
+    }
+    double vals[NQ], dets[NQ];
+    element_function<NN, NQ, NL>(tb, D, func, x, y, ux, uy, vals, dets);
+    if (reduction == FEMB_REDUCE_NONE) {
+#pragma unroll
+        for (int p = 0; p < NQ; ++p) F.out[e * NQ + p] = vals[p];
+        return;
+    }
+    double r = 0.0;
+    if (reduction == FEMB_REDUCE_SUM || reduction == FEMB_REDUCE_MEAN) {
+#pragma unroll
+        for (int p = 0; p < NQ; ++p) r += vals[p];
+        if (reduction == FEMB_REDUCE_MEAN) r /= (double)NQ;
+    } else if (reduction == FEMB_REDUCE_INTEGRATE) {
+#pragma unroll
+        for (int p = 0; p < NQ; ++p) r = fma(vals[p] * dets[p], tb.w[p], r);
+    } else if (reduction == FEMB_REDUCE_MIN) {
+        r = vals[0];
+#pragma unroll
+        for (int p = 1; p < NQ; ++p) r = fmin(r, vals[p]);
+    } else {
+        r = vals[0];
+#pragma unroll
+        for (int p = 1; p < NQ; ++p) r = fmax(r, vals[p]);
+    }
+    F.out[e] = r;
+}
+
+// =============================================================================================
+// per-element blocks (debug / finer seam): Ke (E, 2n, 2n), Re (E, n, 2)
+// =============================================================================================
+template <int NN, int NQ, bool NL>
+__global__ void __launch_bounds__(128) k_element_blocks(const __grid_constant__ Tables<NN, NQ> tb, const DMat D,
+                                                        const AsmArgs A, double* __restrict__ Ke,
+                                                        double* __restrict__ Re) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.y;
+    if (e >= A.E) return;
+    int node[NN];
+    double x[NN], y[NN], ux[NN], uy[NN];
+    load_element<NN>(A, e, node, x, y, ux, uy);
+    const double theta = __ldg(A.thick + A.elemOffset + e);
+    double Krow[NN][4], Ra[2];
+    element_row<NN, NQ, NL, true, true>(tb, D, a, x, y, ux, uy, theta, Krow, Ra);
+    constexpr int ND = 2 * NN;
+    if (Ke) {
+        double* r0 = Ke + (e * ND + 2 * a) * ND;
+#pragma unroll
+        for (int b = 0; b < NN; ++b) {
+            r0[2 * b] = Krow[b][0];
+            r0[2 * b + 1] = Krow[b][1];
+            r0[ND + 2 * b] = Krow[b][2];
+            r0[ND + 2 * b + 1] = Krow[b][3];
+        }
+    }
+    if (Re) {
+        Re[(e * NN + a) * 2] = Ra[0];
+        Re[(e * NN + a) * 2 + 1] = Ra[1];
+    }
+}
+
+// =============================================================================================
+// C ABI: element functions
+// =============================================================================================
+template <int NN, int NQ>
+static void launch_function(const BlockData& b, const DMat& D, const FuncArgs& F, bool nl, int func, int reduction,
+                            cudaStream_t st) {
+    const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
+    if (nl) k_function<NN, NQ, true><<<grid_for(F.E, 128), 128, 0, st>>>(tb, D, F, func, reduction);
+    else k_function<NN, NQ, false><<<grid_for(F.E, 128), 128, 0, st>>>(tb, D, F, func, reduction);
+}
+
+extern "C" int femb_function_dev(femb_plan* p, const double* d_coords, const double* d_states, const femb_material* mat,
+                                 int32_t func, int32_t reduction, double* d_out) {
+    TRY(need_final(p, "femb_function_dev"));
+    if (!mat || !d_coords || !d_states || !d_out) return fail("femb_function_dev: NULL argument");
+    if (func != FEMB_FUNC_MASS && func != FEMB_FUNC_VON_MISES) return fail("femb_function_dev: unknown function id %d", func);
+    if (reduction < FEMB_REDUCE_NONE || reduction > FEMB_REDUCE_MAX)
+        return fail("femb_function_dev: unknown reduction id %d", reduction);
+    TRY(use_device(p));
+    const DMat D = make_dmat(*mat);
+    int64_t launches = 0;
+    for (auto& b : p->blocks) {
+        FuncArgs F;
+        F.E = b.numElems;
+        F.conn = b.d_conn;
+        F.coords = (const double2*)d_coords;
+        F.states = (const double2*)d_states;
+        F.out = d_out + (reduction == FEMB_REDUCE_NONE ? b.pointOffset : b.elemOffset);
+        FEMB_DISPATCH_FAMILY(b.nn, b.nq, (launch_function<NN, NQ>(b, D, F, mat->nonlinear != 0, func, reduction, p->stream)));
+        launches++;
+    }
+    p->launches = launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int femb_function(femb_plan* p, const double* coords, const double* states, const femb_material* mat,
+                             int32_t func, int32_t reduction, double* out) {
+    TRY(need_final(p, "femb_function"));
+    if (!coords || !states || !out) return fail("femb_function: NULL argument");
+    TRY(use_device(p));
+    const int64_t numDOF = femb_plan_num_dof(p);
+    const size_t nout = (size_t)(reduction == FEMB_REDUCE_NONE ? p->numPoints : p->numElems);
+    TRY(stage(&p->s_coords, coords, (size_t)p->numNodes * 2, p->stream));
+    TRY(stage(&p->s_states, states, (size_t)numDOF, p->stream));
+    if (p->s_outCap < nout) {
+        dfree(p->s_out);
+        TRY(dalloc(&p->s_out, nout));
+        p->s_outCap = nout;
+    }
+    TRY(femb_function_dev(p, p->s_coords, p->s_states, mat, func, reduction, p->s_out));
+    CUDA_TRY(cudaMemcpyAsync(out, p->s_out, nout * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// =============================================================================================
+// C ABI: per-element blocks
+// =============================================================================================
+template <int NN, int NQ>
+static void launch_blocks(const BlockData& b, const DMat& D, const AsmArgs& A, bool nl, double* Ke, double* Re,
+                          cudaStream_t st) {
+    const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
+    dim3 grid(grid_for(A.E, 128), NN);
+    if (nl) k_element_blocks<NN, NQ, true><<<grid, 128, 0, st>>>(tb, D, A, Ke, Re);
+    else k_element_blocks<NN, NQ, false><<<grid, 128, 0, st>>>(tb, D, A, Ke, Re);
+}
+
+extern "C" int femb_element_blocks(femb_plan* p, const double* coords, const double* states, const double* thickness,
+                                   const femb_material* mat, double* Ke, double* Re) {
+    TRY(need_final(p, "femb_element_blocks"));
+    if (!coords || !states || !thickness || !mat) return fail("femb_element_blocks: NULL argument");
+    TRY(use_device(p));
+    const int64_t numDOF = femb_plan_num_dof(p);
+    TRY(stage(&p->s_coords, coords, (size_t)p->numNodes * 2, p->stream));
+    TRY(stage(&p->s_states, states, (size_t)numDOF, p->stream));
+    TRY(stage(&p->s_thick, thickness, (size_t)p->numElems, p->stream));
+    double *d_Ke = nullptr, *d_Re = nullptr;
+    if (Ke) CUDA_TRY(cudaMalloc(&d_Ke, p->keTotal * sizeof(double)));
+    if (Re) CUDA_TRY(cudaMalloc(&d_Re, p->reTotal * sizeof(double)));
+    const DMat D = make_dmat(*mat);
+    int64_t launches = 0;
+    for (auto& b : p->blocks) {
+        AsmArgs A;
+        A.E = b.numElems;
+        A.elemOffset = b.elemOffset;
+        A.conn = b.d_conn;
+        A.slot = nullptr;
+        A.nrowptr = nullptr;
+        A.coords = (const double2*)p->s_coords;
+        A.states = (const double2*)p->s_states;
+        A.thick = p->s_thick;
+        A.K = nullptr;
+        A.R = nullptr;
+        FEMB_DISPATCH_FAMILY(b.nn, b.nq, (launch_blocks<NN, NQ>(b, D, A, mat->nonlinear != 0, d_Ke ? d_Ke + b.keOffset : nullptr,
+                                                               d_Re ? d_Re + b.reOffset : nullptr, p->stream)));
+        launches++;
+    }
+    p->launches = launches;
+    int rc = 0;
+    if (Ke && cudaMemcpyAsync(Ke, d_Ke, p->keTotal * sizeof(double), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess) rc = 1;
+    if (Re && cudaMemcpyAsync(Re, d_Re, p->reTotal * sizeof(double), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess) rc = 1;
+    if (cudaStreamSynchronize(p->stream) != cudaSuccess) rc = 1;
+    cudaFree(d_Ke);
+    cudaFree(d_Re);
+    if (rc) return fail("femb_element_blocks: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+// =============================================================================================
+// C ABI: AssemblyUtils equivalents on the device
+// =============================================================================================
+__global__ void k_flag_nonzero(const double* __restrict__ vals, int* __restrict__ flags, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (vals[i] != 0.0) ? 1 : 0;
+}
+
+__global__ void k_coo_compact(const double* __restrict__ vals, const long long* __restrict__ dof, const int* __restrict__ flags,
+                              const int* __restrict__ pos, long long n, int nd, long long* __restrict__ rows,
+                              long long* __restrict__ cols, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    const long long e = i / ((long long)nd * nd);
+    const int rc = (int)(i - e * nd * nd);
+    const int r = rc / nd, c = rc - r * nd;
+    const int q = pos[i];
+    rows[q] = dof[e * nd + r];
+    cols[q] = dof[e * nd + c];
+    out[q] = vals[i];
+}
+
+extern "C" int femb_local_matrices_to_coo(const double* localMats, const int64_t* localDOF, int64_t numElems, int32_t nd,
+                                          int32_t device, int64_t* rows, int64_t* cols, double* vals, int64_t* numOut) {
+    if (!localMats || !localDOF || !rows || !cols || !vals || !numOut) return fail("femb_local_matrices_to_coo: NULL argument");
+    if (femb_device_count() == 0) return fail("femb_local_matrices_to_coo: no CUDA device available");
+    const int64_t n = numElems * (int64_t)nd * nd;
+    if (n >= (1ll << 31)) return fail("femb_local_matrices_to_coo: too many entries");
+    *numOut = 0;
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(device));
+    double *d_vals = nullptr, *d_out = nullptr;
+    long long *d_dof = nullptr, *d_rows = nullptr, *d_cols = nullptr;
+    int *d_flags = nullptr, *d_pos = nullptr;
+    CUDA_TRY(cudaMalloc(&d_vals, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_out, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_dof, numElems * nd * sizeof(long long)));
+    CUDA_TRY(cudaMalloc(&d_rows, n * sizeof(long long)));
+    CUDA_TRY(cudaMalloc(&d_cols, n * sizeof(long long)));
+    CUDA_TRY(cudaMalloc(&d_flags, n * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_pos, (n + 1) * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(d_vals, localMats, n * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_dof, localDOF, numElems * nd * sizeof(long long), cudaMemcpyHostToDevice));
+    int64_t launches = 0;
+    k_flag_nonzero<<<grid_for(n, 256), 256>>>(d_vals, d_flags, n);
+    TRY(exclusive_scan(d_flags, d_pos, n, 0, launches));
+    k_coo_compact<<<grid_for(n, 256), 256>>>(d_vals, d_dof, d_flags, d_pos, n, nd, d_rows, d_cols, d_out);
+    int total = 0;
+    CUDA_TRY(cudaMemcpy(&total, d_pos + n, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(rows, d_rows, total * sizeof(long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(cols, d_cols, total * sizeof(long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(vals, d_out, total * sizeof(double), cudaMemcpyDeviceToHost));
+    *numOut = total;
+    cudaFree(d_vals);
+    cudaFree(d_out);
+    cudaFree(d_dof);
+    cudaFree(d_rows);
+    cudaFree(d_cols);
+    cudaFree(d_flags);
+    cudaFree(d_pos);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_scatter_residuals(const double* __restrict__ localRes, const long long* __restrict__ conn, long long n,
+                                    int s, long long numNodes, double* __restrict__ R, int* flag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over (element, node)
+    if (i >= n) return;
+    const long long node = conn[i];
+    if (node < 0 || node >= numNodes) {
+        atomicExch(flag, 1);
+        return;
+    }
+    for (int st = 0; st < s; ++st) atomicAdd(R + node * s + st, localRes[i * s + st]);
+}
+
+extern "C" int femb_scatter_local_residuals(const double* localRes, const int64_t* conn, int64_t numElems, int32_t nn,
+                                            int32_t numStates, int64_t numNodes, int32_t device, double* globalResidual) {
+    if (!localRes || !conn || !globalResidual) return fail("femb_scatter_local_residuals: NULL argument");
+    if (femb_device_count() == 0) return fail("femb_scatter_local_residuals: no CUDA device available");
+    CUDA_TRY(cudaSetDevice(device));
+    const int64_t n = numElems * nn, nd = numNodes * numStates;
+    double *d_res = nullptr, *d_R = nullptr;
+    long long* d_conn = nullptr;
+    int* d_flag = nullptr;
+    CUDA_TRY(cudaMalloc(&d_res, std::max<int64_t>(n * numStates, 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_R, std::max<int64_t>(nd, 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_conn, std::max<int64_t>(n, 1) * sizeof(long long)));
+    CUDA_TRY(cudaMalloc(&d_flag, sizeof(int)));
+    CUDA_TRY(cudaMemset(d_flag, 0, sizeof(int)));
+    CUDA_TRY(cudaMemcpy(d_res, localRes, n * numStates * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_R, globalResidual, nd * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_conn, conn, n * sizeof(long long), cudaMemcpyHostToDevice));
+    if (n > 0) k_scatter_residuals<<<grid_for(n, 256), 256>>>(d_res, d_conn, n, numStates, numNodes, d_R, d_flag);
+    int flag = 0;
+    CUDA_TRY(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(globalResidual, d_R, nd * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_res);
+    cudaFree(d_R);
+    cudaFree(d_conn);
+    cudaFree(d_flag);
+    if (flag) return fail("femb_scatter_local_residuals: connectivity out of range");
+    return 0;
+}

@@ -1,0 +1,523 @@
+// Plan: mesh topology + element tables -> node adjacency, sorted CSR pattern, scatter map, BC staging.
+#include "femb_internal.h"
+
+using namespace femb;
+
+// =============================================================================================
+// pattern build kernels
+// =============================================================================================
+// int64 row-major (E, nn) connectivity -> node-major int32, with range check
+__global__ void k_convert_conn(const long long* __restrict__ conn64, int* __restrict__ conn32, long long E, int nn,
+                               long long numNodes, int* __restrict__ flag) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= E * nn) return;
+    const long long e = t / nn;
+    const int a = (int)(t - e * nn);
+    const long long node = conn64[t];
+    if (node < 0 || node >= numNodes) {
+        atomicExch(flag, 1);
+        conn32[(long long)a * E + e] = 0;
+        return;
+    }
+    conn32[(long long)a * E + e] = (int)node;
+}
+
+// adjacency counts: number of elements and number of candidate neighbours per node
+__global__ void k_count_adj(const int* __restrict__ conn, long long E, int nn, int* __restrict__ adjCount,
+                            int* __restrict__ candCount) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= E * nn) return;
+    const int node = conn[t];
+    atomicAdd(&adjCount[node], 1);
+    atomicAdd(&candCount[node], nn);
+}
+
+__global__ void k_fill_adj(const int* __restrict__ conn, long long E, int nn, long long elemOffset,
+                           const int* __restrict__ adjPtr, int* __restrict__ cursor, int* __restrict__ adj) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= E * nn) return;
+    const long long e = t % E;
+    const int node = conn[t];
+    const int p = atomicAdd(&cursor[node], 1);
+    adj[adjPtr[node] + p] = (int)(elemOffset + e);
+}
+
+// the atomic fill leaves each node's element list in arbitrary order: sort it (short lists, one thread per node)
+__global__ void k_sort_adj(long long numNodes, const int* __restrict__ adjPtr, int* __restrict__ adj) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numNodes) return;
+    const int lo = adjPtr[i], hi = adjPtr[i + 1];
+    for (int m = lo + 1; m < hi; ++m) {
+        const int v = adj[m];
+        int q = m - 1;
+        while (q >= lo && adj[q] > v) {
+            adj[q + 1] = adj[q];
+            --q;
+        }
+        adj[q + 1] = v;
+    }
+}
+
+// one thread per node: sorted, de-duplicated list of neighbour nodes (itself included) written into
+// its candidate segment; deg[i] = list length.  The adjacency order is non-deterministic (atomics) but
+// the sorted result is not.
+__global__ void k_build_rows(BlockTable bt, long long numNodes, const int* __restrict__ adjPtr,
+                             const int* __restrict__ adj, const int* __restrict__ candPtr, int* __restrict__ cand,
+                             int* __restrict__ deg) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numNodes) return;
+    int* seg = cand + candPtr[i];
+    int count = 0;
+    for (int q = adjPtr[i]; q < adjPtr[i + 1]; ++q) {
+        const long long ge = adj[q];
+        int b = 0;
+        while (b + 1 < bt.numBlocks && ge >= bt.elemOffset[b + 1]) ++b;
+        const long long e = ge - bt.elemOffset[b];
+        const int nn = bt.nn[b];
+        const long long E = bt.numElems[b];
+        const int* conn = bt.conn[b];
+        for (int a = 0; a < nn; ++a) {
+            const int j = conn[(long long)a * E + e];
+            // binary search for the insertion point
+            int lo = 0, hi = count;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (seg[mid] < j) lo = mid + 1; else hi = mid;
+            }
+            if (lo < count && seg[lo] == j) continue;
+            for (int m = count; m > lo; --m) seg[m] = seg[m - 1];
+            seg[lo] = j;
+            ++count;
+        }
+    }
+    deg[i] = count;
+}
+
+__global__ void k_compact_rows(long long numNodes, const int* __restrict__ candPtr, const int* __restrict__ cand,
+                               const int* __restrict__ nrowptr, int* __restrict__ ncols) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numNodes) return;
+    const int* seg = cand + candPtr[i];
+    const int off = nrowptr[i], d = nrowptr[i + 1] - off;
+    for (int k = 0; k < d; ++k) ncols[off + k] = seg[k];
+}
+
+// slot[(a*nn+b)*E + e] = position of (node_a, node_b) in the node-level CSR
+__global__ void k_build_slots(const int* __restrict__ conn, long long E, int nn, const int* __restrict__ nrowptr,
+                              const int* __restrict__ ncols, int* __restrict__ slot) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= E * nn * nn) return;
+    const long long e = t % E;
+    const int ab = (int)(t / E);
+    const int a = ab / nn, b = ab - a * nn;
+    const int i = conn[(long long)a * E + e], j = conn[(long long)b * E + e];
+    int lo = nrowptr[i], hi = nrowptr[i + 1];
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ncols[mid] < j) lo = mid + 1; else hi = mid;
+    }
+    slot[t] = lo;
+}
+
+// DOF-level CSR (int64) from the node-level CSR.  Row s*i + r holds, for every neighbour k of node i,
+// the s columns s*j_k .. s*j_k + s-1; its values start at s*s*off_i + r*s*deg_i.
+__global__ void k_dof_pattern(long long numNodes, int s, const int* __restrict__ nrowptr, const int* __restrict__ ncols,
+                              long long* __restrict__ indptr, long long* __restrict__ indices) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > numNodes) return;
+    if (i == numNodes) {
+        indptr[(long long)s * numNodes] = (long long)s * s * nrowptr[numNodes];
+        return;
+    }
+    const long long off = nrowptr[i], d = nrowptr[i + 1] - off;
+    for (int r = 0; r < s; ++r) {
+        const long long start = (long long)s * s * off + (long long)r * s * d;
+        indptr[(long long)s * i + r] = start;
+        for (long long k = 0; k < d; ++k) {
+            const long long j = ncols[off + k];
+            for (int c = 0; c < s; ++c) indices[start + s * k + c] = (long long)s * j + c;
+        }
+    }
+}
+
+
+__global__ void k_check_bcs(long long nBC, const int* __restrict__ bcDof, const int* __restrict__ nrowptr, int* flag) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nBC) return;
+    const int i = bcDof[t] >> 1;
+    if (nrowptr[i + 1] == nrowptr[i]) atomicExch(flag, 2);
+}
+
+// =============================================================================================
+// C ABI: plan
+// =============================================================================================
+extern "C" int femb_plan_create(int64_t numNodes, int32_t numDim, int32_t numStates, int32_t device, femb_plan** out) {
+    if (!out) return fail("femb_plan_create: out is NULL");
+    *out = nullptr;
+    if (numDim != 2 || numStates != 2)
+        return fail("femb_plan_create: only 2-D models with 2 states per node are supported (got numDim=%d, numStates=%d)",
+                    numDim, numStates);
+    if (numNodes <= 0 || numNodes >= (1ll << 30)) return fail("femb_plan_create: numNodes out of range");
+    int ndev = femb_device_count();
+    if (ndev == 0) return fail("femb_plan_create: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("femb_plan_create: device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    femb_plan* p = new femb_plan();
+    p->device = device;
+    p->numNodes = numNodes;
+    p->numDim = numDim;
+    p->numStates = numStates;
+    if (cudaStreamCreateWithFlags(&p->ownStream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete p;
+        return fail("femb_plan_create: cudaStreamCreate failed");
+    }
+    p->stream = p->ownStream;
+    if (dalloc(&p->d_flag, 1)) {
+        delete p;
+        return 1;
+    }
+    *out = p;
+    return 0;
+}
+
+extern "C" int femb_plan_add_block(femb_plan* p, int32_t nn, int32_t nq, const double* N, const double* dNdxi,
+                                   const double* w, int64_t numElems, const int64_t* conn) {
+    if (!p) return fail("femb_plan_add_block: plan is NULL");
+    if (p->finalized) return fail("femb_plan_add_block: plan already finalized");
+    if ((int)p->blocks.size() >= MAX_BLOCKS) return fail("femb_plan_add_block: at most %d element types", MAX_BLOCKS);
+    if (!family_supported(nn, nq))
+        return fail("femb_plan_add_block: unsupported element family (%d nodes, %d quadrature points)", nn, nq);
+    if (numElems <= 0 || !conn || !N || !dNdxi || !w) return fail("femb_plan_add_block: bad arguments");
+    if (numElems * (int64_t)nn * nn >= (1ll << 31)) return fail("femb_plan_add_block: block too large for int32 slot map");
+    TRY(use_device(p));
+    BlockData b;
+    b.nn = nn;
+    b.nq = nq;
+    b.numElems = numElems;
+    b.elemOffset = p->numElems;
+    b.pointOffset = p->numPoints;
+    b.keOffset = p->keTotal;
+    b.reOffset = p->reTotal;
+    b.N.assign(N, N + (size_t)nq * nn);
+    b.dN.assign(dNdxi, dNdxi + (size_t)nq * 2 * nn);
+    b.w.assign(w, w + nq);
+    long long* d_conn64 = nullptr;
+    const size_t cnt = (size_t)numElems * nn;
+    CUDA_TRY(cudaMalloc(&d_conn64, cnt * sizeof(long long)));
+    CUDA_TRY(cudaMalloc(&b.d_conn, cnt * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(d_conn64, conn, cnt * sizeof(long long), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
+    k_convert_conn<<<grid_for((int64_t)cnt, 256), 256, 0, p->stream>>>(d_conn64, b.d_conn, numElems, nn, p->numNodes,
+                                                                        p->d_flag);
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    cudaFree(d_conn64);
+    if (flag) {
+        cudaFree(b.d_conn);
+        return fail("femb_plan_add_block: connectivity refers to a node outside [0, %lld)", (long long)p->numNodes);
+    }
+    p->numElems += numElems;
+    p->numPoints += numElems * nq;
+    p->keTotal += numElems * (int64_t)(2 * nn) * (2 * nn);
+    p->reTotal += numElems * (int64_t)nn * 2;
+    p->blocks.push_back(std::move(b));
+    return 0;
+}
+
+extern "C" int femb_plan_finalize(femb_plan* p) {
+    if (!p) return fail("femb_plan_finalize: plan is NULL");
+    if (p->finalized) return 0;
+    if (p->blocks.empty()) return fail("femb_plan_finalize: no element blocks");
+    TRY(use_device(p));
+    cudaStream_t st = p->stream;
+    cudaEvent_t ev0, ev1;
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    CUDA_TRY(cudaEventRecord(ev0, st));
+    const int64_t N = p->numNodes;
+    int64_t launches = 0;
+    int *d_adjCount = nullptr, *d_candCount = nullptr, *d_candPtr = nullptr, *d_cursor = nullptr;
+    int *d_cand = nullptr, *d_deg = nullptr;
+    int*& d_adjPtr = p->d_adjPtr;  // kept: the patch programs walk the node -> element adjacency
+    int*& d_adj = p->d_adj;
+    CUDA_TRY(cudaMalloc(&d_adjCount, (N + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_candCount, (N + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_adjPtr, (N + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_candPtr, (N + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_cursor, (N + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_deg, (N + 1) * sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(d_adjCount, 0, (N + 1) * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(d_candCount, 0, (N + 1) * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(d_cursor, 0, (N + 1) * sizeof(int), st));
+    int64_t totalAdj = 0, totalCand = 0;
+    for (auto& b : p->blocks) {
+        k_count_adj<<<grid_for(b.numElems * b.nn, 256), 256, 0, st>>>(b.d_conn, b.numElems, b.nn, d_adjCount, d_candCount);
+        launches++;
+        totalAdj += b.numElems * b.nn;
+        totalCand += b.numElems * (int64_t)b.nn * b.nn;
+    }
+    if (totalCand >= (1ll << 31)) return fail("femb_plan_finalize: mesh too large for int32 candidate offsets");
+    TRY(exclusive_scan(d_adjCount, d_adjPtr, N, st, launches));
+    TRY(exclusive_scan(d_candCount, d_candPtr, N, st, launches));
+    CUDA_TRY(cudaMalloc(&d_adj, std::max<int64_t>(totalAdj, 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_cand, std::max<int64_t>(totalCand, 1) * sizeof(int)));
+    BlockTable bt;
+    bt.numBlocks = (int)p->blocks.size();
+    for (int i = 0; i < bt.numBlocks; ++i) {
+        auto& b = p->blocks[i];
+        bt.nn[i] = b.nn;
+        bt.numElems[i] = b.numElems;
+        bt.elemOffset[i] = b.elemOffset;
+        bt.conn[i] = b.d_conn;
+        k_fill_adj<<<grid_for(b.numElems * b.nn, 256), 256, 0, st>>>(b.d_conn, b.numElems, b.nn, b.elemOffset, d_adjPtr,
+                                                                     d_cursor, d_adj);
+        launches++;
+    }
+    k_sort_adj<<<grid_for(N, 128), 128, 0, st>>>(N, d_adjPtr, d_adj);
+    launches++;
+    k_build_rows<<<grid_for(N, 128), 128, 0, st>>>(bt, N, d_adjPtr, d_adj, d_candPtr, d_cand, d_deg);
+    launches++;
+    CUDA_TRY(cudaMalloc(&p->d_nrowptr, (N + 1) * sizeof(int)));
+    TRY(exclusive_scan(d_deg, p->d_nrowptr, N, st, launches));
+    int nnzNode = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nnzNode, p->d_nrowptr + N, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    p->nnzNode = nnzNode;
+    CUDA_TRY(cudaMalloc(&p->d_ncols, std::max<int64_t>(nnzNode, 1) * sizeof(int)));
+    k_compact_rows<<<grid_for(N, 128), 128, 0, st>>>(N, d_candPtr, d_cand, p->d_nrowptr, p->d_ncols);
+    launches++;
+    for (auto& b : p->blocks) {
+        const int64_t cnt = b.numElems * (int64_t)b.nn * b.nn;
+        CUDA_TRY(cudaMalloc(&b.d_slot, cnt * sizeof(int)));
+        k_build_slots<<<grid_for(cnt, 256), 256, 0, st>>>(b.d_conn, b.numElems, b.nn, p->d_nrowptr, p->d_ncols, b.d_slot);
+        launches++;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    cudaFree(d_cand);  // the largest temporary: release it before the patch programs allocate theirs
+    d_cand = nullptr;
+    TRY(build_patches(p, launches));
+    CUDA_TRY(cudaEventRecord(ev1, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&p->buildMs, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    cudaFree(d_adjCount);
+    cudaFree(d_candCount);
+    cudaFree(d_candPtr);
+    cudaFree(d_cursor);
+    cudaFree(d_cand);
+    cudaFree(d_deg);
+    p->launches = launches;
+    p->finalized = true;
+    return 0;
+}
+
+extern "C" void femb_plan_destroy(femb_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->ownStream) cudaStreamSynchronize(p->ownStream);
+    for (auto& b : p->blocks) {
+        dfree(b.d_conn);
+        dfree(b.d_slot);
+    }
+    dfree(p->d_nrowptr);
+    dfree(p->d_ncols);
+    dfree(p->d_adjPtr);
+    dfree(p->d_adj);
+    dfree(p->d_hintCoords);
+    dfree(p->d_bcMask);
+    free_patches(p);
+    dfree(p->d_bcDof);
+    dfree(p->d_bcVal);
+    dfree(p->d_bcCount);
+    dfree(p->s_coords);
+    dfree(p->s_states);
+    dfree(p->s_thick);
+    dfree(p->s_loads);
+    dfree(p->s_K);
+    dfree(p->s_R);
+    dfree(p->s_out);
+    dfree(p->d_flag);
+    for (auto& e : p->profEvents) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    if (p->ownStream) cudaStreamDestroy(p->ownStream);
+    delete p;
+}
+
+extern "C" int femb_plan_set_stream(femb_plan* p, void* cudaStream, int32_t external) {
+    if (!p) return fail("femb_plan_set_stream: plan is NULL");
+    p->stream = external ? (cudaStream_t)cudaStream : p->ownStream;  // external NULL = the legacy default stream
+    return 0;
+}
+
+extern "C" int femb_plan_set_locality_hint(femb_plan* p, const double* coords) {
+    if (!p) return fail("femb_plan_set_locality_hint: plan is NULL");
+    if (p->finalized) return fail("femb_plan_set_locality_hint: plan already finalized");
+    TRY(use_device(p));
+    dfree(p->d_hintCoords);
+    if (!coords) return 0;
+    const size_t n = (size_t)p->numNodes * p->numDim;
+    CUDA_TRY(cudaMalloc(&p->d_hintCoords, n * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(p->d_hintCoords, coords, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t value) {
+    if (!p || !name) return fail("femb_plan_set_option: NULL argument");
+    if (!strcmp(name, "patch_nodes")) {
+        if (p->finalized) return fail("femb_plan_set_option: patch_nodes must be set before finalize");
+        if (value < 0 || value > 1024) return fail("femb_plan_set_option: patch_nodes out of range");
+        p->patchNodes = (int)value;
+    } else if (!strcmp(name, "use_patches")) {
+        p->usePatch = value != 0;
+    } else {
+        return fail("femb_plan_set_option: unknown option %s", name);
+    }
+    return 0;
+}
+
+extern "C" int64_t femb_plan_get_info(const femb_plan* p, const char* name) {
+    if (!p || !name) return -1;
+    if (!strcmp(name, "num_patches")) return p->numPatches;
+    if (!strcmp(name, "patch_nodes")) return p->patchNodes;
+    if (!strcmp(name, "patch_elems_total")) {
+        int64_t t = 0;
+        for (auto& b : p->blocks) t += b.prog.totalElems;
+        return t;
+    }
+    if (!strcmp(name, "patch_elems_max")) {
+        int64_t t = 0;
+        for (auto& b : p->blocks) t = std::max<int64_t>(t, b.prog.maxElems);
+        return t;
+    }
+    if (!strcmp(name, "patch_sources_total")) {
+        int64_t t = 0;
+        for (auto& b : p->blocks) t += b.prog.totalSources;
+        return t;
+    }
+    if (!strcmp(name, "patch_path")) {
+        bool all = p->patchesBuilt && p->usePatch;
+        for (auto& b : p->blocks) all = all && b.prog.built;
+        return all ? 1 : 0;
+    }
+    return -1;
+}
+
+extern "C" int femb_plan_sync(femb_plan* p) {
+    if (!p) return fail("femb_plan_sync: plan is NULL");
+    TRY(use_device(p));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int64_t femb_plan_num_dof(const femb_plan* p) { return p ? p->numNodes * p->numStates : -1; }
+extern "C" int64_t femb_plan_num_elems(const femb_plan* p) { return p ? p->numElems : -1; }
+extern "C" int64_t femb_plan_nnz(const femb_plan* p) {
+    return (p && p->finalized) ? p->nnzNode * (int64_t)p->numStates * p->numStates : -1;
+}
+extern "C" double femb_plan_build_ms(const femb_plan* p) { return p ? (double)p->buildMs : -1.0; }
+extern "C" int64_t femb_plan_last_launches(const femb_plan* p) { return p ? p->launches : -1; }
+
+extern "C" int femb_plan_pattern_dev(femb_plan* p, int64_t* d_indptr, int64_t* d_indices) {
+    TRY(need_final(p, "femb_plan_pattern_dev"));
+    TRY(use_device(p));
+    k_dof_pattern<<<grid_for(p->numNodes + 1, 128), 128, 0, p->stream>>>(
+        p->numNodes, p->numStates, p->d_nrowptr, p->d_ncols, (long long*)d_indptr, (long long*)d_indices);
+    p->launches = 1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int femb_plan_pattern(femb_plan* p, int64_t* indptr, int64_t* indices) {
+    TRY(need_final(p, "femb_plan_pattern"));
+    TRY(use_device(p));
+    const int64_t nd = femb_plan_num_dof(p), nnz = femb_plan_nnz(p);
+    long long *d_ip = nullptr, *d_ix = nullptr;
+    CUDA_TRY(cudaMalloc(&d_ip, (nd + 1) * sizeof(long long)));
+    CUDA_TRY(cudaMalloc(&d_ix, std::max<int64_t>(nnz, 1) * sizeof(long long)));
+    int rc = femb_plan_pattern_dev(p, (int64_t*)d_ip, (int64_t*)d_ix);
+    if (!rc) {
+        cudaError_t e1 = cudaMemcpyAsync(indptr, d_ip, (nd + 1) * sizeof(long long), cudaMemcpyDeviceToHost, p->stream);
+        cudaError_t e2 = cudaMemcpyAsync(indices, d_ix, nnz * sizeof(long long), cudaMemcpyDeviceToHost, p->stream);
+        cudaError_t e3 = cudaStreamSynchronize(p->stream);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = fail("femb_plan_pattern: copy back failed");
+    }
+    cudaFree(d_ip);
+    cudaFree(d_ix);
+    return rc;
+}
+
+// =============================================================================================
+// C ABI: boundary conditions
+// =============================================================================================
+extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const double* bcVal, int64_t nBC) {
+    TRY(need_final(p, "femb_plan_set_bcs"));
+    TRY(use_device(p));
+    dfree(p->d_bcDof);
+    dfree(p->d_bcVal);
+    dfree(p->d_bcCount);
+    p->nBC = 0;
+    if (nBC <= 0) return 0;
+    if (!bcDof || !bcVal) return fail("femb_plan_set_bcs: NULL BC arrays");
+    const int64_t numDOF = femb_plan_num_dof(p);
+    // reference semantics (AssemblyUtils.py:55-60,93): every occurrence adds 1.0 to the diagonal, the
+    // last value assigned to a DOF wins in the residual
+    std::unordered_map<int64_t, size_t> where;
+    std::vector<int> dofs;
+    std::vector<double> vals, counts;
+    for (int64_t k = 0; k < nBC; ++k) {
+        int64_t d = bcDof[k];
+        if (d < 0) d += numDOF;  // numpy-style negative index
+        if (d < 0 || d >= numDOF) return fail("femb_plan_set_bcs: BC DOF %lld out of range", (long long)bcDof[k]);
+        auto it = where.find(d);
+        if (it == where.end()) {
+            where.emplace(d, dofs.size());
+            dofs.push_back((int)d);
+            vals.push_back(bcVal[k]);
+            counts.push_back(1.0);
+        } else {
+            vals[it->second] = bcVal[k];
+            counts[it->second] += 1.0;
+        }
+    }
+    const size_t n = dofs.size();
+    {  // ascending DOF order: the fused kernel looks constrained DOFs up by binary search
+        std::vector<size_t> perm(n);
+        for (size_t i = 0; i < n; ++i) perm[i] = i;
+        std::sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return dofs[a] < dofs[b]; });
+        std::vector<int> d2(n);
+        std::vector<double> v2(n), c2(n);
+        for (size_t i = 0; i < n; ++i) {
+            d2[i] = dofs[perm[i]];
+            v2[i] = vals[perm[i]];
+            c2[i] = counts[perm[i]];
+        }
+        dofs.swap(d2);
+        vals.swap(v2);
+        counts.swap(c2);
+    }
+    std::vector<unsigned char> mask((size_t)p->numNodes, 0);
+    for (size_t i = 0; i < n; ++i) mask[dofs[i] >> 1] |= (unsigned char)(1u << (dofs[i] & 1));
+    TRY(dalloc(&p->d_bcMask, (size_t)p->numNodes));
+    CUDA_TRY(cudaMemcpyAsync(p->d_bcMask, mask.data(), mask.size(), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMalloc(&p->d_bcDof, n * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&p->d_bcVal, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&p->d_bcCount, n * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(p->d_bcDof, dofs.data(), n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_bcVal, vals.data(), n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_bcCount, counts.data(), n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
+    k_check_bcs<<<grid_for((int64_t)n, 256), 256, 0, p->stream>>>((long long)n, p->d_bcDof, p->d_nrowptr, p->d_flag);
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (flag) return fail("femb_plan_set_bcs: a BC is applied to a node that belongs to no element (no diagonal entry in the pattern)");
+    p->nBC = (int64_t)n;
+    return 0;
+}

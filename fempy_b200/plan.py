@@ -83,7 +83,24 @@ class AssemblyPlan:
         return int(self._lib.femb_plan_last_launches(self._h))
 
     def setStream(self, cudaStream):
-        check(self._lib.femb_plan_set_stream(self._h, C.c_void_p(cudaStream) if cudaStream else None))
+        """Run on the caller's CUDA stream handle (int; 0 = legacy default stream); None = the plan's own stream."""
+        if cudaStream is None:
+            check(self._lib.femb_plan_set_stream(self._h, None, 0))
+        else:
+            check(self._lib.femb_plan_set_stream(self._h, C.c_void_p(int(cudaStream)), 1))
+
+    def setLocalityHint(self, coords):
+        """Node coordinates used only to cut spatially compact node patches (before finalize)."""
+        coords = as_f64(coords)
+        if coords.shape != (self.numNodes, self.numDim):
+            raise ValueError("coords must be numNodes x numDim")
+        check(self._lib.femb_plan_set_locality_hint(self._h, dptr(coords)))
+
+    def setOption(self, name, value):
+        check(self._lib.femb_plan_set_option(self._h, name.encode(), int(value)))
+
+    def info(self, name):
+        return int(self._lib.femb_plan_get_info(self._h, name.encode()))
 
     def sync(self):
         check(self._lib.femb_plan_sync(self._h))

@@ -45,6 +45,7 @@ def planFor(model, device=0):
     if plan is not None:
         return plan
     plan = AssemblyPlan(model.numNodes, model.numDim, model.constitutiveModel.numStates, device=device)
+    plan.setLocalityHint(model.nodeCoords)
     for elType, elData in model.elements.items():
         el = elData["elementObject"]
         pts = np.atleast_2d(el.getIntegrationPointCoords())

@@ -78,9 +78,20 @@ int femb_plan_add_block(femb_plan* plan, int32_t nodesPerElem, int32_t numQuad, 
 int femb_plan_finalize(femb_plan* plan);
 void femb_plan_destroy(femb_plan* plan);
 
-/* run the plan's kernels on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream);
- * NULL restores the plan's own stream */
-int femb_plan_set_stream(femb_plan* plan, void* cudaStream);
+/* optional, before finalize: node coordinates (numNodes, numDim) used ONLY to order nodes for locality when
+ * the node patches of the write-once assembly are cut (Morton order); results do not depend on it */
+int femb_plan_set_locality_hint(femb_plan* plan, const double* coords);
+
+/* tuning knobs: "patch_nodes" (owned nodes per patch, before finalize; 0 = default),
+ * "use_patches" (0: scatter kernels with FP64 atomics, 1: write-once patch kernels where available) */
+int femb_plan_set_option(femb_plan* plan, const char* name, int64_t value);
+/* "num_patches", "patch_nodes", "patch_elems_total", "patch_elems_max", "patch_sources_total", "patch_path" */
+int64_t femb_plan_get_info(const femb_plan* plan, const char* name);
+
+/* external != 0: run the plan's kernels on the caller's CUDA stream (e.g.
+ * torch.cuda.current_stream().cuda_stream; NULL is the legacy default stream); external == 0: back to the
+ * plan's own stream */
+int femb_plan_set_stream(femb_plan* plan, void* cudaStream, int32_t external);
 int femb_plan_sync(femb_plan* plan);
 
 int64_t femb_plan_num_dof(const femb_plan* plan);
