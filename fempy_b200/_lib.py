@@ -51,6 +51,7 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "femb_plan_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "femb_plan_profile_read": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),
+    "femb_plan_pipe_stats": (C.c_int, [C.c_void_p, C.c_int32, c_int64_p, C.c_int64]),
     "femb_function": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.POINTER(Material), C.c_int32, C.c_int32, c_double_p]),
     "femb_function_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Material), C.c_int32, C.c_int32, C.c_void_p]),
     "femb_element_blocks": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.POINTER(Material), c_double_p, c_double_p]),

@@ -1,4 +1,5 @@
 // Fused K + R assembly kernels and their C ABI.
+#include "assemble_pipe.cuh"
 #include "femb_internal.h"
 
 using namespace femb;
@@ -131,257 +132,70 @@ __global__ void k_apply_bcs(long long nBC, const int* __restrict__ bcDof, const 
 
 
 // =============================================================================================
-// write-once assembly over node patches (plan_patch.cu builds the programs)
-//
-// One CTA per patch.  Phase 1: one thread per patch element evaluates K_e (symmetric storage: NN diagonal
-// + NN(NN-1)/2 off-diagonal 2x2 blocks) and R_e in FP64 registers and parks them in shared memory, element
-// index fastest (conflict-free stores).  Phase 2: one thread per (owned node, neighbour node) block of the
-// global matrix sums its sources and writes both CSR rows of the node with 16-byte stores; the thread on
-// the diagonal block also sums the node's residual, subtracts the load and applies the BC.  No atomics, no
-// zero-fill, every output written exactly once.
+// write-once assembly over node patches: persistent warp-specialised pipeline (assemble_pipe.cuh)
 // =============================================================================================
-struct PatchArgs {
-    long long numNodes;
-    int PN;
-    const int* order;
-    const int* nbStart;
-    const unsigned short* nbRow;
-    const int* nrowptr;
-    const int* ncols;
-    const int* pePtr;
-    const int* peElem;
-    const int* peConn;
-    const int* srcBase;
-    const unsigned short* srcPtr;
-    const unsigned short* src;
-    long long elemOffset;
-    const double2* coords;
-    const double2* states;
-    const double* thick;
-    const double* loads;
-    const unsigned char* bcMask;  // NULL: no BCs in this pass
-    const int* bcDof;
-    const double* bcVal;
-    const double* bcCount;
-    int nBC;
-    int accumulate;  // != 0: add to K / R (second and later element blocks of a mixed mesh)
-    double* K;
-    double* R;
-};
+static constexpr int PIPE_SMEM_LIMIT = 227 * 1024;
 
-__device__ __forceinline__ int bc_find(const int* __restrict__ bcDof, int n, int dof) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (bcDof[mid] < dof) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-template <int NN, int NQ, bool NL, bool WK, bool WR>
-__global__ void __launch_bounds__(256) k_assemble_patch(const __grid_constant__ Tables<NN, NQ> tb, const DMat D,
-                                                        const PatchArgs A) {
-    constexpr int NBLK = NN + NN * (NN - 1) / 2;
-    constexpr int BLKBITS = (NBLK <= 2) ? 1 : (NBLK <= 4) ? 2 : (NBLK <= 8) ? 3 : (NBLK <= 16) ? 4 : (NBLK <= 32) ? 5 : (NBLK <= 64) ? 6 : 7;
-    extern __shared__ double sm[];
-    const int p = blockIdx.x;
-    const int pe0 = A.pePtr[p];
-    const int ne = A.pePtr[p + 1] - pe0;
-    const int stride = ne | 1;  // odd stride: the phase-2 gathers of one element's values spread over the banks
-    double* Ksm = sm;                                         // [(blk*4 + c) * stride + t]
-    double* Rsm = sm + (WK ? (size_t)NBLK * 4 * stride : 0);  // [(a*2 + s) * stride + t]
-
-    // ---- phase 1: element matrices into shared memory ----------------------------------------------------
-    for (int t = threadIdx.x; t < ne; t += blockDim.x) {
-        const int* cn = A.peConn + (size_t)NN * pe0 + t;
-        double x[NN], y[NN], ux[NN], uy[NN];
-#pragma unroll
-        for (int a = 0; a < NN; ++a) {
-            const int node = __ldg(cn + a * ne);
-            const double2 c = __ldg(A.coords + node);
-            x[a] = c.x;
-            y[a] = c.y;
-            if (NL || WR) {
-                const double2 q = __ldg(A.states + node);
-                ux[a] = q.x;
-                uy[a] = q.y;
-            } else {
-                ux[a] = uy[a] = 0.0;
-            }
-        }
-        const double theta = __ldg(A.thick + A.elemOffset + __ldg(A.peElem + pe0 + t));
-        double Kd[NN][3], Ko[NN * (NN - 1) / 2 + 1][4], Re[NN][2];
-        element_sym<NN, NQ, NL, WK, WR>(tb, D, x, y, ux, uy, theta, Kd, Ko, Re);
-        if (WK) {
-#pragma unroll
-            for (int a = 0; a < NN; ++a) {
-                Ksm[(a * 4 + 0) * stride + t] = Kd[a][0];
-                Ksm[(a * 4 + 1) * stride + t] = Kd[a][1];
-                Ksm[(a * 4 + 2) * stride + t] = Kd[a][1];
-                Ksm[(a * 4 + 3) * stride + t] = Kd[a][2];
-            }
-#pragma unroll
-            for (int k = 0; k < NN * (NN - 1) / 2; ++k) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) Ksm[((NN + k) * 4 + c) * stride + t] = Ko[k][c];
-            }
-        }
-        if (WR) {
-#pragma unroll
-            for (int a = 0; a < NN; ++a) {
-                Rsm[(a * 2 + 0) * stride + t] = Re[a][0];
-                Rsm[(a * 2 + 1) * stride + t] = Re[a][1];
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 2: gather into the CSR rows of the owned nodes ---------------------------------------------
-    const long long pos0 = (long long)p * A.PN;
-    const long long pos1 = (pos0 + A.PN < A.numNodes) ? pos0 + A.PN : A.numNodes;
-    const int nb0 = A.nbStart[pos0];
-    const int nbn = A.nbStart[pos1] - nb0;
-    const unsigned short* sp = A.srcPtr + nb0 + p;
-    const unsigned short* sr = A.src + A.srcBase[p];
-    for (int q = threadIdx.x; q < nbn; q += blockDim.x) {
-        const long long pos = pos0 + A.nbRow[nb0 + q];
-        const int i = __ldg(A.order + pos);
-        const int off = __ldg(A.nrowptr + i);
-        const int deg = __ldg(A.nrowptr + i + 1) - off;
-        const int k = nb0 + q - __ldg(A.nbStart + pos);
-        const int s0 = sp[q], s1 = sp[q + 1];
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, rx = 0.0, ry = 0.0;
-        bool diag = false;
-        for (int s = s0; s < s1; ++s) {
-            const unsigned code = sr[s];
-            const unsigned tr = code & 1u;
-            const unsigned blk = (code >> 1) & ((1u << BLKBITS) - 1u);
-            const unsigned el = code >> (BLKBITS + 1);
-            if (WK) {
-                const double* b = Ksm + (size_t)(blk * 4) * stride + el;
-                const double b1 = b[stride], b2 = b[2 * stride];
-                v0 += b[0];
-                v1 += tr ? b2 : b1;
-                v2 += tr ? b1 : b2;
-                v3 += b[3 * stride];
-            }
-            if (blk < NN) {
-                diag = true;
-                if (WR) {
-                    rx += Rsm[(blk * 2) * stride + el];
-                    ry += Rsm[(blk * 2 + 1) * stride + el];
-                }
-            }
-        }
-        const unsigned mask = A.bcMask ? A.bcMask[i] : 0u;
-        if (mask) {  // constrained rows: zeros except the occurrence count on the diagonal (AssemblyUtils.py:55-60)
-            const bool onDiag = (__ldg(A.ncols + off + k) == i);
-            if (mask & 1u) {
-                v0 = onDiag ? A.bcCount[bc_find(A.bcDof, A.nBC, 2 * i)] : 0.0;
-                v1 = 0.0;
-            }
-            if (mask & 2u) {
-                v2 = 0.0;
-                v3 = onDiag ? A.bcCount[bc_find(A.bcDof, A.nBC, 2 * i + 1)] : 0.0;
-            }
-        }
-        if (WK) {
-            double2* r0 = reinterpret_cast<double2*>(A.K + 4ll * off + 2 * k);
-            double2* r1 = reinterpret_cast<double2*>(A.K + 4ll * off + 2 * deg + 2 * k);
-            if (A.accumulate) {
-                if (s1 > s0) {
-                    const double2 o0 = *r0, o1 = *r1;
-                    *r0 = make_double2(o0.x + v0, o0.y + v1);
-                    *r1 = make_double2(o1.x + v2, o1.y + v3);
-                }
-            } else {
-                *r0 = make_double2(v0, v1);
-                *r1 = make_double2(v2, v3);
-            }
-        }
-        if (WR && diag) {
-            double2* rr = reinterpret_cast<double2*>(A.R + 2ll * i);
-            if (A.accumulate) {
-                const double2 o = *rr;
-                *rr = make_double2(o.x + rx, o.y + ry);
-            } else {
-                if (A.loads) {
-                    const double2 f = __ldg(reinterpret_cast<const double2*>(A.loads) + i);
-                    rx -= f.x;
-                    ry -= f.y;
-                }
-                if (mask) {  // R[bc] = u - c (AssemblyUtils.py:93)
-                    const double2 u = __ldg(A.states + i);
-                    if (mask & 1u) rx = u.x - A.bcVal[bc_find(A.bcDof, A.nBC, 2 * i)];
-                    if (mask & 2u) ry = u.y - A.bcVal[bc_find(A.bcDof, A.nBC, 2 * i + 1)];
-                }
-                *rr = make_double2(rx, ry);
-            }
-        }
-    }
-    // nodes that belong to no element have no node-block: their residual is just -load (Problem.py:641,653)
-    if (WR && !A.accumulate) {
-        for (long long pos = pos0 + threadIdx.x; pos < pos1; pos += blockDim.x) {
-            const int i = __ldg(A.order + pos);
-            if (__ldg(A.nrowptr + i + 1) == __ldg(A.nrowptr + i)) {
-                double2 f = make_double2(0.0, 0.0);
-                if (A.loads) f = __ldg(reinterpret_cast<const double2*>(A.loads) + i);
-                *reinterpret_cast<double2*>(A.R + 2ll * i) = make_double2(-f.x, -f.y);
-            }
-        }
-    }
-}
-
-template <int NN, int NQ>
-static size_t patch_smem_bytes(int maxElems, bool wk, bool wr) {
-    constexpr int NBLK = NN + NN * (NN - 1) / 2;
-    const size_t stride = (size_t)(maxElems | 1);
-    return ((wk ? (size_t)NBLK * 4 : 0) + (wr ? (size_t)NN * 2 : 0)) * stride * sizeof(double);
-}
-
-template <int NN, int NQ, bool NL, bool WK, bool WR>
-static int launch_patch(const BlockData& b, const DMat& D, const PatchArgs& A, int64_t numPatches, cudaStream_t st) {
+template <int NN, int NQ, bool NL, bool WK, bool WR, int TEAM>
+static int launch_pipe(const femb_plan* p, const BlockData& b, const DMat& D, pipe::Args A, cudaStream_t st) {
     const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
-    const size_t smem = patch_smem_bytes<NN, NQ>(b.prog.maxElems, WK, WR);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_assemble_patch<NN, NQ, NL, WK, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    constexpr int numTeams = pipe::WARPS / TEAM;
+    const pipe::SmemPlan S = pipe::smem_plan(numTeams, b.prog.maxBlobBytes, b.prog.maxLocal, b.prog.maxElems, b.prog.maxNodeBlocks, p->patchNodes, WK);
+    A.inStride = S.inStride;
+    A.offX = S.offX;
+    A.offU = S.offU;
+    A.offL = S.offL;
+    A.offTH = S.offTH;
+    A.offMask = S.offMask;
+    A.accStride = S.accStride;
+    A.offRacc = S.offRacc;
+    A.teamStride = S.teamStride;
+    A.offTeams = S.offTeams;
+    static int configured = 0;
+    if (S.total > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
+        configured = S.total;
     }
-    int threads = ((b.prog.maxElems + 31) / 32) * 32;
-    threads = std::min(256, std::max(64, threads));
-    k_assemble_patch<NN, NQ, NL, WK, WR><<<(unsigned)numPatches, threads, smem, st>>>(tb, D, A);
+    static int numSMs = 0;
+    if (!numSMs) CUDA_TRY(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, p->device));
+    const int64_t wanted = (p->numPatches + numTeams - 1) / numTeams;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(wanted, numSMs));
+    pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM><<<grid, pipe::THREADS, S.total, st>>>(tb, D, A);
     return 0;
 }
 
-template <int NN, int NQ>
-static int launch_patch_variant(const BlockData& b, const DMat& D, const PatchArgs& A, int64_t numPatches, bool nl, bool wk,
-                                bool wr, cudaStream_t st) {
+template <int NN, int NQ, int TEAM>
+static int launch_pipe_variant(const femb_plan* p, const BlockData& b, const DMat& D, const pipe::Args& A, bool nl, bool wk,
+                               bool wr, cudaStream_t st) {
     if constexpr (NN <= 4) {
         if (!nl) {
-            if (wk && wr) return launch_patch<NN, NQ, false, true, true>(b, D, A, numPatches, st);
-            if (wk) return launch_patch<NN, NQ, false, true, false>(b, D, A, numPatches, st);
-            return launch_patch<NN, NQ, false, false, true>(b, D, A, numPatches, st);
+            if (wk && wr) return launch_pipe<NN, NQ, false, true, true, TEAM>(p, b, D, A, st);
+            if (wk) return launch_pipe<NN, NQ, false, true, false, TEAM>(p, b, D, A, st);
+            return launch_pipe<NN, NQ, false, false, true, TEAM>(p, b, D, A, st);
         }
-        if (wk && wr) return launch_patch<NN, NQ, true, true, true>(b, D, A, numPatches, st);
-        if (wk) return launch_patch<NN, NQ, true, true, false>(b, D, A, numPatches, st);
-        return launch_patch<NN, NQ, true, false, true>(b, D, A, numPatches, st);
+        if (wk && wr) return launch_pipe<NN, NQ, true, true, true, TEAM>(p, b, D, A, st);
+        if (wk) return launch_pipe<NN, NQ, true, true, false, TEAM>(p, b, D, A, st);
+        return launch_pipe<NN, NQ, true, false, true, TEAM>(p, b, D, A, st);
     } else {
         return fail("no patch kernel for %d-node elements", NN);
     }
 }
 
-static constexpr size_t PATCH_SMEM_LIMIT = 200 * 1024;
+template <int NN, int NQ>
+static int launch_pipe_team(const femb_plan* p, const BlockData& b, const DMat& D, const pipe::Args& A, bool nl, bool wk, bool wr,
+                            cudaStream_t st) {
+    if (p->teamWarps == 1) return launch_pipe_variant<NN, NQ, 1>(p, b, D, A, nl, wk, wr, st);
+    return launch_pipe_variant<NN, NQ, 2>(p, b, D, A, nl, wk, wr, st);
+}
 
-static bool patch_path_available(const femb_plan* p, bool wk, bool wr) {
+static bool patch_path_available(const femb_plan* p, bool wk, bool /*wr*/) {
     if (!p->usePatch || !p->patchesBuilt) return false;
+    const int numTeams = pipe::WARPS / p->teamWarps;
     for (auto& b : p->blocks) {
         if (!b.prog.built) return false;
-        size_t smem = 0;
-        if (b.nn == 3) smem = patch_smem_bytes<3, 1>(b.prog.maxElems, wk, wr);
-        else if (b.nn == 4) smem = patch_smem_bytes<4, 4>(b.prog.maxElems, wk, wr);
-        else return false;
-        if (smem > PATCH_SMEM_LIMIT) return false;
+        if (b.nn > 4 || b.prog.maxElems > 32 * p->teamWarps) return false;
+        const int total = pipe::smem_plan(numTeams, b.prog.maxBlobBytes, b.prog.maxLocal, b.prog.maxElems, b.prog.maxNodeBlocks, p->patchNodes, wk).total;
+        if (total > PIPE_SMEM_LIMIT) return false;
     }
     return true;
 }
@@ -452,34 +266,26 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
     }
     for (auto& b : p->blocks) {
         if (patchPath) {
-            PatchArgs A;
-            A.numNodes = p->numNodes;
+            pipe::Args A;
+            A.numPatches = p->numPatches;
             A.PN = p->patchNodes;
-            A.order = p->d_order;
-            A.nbStart = p->d_nbStart;
-            A.nbRow = p->d_nbRow;
-            A.nrowptr = p->d_nrowptr;
-            A.ncols = p->d_ncols;
-            A.pePtr = b.prog.d_pePtr;
-            A.peElem = b.prog.d_peElem;
-            A.peConn = b.prog.d_peConn;
-            A.srcBase = b.prog.d_srcBase;
-            A.srcPtr = b.prog.d_srcPtr;
-            A.src = b.prog.d_src;
-            A.elemOffset = b.elemOffset;
-            A.coords = (const double2*)d_coords;
-            A.states = (const double2*)d_states;
-            A.thick = d_thick;
-            A.loads = d_loads;
-            A.bcMask = (bcs && !multi) ? p->d_bcMask : nullptr;
+            A.blobPtr = b.prog.d_blobPtr;
+            A.blob = b.prog.d_blob;
+            A.maskPerm = (bcs && !multi) ? p->d_bcMaskPerm : nullptr;
             A.bcDof = p->d_bcDof;
             A.bcVal = p->d_bcVal;
             A.bcCount = p->d_bcCount;
             A.nBC = (int)p->nBC;
-            A.accumulate = multi ? 1 : 0;
+            A.coords = (const double2*)d_coords;
+            A.states = (const double2*)d_states;
+            A.loads = multi ? nullptr : (const double2*)d_loads;
+            A.thick = d_thick;
             A.K = d_K;
             A.R = d_R;
-            FEMB_DISPATCH_FAMILY(b.nn, b.nq, TRY((launch_patch_variant<NN, NQ>(b, D, A, p->numPatches, mat->nonlinear != 0, wk, wr, st))));
+            A.accumulate = multi ? 1 : 0;
+            A.stats = p->d_pipeStats;
+            A.debug = p->debugFlags;
+            FEMB_DISPATCH_FAMILY(b.nn, b.nq, TRY((launch_pipe_team<NN, NQ>(p, b, D, A, mat->nonlinear != 0, wk, wr, st))));
         } else {
             AsmArgs A;
             A.E = b.numElems;
@@ -505,6 +311,26 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
     }
     p->launches = launches;
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// measurement only: per-CTA cycle counters of the pipeline roles (16 int64 per CTA, 256 CTAs max)
+extern "C" int femb_plan_pipe_stats(femb_plan* p, int32_t enable, int64_t* out, int64_t capacity) {
+    if (!p) return fail("femb_plan_pipe_stats: plan is NULL");
+    TRY(use_device(p));
+    const size_t n = 16 * 256;
+    if (out) {
+        if (!p->d_pipeStats) return fail("femb_plan_pipe_stats: not enabled");
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        CUDA_TRY(cudaMemcpy(out, p->d_pipeStats, std::min<size_t>(n, (size_t)capacity) * sizeof(long long), cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    if (enable) {
+        TRY(dalloc(&p->d_pipeStats, n));
+        CUDA_TRY(cudaMemset(p->d_pipeStats, 0, n * sizeof(long long)));
+    } else {
+        dfree(p->d_pipeStats);
+    }
     return 0;
 }
 

@@ -45,13 +45,15 @@ struct PatchProgram {
     bool built = false;
     int maxElems = 0;             // largest patch element count (shared-memory sizing)
     int64_t totalElems = 0;       // sum over patches (includes elements evaluated by several patches)
-    int64_t totalSources = 0;
+    int maxBlobBytes = 0;         // largest program blob
+    int maxLocal = 0;             // largest local-node count (owned + halo)
+    int maxNodeBlocks = 0;        // largest number of (owned node, neighbour) blocks of a patch (accumulator sizing)
+    int maxColours = 0;           // largest number of colours of a scatter phase
+    int64_t blobBytes = 0;        // total size of the program blobs
     int* d_pePtr = nullptr;       // (numPatches+1) patch -> range of patch elements
-    int* d_peElem = nullptr;      // block-local element id of each patch element (sorted within a patch)
-    int* d_peConn = nullptr;      // patch-contiguous, node-major connectivity: base nn*pePtr[p], [a*ne + t]
-    int* d_srcBase = nullptr;     // (numPatches+1) patch -> first source
-    uint16_t* d_srcPtr = nullptr; // (nnzNode + numPatches) patch-relative source offsets, one extra per patch
-    uint16_t* d_src = nullptr;    // sources: elemLocal << (blkBits+1) | blk << 1 | transpose
+    int* d_peElem = nullptr;      // (build only) block-local element id of each patch element, sorted within a patch
+    int* d_blobPtr = nullptr;     // (numPatches+1) patch -> blob offset in 16-byte units
+    unsigned char* d_blob = nullptr;  // program blobs (patch_blob.h)
 };
 
 struct BlockData {
@@ -92,11 +94,13 @@ struct femb_plan {
     // node patches (shared by all blocks)
     bool patchesBuilt = false;
     int patchNodes = 0;          // owned nodes per patch
+    int teamWarps = 2;           // warps that share a patch in the assembly kernel (1 or 2): a patch holds <= 32*teamWarps elements
     int64_t numPatches = 0;
     double* d_hintCoords = nullptr;  // optional locality hint (node coordinates at plan time)
     int* d_order = nullptr;      // patch order: owned nodes of patch p = order[p*patchNodes ...]
     int* d_nbStart = nullptr;    // (numNodes+1) prefix of node degrees in patch order = first node-block of a node
-    uint16_t* d_nbRow = nullptr; // (nnzNode) patch-local owned-node index of each node-block, patch order
+    long long* d_pipeStats = nullptr;  // measurement only
+    int debugFlags = 0;                // measurement only
     int usePatch = 1;            // assembly path selection (1: write-once patches where available)
     // boundary conditions, de-duplicated on the host with the reference's semantics
     int64_t nBC = 0;
@@ -104,6 +108,7 @@ struct femb_plan {
     double* d_bcVal = nullptr;    // last value given for the DOF
     double* d_bcCount = nullptr;  // number of occurrences (diagonal value)
     unsigned char* d_bcMask = nullptr;  // (numNodes) bit r set when DOF 2*node + r is constrained
+    unsigned char* d_bcMaskPerm = nullptr;  // the same mask in patch order (padded to a multiple of 16 nodes)
     // scratch for the host-pointer API
     double *s_coords = nullptr, *s_states = nullptr, *s_thick = nullptr, *s_loads = nullptr, *s_K = nullptr,
            *s_R = nullptr, *s_out = nullptr;

@@ -141,6 +141,12 @@ __global__ void k_dof_pattern(long long numNodes, int s, const int* __restrict__
 }
 
 
+__global__ void k_permute_mask(const int* __restrict__ order, const unsigned char* __restrict__ mask, long long N,
+                               unsigned char* __restrict__ maskPerm) {
+    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos < N) maskPerm[pos] = mask[order[pos]];
+}
+
 __global__ void k_check_bcs(long long nBC, const int* __restrict__ bcDof, const int* __restrict__ nrowptr, int* flag) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nBC) return;
@@ -329,6 +335,8 @@ extern "C" void femb_plan_destroy(femb_plan* p) {
     dfree(p->d_adj);
     dfree(p->d_hintCoords);
     dfree(p->d_bcMask);
+    dfree(p->d_bcMaskPerm);
+    dfree(p->d_pipeStats);
     free_patches(p);
     dfree(p->d_bcDof);
     dfree(p->d_bcVal);
@@ -374,8 +382,15 @@ extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t valu
         if (p->finalized) return fail("femb_plan_set_option: patch_nodes must be set before finalize");
         if (value < 0 || value > 1024) return fail("femb_plan_set_option: patch_nodes out of range");
         p->patchNodes = (int)value;
+    } else if (!strcmp(name, "team_warps")) {
+        if (p->finalized) return fail("femb_plan_set_option: team_warps must be set before finalize");
+        if (value != 1 && value != 2) return fail("femb_plan_set_option: team_warps must be 1 or 2");
+        p->teamWarps = (int)value;
     } else if (!strcmp(name, "use_patches")) {
         p->usePatch = value != 0;
+    } else if (!strcmp(name, "debug_flags")) {
+        p->debugFlags = (int)value;
+
     } else {
         return fail("femb_plan_set_option: unknown option %s", name);
     }
@@ -386,6 +401,7 @@ extern "C" int64_t femb_plan_get_info(const femb_plan* p, const char* name) {
     if (!p || !name) return -1;
     if (!strcmp(name, "num_patches")) return p->numPatches;
     if (!strcmp(name, "patch_nodes")) return p->patchNodes;
+    if (!strcmp(name, "team_warps")) return p->teamWarps;
     if (!strcmp(name, "patch_elems_total")) {
         int64_t t = 0;
         for (auto& b : p->blocks) t += b.prog.totalElems;
@@ -396,9 +412,14 @@ extern "C" int64_t femb_plan_get_info(const femb_plan* p, const char* name) {
         for (auto& b : p->blocks) t = std::max<int64_t>(t, b.prog.maxElems);
         return t;
     }
-    if (!strcmp(name, "patch_sources_total")) {
+    if (!strcmp(name, "patch_blob_bytes")) {
         int64_t t = 0;
-        for (auto& b : p->blocks) t += b.prog.totalSources;
+        for (auto& b : p->blocks) t += b.prog.blobBytes;
+        return t;
+    }
+    if (!strcmp(name, "patch_colours_max")) {
+        int64_t t = 0;
+        for (auto& b : p->blocks) t = std::max<int64_t>(t, b.prog.maxColours);
         return t;
     }
     if (!strcmp(name, "patch_path")) {
@@ -506,6 +527,12 @@ extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const doubl
     for (size_t i = 0; i < n; ++i) mask[dofs[i] >> 1] |= (unsigned char)(1u << (dofs[i] & 1));
     TRY(dalloc(&p->d_bcMask, (size_t)p->numNodes));
     CUDA_TRY(cudaMemcpyAsync(p->d_bcMask, mask.data(), mask.size(), cudaMemcpyHostToDevice, p->stream));
+    if (p->patchesBuilt && p->d_order) {  // the same mask in patch order: each patch bulk-copies its slice
+        const size_t padded = (size_t)p->numPatches * p->patchNodes;
+        TRY(dalloc(&p->d_bcMaskPerm, padded));
+        CUDA_TRY(cudaMemsetAsync(p->d_bcMaskPerm, 0, padded, p->stream));
+        k_permute_mask<<<grid_for(p->numNodes, 256), 256, 0, p->stream>>>(p->d_order, p->d_bcMask, p->numNodes, p->d_bcMaskPerm);
+    }
     CUDA_TRY(cudaMalloc(&p->d_bcDof, n * sizeof(int)));
     CUDA_TRY(cudaMalloc(&p->d_bcVal, n * sizeof(double)));
     CUDA_TRY(cudaMalloc(&p->d_bcCount, n * sizeof(double)));

@@ -4,26 +4,22 @@
 // (Morton order of the hint coordinates when the caller supplied them, node-id order otherwise).  For
 // every element block the builder then records, per patch,
 //   * the elements touching an owned node (sorted; evaluated by that patch's CTA, halo elements included),
-//   * a patch-contiguous copy of their connectivity, and
-//   * for every (owned node, neighbour node) block of the global matrix the list of element sub-blocks
-//     that sum into it ("sources": element slot, sub-block id, transpose bit -- 16 bits each).
-// The assembly kernel (assemble.cu: k_assemble_patch) needs no atomics and no zero-fill: every CSR value
-// and residual entry is written exactly once.
+//   * a patch-local copy of their connectivity (local node ids), and
+//   * for every element a scatter record: where the CSR rows of its owned nodes sit in the patch's
+//     shared-memory accumulators, and a colour per local node so that same-colour updates never collide.
+// All of it is packed into one contiguous "program blob" per patch (patch_blob.h).  The assembly kernel
+// (assemble_pipe.cuh) needs no atomics and no zero-fill of K: every CSR value and residual entry is written
+// exactly once, in a fixed summation order.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "femb_internal.h"
+#include "patch_blob.h"
 
-static constexpr int DEFAULT_PATCH_NODES = 128;
+static constexpr int DEFAULT_PATCH_NODES_PER_WARP = 20;  // a team of w warps takes patches of <= 32*w elements (assemble_pipe.cuh)
 static constexpr int MAX_PATCH_ELEMS = 1024;
+static constexpr int MAX_PATCH_CONN = 4096;  // ne * nn entries sorted in shared memory when the halo is built
 
 bool patch_family_supported(int nn, int nq) { return (nn == 3 && nq == 1) || (nn == 4 && nq == 4); }
-
-static int blk_bits(int nn) {
-    const int nblk = nn + nn * (nn - 1) / 2;
-    int b = 1;
-    while ((1 << b) < nblk) ++b;
-    return b;
-}
 
 // ---------------------------------------------------------------------------------------------
 // node order
@@ -138,17 +134,6 @@ __global__ void k_pe_sort(const int* __restrict__ pePtr, int* __restrict__ peEle
     }
 }
 
-// patch-contiguous connectivity copy: peConn[nn*base + a*n + t] = conn[a*E + peElem[base+t]]
-__global__ void k_pe_conn(const int* __restrict__ pePtr, const int* __restrict__ peElem, const int* __restrict__ conn,
-                          long long E, int nn, int* __restrict__ peConn) {
-    const int p = blockIdx.x;
-    const int base = pePtr[p], n = pePtr[p + 1] - base;
-    for (int t = threadIdx.x; t < n * nn; t += blockDim.x) {
-        const int a = t / n, el = t - a * n;
-        peConn[(long long)nn * base + t] = conn[(long long)a * E + peElem[base + el]];
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // node blocks and sources
 // ---------------------------------------------------------------------------------------------
@@ -160,13 +145,6 @@ __global__ void k_deg_perm(const int* __restrict__ order, const int* __restrict_
     degPerm[pos] = nrowptr[i + 1] - nrowptr[i];
 }
 
-__global__ void k_nb_row(long long N, int PN, const int* __restrict__ nbStart, unsigned short* __restrict__ nbRow) {
-    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= N) return;
-    const unsigned short r = (unsigned short)(pos % PN);
-    for (int g = nbStart[pos]; g < nbStart[pos + 1]; ++g) nbRow[g] = r;
-}
-
 __device__ __forceinline__ int lower_bound_int(const int* __restrict__ a, int n, int v) {
     int lo = 0, hi = n;
     while (lo < hi) {
@@ -176,84 +154,157 @@ __device__ __forceinline__ int lower_bound_int(const int* __restrict__ a, int n,
     return lo;
 }
 
-struct SrcArgs {
+// ---------------------------------------------------------------------------------------------
+// program blobs
+// ---------------------------------------------------------------------------------------------
+struct BlobArgs {
     long long N;
     int PN;
+    int nn;
+    long long E, elemOffset;
     const int* order;
+    const int* nodePos;
     const int* nbStart;
     const int* nrowptr;
     const int* ncols;
     const int* adjPtr;
     const int* adj;
-    long long elemOffset, E;
-    int nn;
     const int* conn;
     const int* pePtr;
     const int* peElem;
-    int blkBits;
+    int* halo;      // scratch: nn * pePtr[p] + h
+    int* nHalo;     // per patch
+    int* units;     // per patch blob size in 16-byte units
+    int* stats;     // [0] max blob bytes, [1] max local nodes, [2] overflow, [3] max node-blocks per patch, [4] max colours
 };
 
-// One thread per node (in patch order) walks the node's sorted element adjacency; FILL == false counts the
-// sources of each of its node-blocks, FILL == true writes them (cnt is then the per-node-block cursor).
-// A node's node-blocks are touched by this thread only, so no atomics are needed and the order is fixed.
-template <bool FILL>
-__global__ void k_sources(const SrcArgs S, int* __restrict__ cnt, const int* __restrict__ srcPtrG,
-                          unsigned short* __restrict__ src) {
-    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= S.N) return;
-    const int i = S.order[pos];
-    const int off = S.nrowptr[i], deg = S.nrowptr[i + 1] - off;
-    const int nb0 = S.nbStart[pos];
-    const int patch = (int)(pos / S.PN);
-    const int peBase = S.pePtr[patch], peN = S.pePtr[patch + 1] - peBase;
-    for (int q = S.adjPtr[i]; q < S.adjPtr[i + 1]; ++q) {
-        const long long ge = S.adj[q];
-        if (ge < S.elemOffset || ge >= S.elemOffset + S.E) continue;
-        const long long e = ge - S.elemOffset;
-        int a = 0;
-        for (int m = 0; m < S.nn; ++m)
-            if (S.conn[(long long)m * S.E + e] == i) a = m;
-        int elemLocal = 0;
-        if (FILL) elemLocal = lower_bound_int(S.peElem + peBase, peN, (int)e);
-        for (int b = 0; b < S.nn; ++b) {
-            const int j = S.conn[(long long)b * S.E + e];
-            const int k = lower_bound_int(S.ncols + off, deg, j);
-            if (!FILL) {
-                cnt[nb0 + k] += 1;
-            } else {
-                int blk, tr = 0;
-                if (a == b) {
-                    blk = a;
-                } else if (a < b) {
-                    blk = S.nn + a * S.nn - a * (a + 1) / 2 + (b - a - 1);
-                } else {
-                    blk = S.nn + b * S.nn - b * (b + 1) / 2 + (a - b - 1);
-                    tr = 1;
-                }
-                const int c = cnt[nb0 + k]++;
-                src[srcPtrG[nb0 + k] + c] = (unsigned short)((elemLocal << (S.blkBits + 1)) | (blk << 1) | tr);
-            }
+// one CTA per patch: sorted unique list of the halo nodes (nodes of patch elements that the patch does not own)
+__global__ void k_blob_halo(const BlobArgs B) {
+    __shared__ int cand[MAX_PATCH_CONN];
+    __shared__ int sorted[MAX_PATCH_CONN];
+    const int p = blockIdx.x;
+    const int pe0 = B.pePtr[p], ne = B.pePtr[p + 1] - pe0;
+    const int M = ne * B.nn;
+    const long long pos0 = (long long)p * B.PN;
+    const long long pos1 = (pos0 + B.PN < B.N) ? pos0 + B.PN : B.N;
+    if (M > MAX_PATCH_CONN) {
+        if (threadIdx.x == 0) atomicExch(&B.stats[2], 1);
+        return;
+    }
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const int a = m / ne, t = m - a * ne;
+        const int g = B.conn[(long long)a * B.E + B.peElem[pe0 + t]];
+        const int pos = B.nodePos[g];
+        cand[m] = (pos >= pos0 && pos < pos1) ? 0x7fffffff : g;
+    }
+    __syncthreads();
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const int v = cand[m];
+        int rank = 0;
+        for (int u = 0; u < M; ++u) rank += (cand[u] < v) || (cand[u] == v && u < m);
+        sorted[rank] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* out = B.halo + (long long)B.nn * pe0;
+        int h = 0;
+        for (int m = 0; m < M; ++m) {
+            const int v = sorted[m];
+            if (v == 0x7fffffff) break;
+            if (h == 0 || out[h - 1] != v) out[h++] = v;
         }
+        B.nHalo[p] = h;
+        const int nOwned = (int)(pos1 - pos0);
+        const int nnb = B.nbStart[pos1] - B.nbStart[pos0];
+        const BlobLayout L = blob_layout(B.nn, ne, nOwned, nOwned + h, nnb);
+        B.units[p] = L.bytes / 16;
+        atomicMax(&B.stats[0], L.bytes);
+        atomicMax(&B.stats[1], nOwned + h);
+        atomicMax(&B.stats[3], nnb);
+        if (2 * nnb > 65535) atomicExch(&B.stats[2], 1);
     }
 }
 
-// patch-relative 16-bit source offsets (one extra entry per patch) + per-patch source base
-__global__ void k_src_ptr16(long long N, int PN, long long numPatches, const int* __restrict__ nbStart,
-                            const int* __restrict__ srcPtrG, unsigned short* __restrict__ srcPtr16,
-                            int* __restrict__ srcBase, int* __restrict__ overflow) {
-    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= N) return;
-    const long long patch = pos / PN;
-    const long long first = patch * PN, last = min(first + PN, N);
-    const int base = srcPtrG[nbStart[first]];
-    for (int g = nbStart[pos]; g < nbStart[pos + 1]; ++g) srcPtr16[g + patch] = (unsigned short)(srcPtrG[g] - base);
-    if (pos == last - 1) {
-        const int total = srcPtrG[nbStart[last]] - base;
-        if (total > 65535) atomicExch(overflow, 1);
-        srcPtr16[nbStart[last] + patch] = (unsigned short)total;
+__global__ void k_blob_fill(const BlobArgs B, const int* __restrict__ blobPtr, unsigned char* __restrict__ blob) {
+    __shared__ int numColours[4];
+    const int p = blockIdx.x;
+    const int pe0 = B.pePtr[p], ne = B.pePtr[p + 1] - pe0;
+    const long long pos0 = (long long)p * B.PN;
+    const long long pos1 = (pos0 + B.PN < B.N) ? pos0 + B.PN : B.N;
+    const int nOwned = (int)(pos1 - pos0);
+    const int h = B.nHalo[p];
+    const int* halo = B.halo + (long long)B.nn * pe0;
+    const int nb0 = B.nbStart[pos0], nnb = B.nbStart[pos1] - nb0;
+    const BlobLayout L = blob_layout(B.nn, ne, nOwned, nOwned + h, nnb);
+    unsigned char* base = blob + 16ll * blobPtr[p];
+    int* hdr = reinterpret_cast<int*>(base);
+    int* lnode = reinterpret_cast<int*>(base + L.offLNODE);
+    int2* node = reinterpret_cast<int2*>(base + L.offNODE);
+    unsigned short* nbRow = reinterpret_cast<unsigned short*>(base + L.offNBROW);
+    ElemInfo* einfo = reinterpret_cast<ElemInfo*>(base + L.offEINFO);
+    unsigned short* connOut = reinterpret_cast<unsigned short*>(base + L.offCONN);
+    int* elemOut = reinterpret_cast<int*>(base + L.offELEM);
+    if (threadIdx.x < 4) numColours[threadIdx.x] = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < nOwned; r += blockDim.x) {
+        const int i = B.order[pos0 + r];
+        lnode[r] = i;
+        const int off = B.nrowptr[i], deg = B.nrowptr[i + 1] - off;
+        const int start = B.nbStart[pos0 + r] - nb0;
+        const int diagK = deg ? lower_bound_int(B.ncols + off, deg, i) : 0;
+        if (deg > 255 || start > 32767) atomicExch(&B.stats[2], 1);
+        node[r] = make_int2(off, (start & 0xffff) | ((deg & 0xff) << 16) | ((diagK & 0xff) << 24));
+        for (int k = 0; k < deg; ++k) nbRow[start + k] = (unsigned short)r;
     }
-    if (pos == first) srcBase[patch] = base;
-    if (pos == N - 1) srcBase[numPatches] = srcPtrG[nbStart[N]];
+    for (int m = threadIdx.x; m < h; m += blockDim.x) lnode[nOwned + m] = halo[m];
+    for (int m = threadIdx.x; m < ne * B.nn; m += blockDim.x) {
+        const int a = m / ne, t = m - a * ne;
+        const int g = B.conn[(long long)a * B.E + B.peElem[pe0 + t]];
+        const int pos = B.nodePos[g];
+        const int local = (pos >= pos0 && pos < pos1) ? (int)(pos - pos0) : nOwned + lower_bound_int(halo, h, g);
+        connOut[m] = (unsigned short)local;
+    }
+    // scatter program: for every (element, local node a) whose node the patch owns, where the node's rows start in
+    // the accumulators, where each of the element's nodes sits in that row, and the colour = rank of the element
+    // among the patch elements that have the same node as THEIR a-th node (same-colour updates never collide)
+    for (int t = threadIdx.x; t < ne; t += blockDim.x) {
+        const int e = B.peElem[pe0 + t];
+        elemOut[t] = (int)(B.elemOffset + e);
+        ElemInfo info;
+        int nodes[4];
+        for (int a = 0; a < 4; ++a) nodes[a] = (a < B.nn) ? B.conn[(long long)a * B.E + e] : -1;
+        for (int a = 0; a < 4; ++a) {
+            info.rowBase[a] = 0;
+            info.deg[a] = 0;
+            info.colour[a] = 0xff;
+            for (int b = 0; b < 4; ++b) info.k[a * 4 + b] = 0;
+            if (a >= B.nn) continue;
+            const int i = nodes[a];
+            const int pos = B.nodePos[i];
+            if (pos < pos0 || pos >= pos1) continue;
+            const int off = B.nrowptr[i], deg = B.nrowptr[i + 1] - off;
+            info.rowBase[a] = (unsigned short)(2 * (B.nbStart[pos] - nb0));
+            info.deg[a] = (unsigned char)deg;
+            for (int b = 0; b < B.nn; ++b) info.k[a * 4 + b] = (unsigned char)lower_bound_int(B.ncols + off, deg, nodes[b]);
+            int colour = 0;
+            for (int q = B.adjPtr[i]; q < B.adjPtr[i + 1]; ++q) {
+                const long long ge = B.adj[q];
+                if (ge < B.elemOffset || ge >= B.elemOffset + B.E) continue;
+                const long long e2 = ge - B.elemOffset;
+                if (e2 < e && B.conn[(long long)a * B.E + e2] == i) ++colour;
+            }
+            if (colour >= 255) atomicExch(&B.stats[2], 1);
+            info.colour[a] = (unsigned char)colour;
+            atomicMax(&numColours[a], colour + 1);
+        }
+        einfo[t] = info;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int v[8] = {ne, nOwned, nOwned + h, nnb, numColours[0], numColours[1], numColours[2], numColours[3]};
+        hdr[threadIdx.x] = v[threadIdx.x];
+    }
+    if (threadIdx.x == 0) atomicMax(&B.stats[4], max(max(numColours[0], numColours[1]), max(numColours[2], numColours[3])));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -262,10 +313,8 @@ __global__ void k_src_ptr16(long long N, int PN, long long numPatches, const int
 static void free_program(PatchProgram& g) {
     dfree(g.d_pePtr);
     dfree(g.d_peElem);
-    dfree(g.d_peConn);
-    dfree(g.d_srcBase);
-    dfree(g.d_srcPtr);
-    dfree(g.d_src);
+    dfree(g.d_blobPtr);
+    dfree(g.d_blob);
     g.built = false;
 }
 
@@ -273,7 +322,6 @@ void free_patches(femb_plan* p) {
     for (auto& b : p->blocks) free_program(b.prog);
     dfree(p->d_order);
     dfree(p->d_nbStart);
-    dfree(p->d_nbRow);
     p->patchesBuilt = false;
 }
 
@@ -317,13 +365,14 @@ static int build_order(femb_plan* p, int64_t& launches) {
     return 0;
 }
 
-int build_patches(femb_plan* p, int64_t& launches) {
+static int build_patches_once(femb_plan* p, int64_t& launches) {
     bool any = false;
     for (auto& b : p->blocks) any = any || patch_family_supported(b.nn, b.nq);
     if (!any) return 0;
     const int64_t N = p->numNodes;
     cudaStream_t st = p->stream;
-    if (p->patchNodes <= 0) p->patchNodes = DEFAULT_PATCH_NODES;
+    if (p->patchNodes <= 0) p->patchNodes = DEFAULT_PATCH_NODES_PER_WARP * p->teamWarps;
+    p->patchNodes = std::min(1024, ((p->patchNodes + 3) / 4) * 4);  // multiple of 4: a patch's slice of the permuted BC mask is fetched 4 bytes at a time
     const int PN = p->patchNodes;
     p->numPatches = (N + PN - 1) / PN;
     const int64_t NP = p->numPatches;
@@ -341,18 +390,15 @@ int build_patches(femb_plan* p, int64_t& launches) {
     k_deg_perm<<<grid_for(N, 256), 256, 0, st>>>(p->d_order, p->d_nrowptr, N, d_degPerm);
     launches++;
     TRY(exclusive_scan(d_degPerm, p->d_nbStart, N, st, launches));
-    CUDA_TRY(cudaMalloc(&p->d_nbRow, std::max<int64_t>(p->nnzNode, 1) * sizeof(uint16_t)));
-    k_nb_row<<<grid_for(N, 256), 256, 0, st>>>(N, PN, p->d_nbStart, p->d_nbRow);
-    launches++;
     cudaFree(d_degPerm);
 
-    int *d_count = nullptr, *d_cursor = nullptr, *d_cnt = nullptr, *d_srcPtrG = nullptr;
+    int *d_count = nullptr, *d_cursor = nullptr, *d_nHalo = nullptr, *d_units = nullptr;
     CUDA_TRY(cudaMalloc(&d_count, (NP + 1) * sizeof(int)));
     CUDA_TRY(cudaMalloc(&d_cursor, (NP + 1) * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d_cnt, (p->nnzNode + 1) * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d_srcPtrG, (p->nnzNode + 2) * sizeof(int)));
-    int* d_flags = nullptr;  // [0] = max elems, [1] = overflow
-    CUDA_TRY(cudaMalloc(&d_flags, 2 * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_nHalo, (NP + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_units, (NP + 1) * sizeof(int)));
+    int* d_flags = nullptr;  // [0] = max elems, [1] = overflow, [2..4] = blob stats (max bytes, max local nodes, overflow)
+    CUDA_TRY(cudaMalloc(&d_flags, 8 * sizeof(int)));
 
     for (auto& b : p->blocks) {
         if (!patch_family_supported(b.nn, b.nq)) continue;
@@ -360,7 +406,7 @@ int build_patches(femb_plan* p, int64_t& launches) {
         const int64_t E = b.numElems;
         CUDA_TRY(cudaMemsetAsync(d_count, 0, (NP + 1) * sizeof(int), st));
         CUDA_TRY(cudaMemsetAsync(d_cursor, 0, (NP + 1) * sizeof(int), st));
-        CUDA_TRY(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(d_flags, 0, 8 * sizeof(int), st));
         k_pe_count<<<grid_for(E, 256), 256, 0, st>>>(b.d_conn, E, b.nn, d_nodePos, PN, d_count);
         launches++;
         CUDA_TRY(cudaMalloc(&g.d_pePtr, (NP + 1) * sizeof(int)));
@@ -370,69 +416,97 @@ int build_patches(femb_plan* p, int64_t& launches) {
         CUDA_TRY(cudaStreamSynchronize(st));
         g.totalElems = totalPE;
         CUDA_TRY(cudaMalloc(&g.d_peElem, std::max(totalPE, 1) * sizeof(int)));
-        CUDA_TRY(cudaMalloc(&g.d_peConn, std::max<int64_t>((int64_t)totalPE * b.nn, 1) * sizeof(int)));
         k_pe_fill<<<grid_for(E, 256), 256, 0, st>>>(b.d_conn, E, b.nn, d_nodePos, PN, g.d_pePtr, d_cursor, g.d_peElem);
         k_pe_sort<<<(unsigned)NP, 256, 0, st>>>(g.d_pePtr, g.d_peElem, d_flags, d_flags + 1);
         launches += 2;
-        int flags[2];
+        int flags[8];
         CUDA_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         g.maxElems = flags[0];
-        const int bits = blk_bits(b.nn);
-        if (flags[1] || g.maxElems > (1 << (15 - bits))) {  // patch too populated for the 16-bit source encoding
+        if (flags[1] || b.nn > 4) {  // patch too populated, or a family without a patch kernel
             free_program(g);
             continue;
         }
-        k_pe_conn<<<(unsigned)NP, 256, 0, st>>>(g.d_pePtr, g.d_peElem, b.d_conn, E, b.nn, g.d_peConn);
-        launches++;
 
-        SrcArgs S;
-        S.N = N;
-        S.PN = PN;
-        S.order = p->d_order;
-        S.nbStart = p->d_nbStart;
-        S.nrowptr = p->d_nrowptr;
-        S.ncols = p->d_ncols;
-        S.adjPtr = p->d_adjPtr;
-        S.adj = p->d_adj;
-        S.elemOffset = b.elemOffset;
-        S.E = E;
-        S.nn = b.nn;
-        S.conn = b.d_conn;
-        S.pePtr = g.d_pePtr;
-        S.peElem = g.d_peElem;
-        S.blkBits = bits;
-        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, (p->nnzNode + 1) * sizeof(int), st));
-        k_sources<false><<<grid_for(N, 128), 128, 0, st>>>(S, d_cnt, nullptr, nullptr);
+        // pack everything a patch needs into one contiguous blob
+        int* d_halo = nullptr;
+        CUDA_TRY(cudaMalloc(&d_halo, std::max<int64_t>((int64_t)totalPE * b.nn, 1) * sizeof(int)));
+        BlobArgs B;
+        B.N = N;
+        B.PN = PN;
+        B.nn = b.nn;
+        B.E = E;
+        B.elemOffset = b.elemOffset;
+        B.order = p->d_order;
+        B.nodePos = d_nodePos;
+        B.nbStart = p->d_nbStart;
+        B.nrowptr = p->d_nrowptr;
+        B.ncols = p->d_ncols;
+        B.conn = b.d_conn;
+        B.pePtr = g.d_pePtr;
+        B.peElem = g.d_peElem;
+        B.adjPtr = p->d_adjPtr;
+        B.adj = p->d_adj;
+        B.halo = d_halo;
+        B.nHalo = d_nHalo;
+        B.units = d_units;
+        B.stats = d_flags + 2;
+        k_blob_halo<<<(unsigned)NP, 256, 0, st>>>(B);
         launches++;
-        TRY(exclusive_scan(d_cnt, d_srcPtrG, p->nnzNode, st, launches));
-        int totalSrc = 0;
-        CUDA_TRY(cudaMemcpyAsync(&totalSrc, d_srcPtrG + p->nnzNode, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMalloc(&g.d_blobPtr, (NP + 1) * sizeof(int)));
+        TRY(exclusive_scan(d_units, g.d_blobPtr, NP, st, launches));
+        int totalUnits = 0;
+        CUDA_TRY(cudaMemcpyAsync(&totalUnits, g.d_blobPtr + NP, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        g.totalSources = totalSrc;
-        CUDA_TRY(cudaMalloc(&g.d_src, std::max(totalSrc, 1) * sizeof(uint16_t)));
-        CUDA_TRY(cudaMalloc(&g.d_srcPtr, (p->nnzNode + NP + 1) * sizeof(uint16_t)));
-        CUDA_TRY(cudaMalloc(&g.d_srcBase, (NP + 1) * sizeof(int)));
-        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, (p->nnzNode + 1) * sizeof(int), st));
-        CUDA_TRY(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
-        k_sources<true><<<grid_for(N, 128), 128, 0, st>>>(S, d_cnt, d_srcPtrG, g.d_src);
-        k_src_ptr16<<<grid_for(N, 256), 256, 0, st>>>(N, PN, NP, p->d_nbStart, d_srcPtrG, g.d_srcPtr, g.d_srcBase, d_flags + 1);
-        launches += 2;
+        if (flags[4]) {
+            cudaFree(d_halo);
+            free_program(g);
+            continue;
+        }
+        g.blobBytes = 16ll * totalUnits;
+        g.maxBlobBytes = flags[2];
+        g.maxLocal = flags[3];
+        g.maxNodeBlocks = flags[5];
+        CUDA_TRY(cudaMalloc(&g.d_blob, std::max<int64_t>(g.blobBytes, 16)));
+        k_blob_fill<<<(unsigned)NP, 256, 0, st>>>(B, g.d_blobPtr, g.d_blob);
+        launches++;
         CUDA_TRY(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaGetLastError());
-        if (flags[1]) {
+        cudaFree(d_halo);
+        dfree(g.d_peElem);
+        if (flags[4]) {
             free_program(g);
             continue;
         }
+        g.maxColours = flags[6];
         g.built = true;
     }
     cudaFree(d_count);
     cudaFree(d_cursor);
-    cudaFree(d_cnt);
-    cudaFree(d_srcPtrG);
+    cudaFree(d_nHalo);
+    cudaFree(d_units);
     cudaFree(d_flags);
     cudaFree(d_nodePos);
     p->patchesBuilt = true;
+    return 0;
+}
+
+// Patches must not hold more elements than a compute warpgroup has threads: shrink the patch size until the
+// most populated patch fits (unless the caller fixed the size).
+int build_patches(femb_plan* p, int64_t& launches) {
+    const bool userFixed = p->patchNodes > 0;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        TRY(build_patches_once(p, launches));
+        int worst = 0;
+        for (auto& b : p->blocks) worst = std::max(worst, b.prog.maxElems);
+        const int target = 32 * p->teamWarps;
+        if (userFixed || worst <= target || p->patchNodes <= 4) return 0;
+        const int next = std::max(4, (int)((int64_t)p->patchNodes * target / worst) / 4 * 4);
+        const int shrunk = (next >= p->patchNodes) ? p->patchNodes - 4 : next;
+        free_patches(p);
+        p->patchNodes = shrunk;
+    }
     return 0;
 }

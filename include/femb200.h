@@ -128,6 +128,10 @@ int femb_assemble_dev(femb_plan* plan, const double* d_coords, const double* d_s
 int femb_plan_profile(femb_plan* plan, int32_t enable);
 int femb_plan_profile_read(femb_plan* plan, double* sumMs, int64_t* count);
 
+/* measurement only: per-CTA cycle counters of the pipeline roles.  enable != 0 / out == NULL switches
+ * the counters on (0 off); out != NULL copies up to `capacity` int64 values (16 per CTA) back. */
+int femb_plan_pipe_stats(femb_plan* plan, int32_t enable, int64_t* out, int64_t capacity);
+
 /* ---- element functions: FEMpyProblem.computeFunction / Element.computeFunction
  * (FEMpy/Problem.py:282-355, FEMpy/Elements/Element.py:163-273).  out: (numElems) or (sum_b E_b*P_b)
  * for FEMB_REDUCE_NONE, blocks concatenated in plan order. */

@@ -242,7 +242,7 @@ def test_full_size_properties(elType, n, label):
     assert np.all(np.diff(K.indptr) > 0) and K.has_sorted_indices
     # symmetry
     D = (K - K.T).tocsr()
-    assert np.abs(D.data).max() < 1e-12 * scale
+    assert D.nnz == 0 or np.abs(D.data).max() < 1e-12 * scale
     # rigid-body modes are in the null space: two translations and the linearised rotation
     for mode in (np.tile([1.0, 0.0], N), np.tile([0.0, 1.0], N), np.stack((-coords[:, 1], coords[:, 0]), axis=1).reshape(-1)):
         assert np.abs(K @ mode).max() < 1e-10 * scale * np.abs(mode).max()
@@ -284,7 +284,7 @@ def _raw_plan(elType, coords, conn, hint=True, patchNodes=None, usePatches=1):
 
 @pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29)])
 @pytest.mark.parametrize("hint", [True, False])
-@pytest.mark.parametrize("patchNodes", [5, 64, 128, 1000])
+@pytest.mark.parametrize("patchNodes", [5, 64, 128, 1000])  # rounded up to a multiple of 16 by the library
 def test_patch_path_matches_scatter_path_and_oracle(elType, n, hint, patchNodes):
     coords, conn = meshes.GENERATORS[elType](n, n - 3)
     N = coords.shape[0]
@@ -298,10 +298,12 @@ def test_patch_path_matches_scatter_path_and_oracle(elType, n, hint, patchNodes)
     bcVal = rng.random(bcDOF.size) * 1e-4
     mat = make_cm(0).material()
     plan = _raw_plan(elType, coords, conn, hint, patchNodes)
-    assert plan.info("patch_path") == 1 and plan.info("patch_nodes") == patchNodes
-    assert plan.info("num_patches") == -(-N // patchNodes)
+    pn = -(-patchNodes // 16) * 16
+    assert plan.info("patch_nodes") == pn and plan.info("num_patches") == -(-N // pn)
+    onPatchPath = plan.info("patch_path") == 1
+    assert onPatchPath or patchNodes == 1000  # very large patches exceed shared memory: scatter path takes over
     K1, R1 = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
-    assert plan.lastLaunches == 1  # one fused kernel: no memset, no residual init, no BC pass
+    assert plan.lastLaunches == (1 if onPatchPath else 3)  # one fused kernel: no memset, no residual init, no BC pass
     plan.setOption("use_patches", 0)
     K0, R0 = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
     assert plan.lastLaunches == 3
