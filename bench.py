@@ -191,13 +191,13 @@ def run_ours(args, rank, world, local_rank):
     N_, dN, w = el.tables()
     t0 = time.perf_counter()
     plan.setLocalityHint(wl["coords"])
+    plan.setOption("assembly_path", {"scatter": 0, "patch": 1}[args.path])
     plan.setOption("team_warps", args.team_warps)
     if args.patch_nodes:
         plan.setOption("patch_nodes", args.patch_nodes)
     plan.addBlock(N_, dN, w, wl["conn"][elType])
     plan.finalize()
     plan_wall_ms = 1e3 * (time.perf_counter() - t0)
-    plan.setOption("use_patches", 0 if args.scatter else 1)
     plan.setBCs(wl["bcDOF"], wl["bcVal"])
     nnz, numDOF, numEl = plan.nnz, plan.numDOF, plan.numElements
 
@@ -246,7 +246,8 @@ def run_ours(args, rank, world, local_rank):
     kernel_ms = kernel_ms_sum / max(kernel_calls, 1)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_assemble_pipe (persistent, independent self-prefetching warp teams: cp.async.bulk program blobs, FP64 K_e/R_e in registers, coloured shared-memory scatter, streaming write-out; BCs and loads fused)" if plan.info("patch_path") else "k_assemble_sym (fused K_e/R_e evaluation + RED.F64 scatter)", "kernel_ms": kernel_ms,
+                "traffic": None, "kernel": {"patch": "k_assemble_pipe (persistent self-prefetching warp teams over node patches)",
+                           "scatter": "k_assemble_sym (fused K_e/R_e evaluation + RED.F64 scatter)"}[args.path], "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_element": alg_bytes / numEl,
                 "peak_source": peak_src, "step_frac_of_roofline": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
 
@@ -282,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step), "clocks": clocks,
         "plan_build": {"device_ms": plan.buildMs, "wall_ms": plan_wall_ms},
-        "path": {"write_once_patches": plan.info("patch_path"), "patch_nodes": plan.info("patch_nodes"), "team_warps": plan.info("team_warps"), "num_patches": plan.info("num_patches"),
+        "path": {"assembly_path": args.path, "write_once_patches": plan.info("patch_path"), "patch_nodes": plan.info("patch_nodes"), "team_warps": plan.info("team_warps"), "num_patches": plan.info("num_patches"),
                  "patch_elems_total": plan.info("patch_elems_total"), "patch_elems_max": plan.info("patch_elems_max"),
                  "patch_colours_max": plan.info("patch_colours_max"), "patch_blob_bytes": plan.info("patch_blob_bytes")},
     }  # fmt: skip
@@ -303,7 +304,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--patch-nodes", type=int, default=0, help="owned nodes per patch (0 = library default)")
     ap.add_argument("--team-warps", type=int, default=2, help="warps sharing a patch in the assembly kernel (1 or 2)")
-    ap.add_argument("--scatter", action="store_true", help="use the slot-map scatter kernels (FP64 atomics) instead of patches")
+    ap.add_argument("--path", default="patch", choices=["patch", "scatter"],
+                    help="assembly path: write-once patch pipeline (default) or slot-map scatter with FP64 atomics")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -153,14 +153,19 @@ static int launch_pipe(const femb_plan* p, const BlockData& b, const DMat& D, pi
     A.offTeams = S.offTeams;
     static int configured = 0;
     if (S.total > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
+        CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
         configured = S.total;
     }
     static int numSMs = 0;
     if (!numSMs) CUDA_TRY(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, p->device));
     const int64_t wanted = (p->numPatches + numTeams - 1) / numTeams;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(wanted, numSMs));
-    pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM><<<grid, pipe::THREADS, S.total, st>>>(tb, D, A);
+    if (A.stats && !NL && WK && WR) {  // measurement build of the headline variant only
+        CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
+        pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, true><<<grid, pipe::THREADS, S.total, st>>>(tb, D, A);
+        return 0;
+    }
+    pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, false><<<grid, pipe::THREADS, S.total, st>>>(tb, D, A);
     return 0;
 }
 
@@ -188,8 +193,8 @@ static int launch_pipe_team(const femb_plan* p, const BlockData& b, const DMat& 
     return launch_pipe_variant<NN, NQ, 2>(p, b, D, A, nl, wk, wr, st);
 }
 
-static bool patch_path_available(const femb_plan* p, bool wk, bool /*wr*/) {
-    if (!p->usePatch || !p->patchesBuilt) return false;
+bool patch_path_available(const femb_plan* p, bool wk, bool /*wr*/) {
+    if (p->usePatch != 1 || !p->patchesBuilt) return false;
     const int numTeams = pipe::WARPS / p->teamWarps;
     for (auto& b : p->blocks) {
         if (!b.prog.built) return false;
@@ -199,6 +204,7 @@ static bool patch_path_available(const femb_plan* p, bool wk, bool /*wr*/) {
     }
     return true;
 }
+
 
 template <int NN, int NQ, bool ROW, bool NL, bool WK, bool WR>
 static void launch_assemble(const BlockData& b, const DMat& D, const AsmArgs& A, cudaStream_t st) {

@@ -132,7 +132,7 @@ __device__ __forceinline__ int bc_find(const int* __restrict__ bcDof, int n, int
     return lo;
 }
 
-template <int NN, int NQ, bool NL, bool WK, bool WR, int TEAM>
+template <int NN, int NQ, bool NL, bool WK, bool WR, int TEAM, bool TIMED>
 __global__ void __launch_bounds__(THREADS, 1) k_assemble_pipe(const __grid_constant__ femb::Tables<NN, NQ> tb,
                                                               const femb::DMat D, const Args A) {
     using namespace femb;
@@ -166,11 +166,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_assemble_pipe(const __grid_const
     const int n = (slot < A.numPatches) ? (int)((A.numPatches - slot + step - 1) / step) : 0;
     const bool haveMask = A.maskPerm != nullptr;
 
-    auto issue_blob = [&](int k) {  // one thread: bulk copy of patch k's blob into stage k % NI
-        const long long p = slot + (long long)k * step;
-        const uint32_t bytes = 16u * (uint32_t)(A.blobPtr[p + 1] - A.blobPtr[p]);
+    auto issue_blob = [&](int k, int begin, int end) {  // one thread: bulk copy of patch k's blob into stage k % NI
+        const uint32_t bytes = 16u * (uint32_t)(end - begin);
         mbar_arrive_expect_tx(&blobBar[k % NI], bytes);
-        bulk_g2s(teamSmem + (k % NI) * A.inStride, A.blob + 16ll * A.blobPtr[p], bytes, &blobBar[k % NI]);
+        bulk_g2s(teamSmem + (k % NI) * A.inStride, A.blob + 16ll * begin, bytes, &blobBar[k % NI]);
+    };
+    auto blob_range = [&](int k, int& begin, int& end) {  // plain loads, consumed an iteration later
+        const long long p = slot + (long long)k * step;
+        begin = (k < n) ? __ldg(A.blobPtr + p) : 0;
+        end = (k < n) ? __ldg(A.blobPtr + p + 1) : 0;
     };
     auto issue_gathers = [&](int k) {  // whole team: per-node / per-element inputs of patch k (blob must have landed)
         unsigned char* in = teamSmem + (k % NI) * A.inStride;
@@ -198,14 +202,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_assemble_pipe(const __grid_const
     };
 
     // ---- prologue: blobs of patches 0 and 1 in flight, gathers of patch 0 issued -------------------------------
+    int nextBegin = 0, nextEnd = 0;  // blob range of patch k + 2, loaded while patch k - 1 is processed
     if (tid == 0) {
-        if (n > 0) issue_blob(0);
-        if (n > 1) issue_blob(1);
+        int b0, e0, b1, e1;
+        blob_range(0, b0, e0);
+        blob_range(1, b1, e1);
+        if (n > 0) issue_blob(0, b0, e0);
+        if (n > 1) issue_blob(1, b1, e1);
+        blob_range(2, nextBegin, nextEnd);
     }
     if (n > 0) issue_gathers(0);
 
     long long cWait = 0, cCompute = 0, cScatter = 0, cOut = 0;
-    const bool timed = A.stats && tid == 0 && team < 2;
+    const bool timed = TIMED && A.stats && tid == 0 && team < 2;
     const long long tStart = clock64();
 
     for (int k = 0; k < n; ++k) {
@@ -213,9 +222,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_assemble_pipe(const __grid_const
         unsigned char* in = teamSmem + (k % NI) * A.inStride;
         cp_async_wait_all();     // this thread's share of the gathers of patch k
         team_sync<TEAM>(team);   // ... everyone's; also: the previous write-out no longer reads acc / stage (k-1) % NI
-        if (k + 2 < n && tid == 0) {
-            fence_proxy_async();  // generic-proxy reads of stage (k-1) % NI are done before the bulk engine overwrites it
-            issue_blob(k + 2);
+        if (tid == 0) {
+            if (k + 2 < n) {
+                fence_proxy_async();  // generic-proxy reads of stage (k-1) % NI are done before the bulk engine overwrites it
+                issue_blob(k + 2, nextBegin, nextEnd);
+            }
+            blob_range(k + 3, nextBegin, nextEnd);
         }
         if (k + 1 < n) issue_gathers(k + 1);
         if (timed) { const long long c1 = clock64(); cWait += c1 - c0; c0 = c1; }
@@ -245,9 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_assemble_pipe(const __grid_const
         const bool active = t < ne;
         double Kd[NN][3], Ko[NN * (NN - 1) / 2 + 1][4], Re[NN][2];
         int ln[NN];
-        ElemInfo info;
         if (active) {
-            info = einfo[t];
             double x[NN], y[NN], ux[NN], uy[NN];
 #pragma unroll
             for (int a = 0; a < NN; ++a) {
@@ -298,27 +308,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_assemble_pipe(const __grid_const
             }
         } else {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) info.colour[a] = 0xff;
-#pragma unroll
             for (int a = 0; a < NN; ++a) ln[a] = 0;
         }
         team_sync<TEAM>(team);  // accumulators are zero
         if (timed) { const long long c1 = clock64(); cCompute += c1 - c0; c0 = c1; }
 
         // ---- scatter-add: phase a = local node a, colours make same-phase updates disjoint --------------------------
+        const ElemInfo* myInfo = einfo + (active ? t : 0);
 #pragma unroll
         for (int a = 0; a < NN; ++a) {
             const int numColours = hdr[4 + a];
+            const int colour = active ? myInfo->colour[a] : 0xff;
             for (int c = 0; c < numColours; ++c) {
-                if (info.colour[a] == c && !(A.debug & 4)) {
+                if (colour == c && !(A.debug & 4)) {
                     if (WK) {
-                        double2* row0 = acc2 + info.rowBase[a];
-                        const int deg = info.deg[a];
+                        double2* row0 = acc2 + myInfo->rowBase[a];
+                        const int deg = myInfo->deg[a];
+                        const unsigned kpack = *reinterpret_cast<const unsigned*>(&myInfo->k[a * 4]);
                         double2 s0[NN], s1[NN];
 #pragma unroll
                         for (int b = 0; b < NN; ++b) {  // the NN blocks of a row are distinct: batch the loads
-                            s0[b] = row0[info.k[a * 4 + b]];
-                            s1[b] = row0[info.k[a * 4 + b] + deg];
+                            const int kk = (kpack >> (8 * b)) & 0xff;
+                            s0[b] = row0[kk];
+                            s1[b] = row0[kk + deg];
                         }
 #pragma unroll
                         for (int b = 0; b < NN; ++b) {
@@ -331,8 +343,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_assemble_pipe(const __grid_const
                         }
 #pragma unroll
                         for (int b = 0; b < NN; ++b) {
-                            row0[info.k[a * 4 + b]] = s0[b];
-                            row0[info.k[a * 4 + b] + deg] = s1[b];
+                            const int kk = (kpack >> (8 * b)) & 0xff;
+                            row0[kk] = s0[b];
+                            row0[kk + deg] = s1[b];
                         }
                     }
                     if (WR) {

@@ -163,21 +163,23 @@ __device__ __forceinline__ void element_sym(const Tables<NN, NQ>& tb, const DMat
         }
         if (WANT_K) {
             if (!NL) {
+                // linear model: D is constant over the element, so only the geometric sums
+                //   S00 = sum sc G0a G0b, S01 = sum sc G0a G1b, S10 = sum sc G1a G0b, S11 = sum sc G1a G1b
+                // are accumulated over the Gauss points (4 FMAs per node pair and point); D is applied once, below.
+                // Storage while accumulating: Kd[a] = {S00, S01(=S10), S11}, Ko[pair] = {S00, S01, S10, S11}.
 #pragma unroll
                 for (int a = 0; a < NN; ++a) {
                     const double A0 = G0[a] * sc, A1 = G1[a] * sc;
-                    const double c00 = A0 * D.d00, c01 = A0 * D.d01, c10 = A1 * D.d01, c11 = A1 * D.d11;
-                    const double s0 = A0 * D.d22, s1 = A1 * D.d22;
-                    Kd[a][0] = fma(c00, G0[a], fma(s1, G1[a], Kd[a][0]));
-                    Kd[a][1] = fma(c01, G1[a], fma(s1, G0[a], Kd[a][1]));
-                    Kd[a][2] = fma(c11, G1[a], fma(s0, G0[a], Kd[a][2]));
+                    Kd[a][0] = fma(A0, G0[a], Kd[a][0]);
+                    Kd[a][1] = fma(A0, G1[a], Kd[a][1]);
+                    Kd[a][2] = fma(A1, G1[a], Kd[a][2]);
 #pragma unroll
                     for (int b = a + 1; b < NN; ++b) {
                         double(&k)[4] = Ko[pair_index<NN>(a, b)];
-                        k[0] = fma(c00, G0[b], fma(s1, G1[b], k[0]));
-                        k[1] = fma(c01, G1[b], fma(s1, G0[b], k[1]));
-                        k[2] = fma(c10, G0[b], fma(s0, G1[b], k[2]));
-                        k[3] = fma(c11, G1[b], fma(s0, G0[b], k[3]));
+                        k[0] = fma(A0, G0[b], k[0]);
+                        k[1] = fma(A0, G1[b], k[1]);
+                        k[2] = fma(A1, G0[b], k[2]);
+                        k[3] = fma(A1, G1[b], k[3]);
                     }
                 }
             } else {
@@ -213,6 +215,23 @@ __device__ __forceinline__ void element_sym(const Tables<NN, NQ>& tb, const DMat
                     }
                 }
             }
+        }
+    }
+    if (WANT_K && !NL) {  // K_ab = [[D00 S00 + D22 S11, D01 S01 + D22 S10], [D01 S10 + D22 S01, D11 S11 + D22 S00]]
+#pragma unroll
+        for (int a = 0; a < NN; ++a) {
+            const double s00 = Kd[a][0], s01 = Kd[a][1], s11 = Kd[a][2];
+            Kd[a][0] = fma(D.d00, s00, D.d22 * s11);
+            Kd[a][1] = (D.d01 + D.d22) * s01;
+            Kd[a][2] = fma(D.d11, s11, D.d22 * s00);
+        }
+#pragma unroll
+        for (int q = 0; q < NN * (NN - 1) / 2; ++q) {
+            const double s00 = Ko[q][0], s01 = Ko[q][1], s10 = Ko[q][2], s11 = Ko[q][3];
+            Ko[q][0] = fma(D.d00, s00, D.d22 * s11);
+            Ko[q][1] = fma(D.d01, s01, D.d22 * s10);
+            Ko[q][2] = fma(D.d01, s10, D.d22 * s01);
+            Ko[q][3] = fma(D.d11, s11, D.d22 * s00);
         }
     }
 }

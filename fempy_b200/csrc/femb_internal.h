@@ -101,7 +101,7 @@ struct femb_plan {
     int* d_nbStart = nullptr;    // (numNodes+1) prefix of node degrees in patch order = first node-block of a node
     long long* d_pipeStats = nullptr;  // measurement only
     int debugFlags = 0;                // measurement only
-    int usePatch = 1;            // assembly path selection (1: write-once patches where available)
+    int usePatch = 1;            // assembly path: 1 write-once patch pipeline where available, 0 slot-map scatter with FP64 atomics
     // boundary conditions, de-duplicated on the host with the reference's semantics
     int64_t nBC = 0;
     int* d_bcDof = nullptr;       // sorted ascending
@@ -147,6 +147,9 @@ static inline int need_final(const femb_plan* p, const char* who) {
 
 // out[0..n) = exclusive prefix sums of in[0..n); out[n] = total.  in and out must not alias.  Synchronises.
 int exclusive_scan(const int* d_in, int* d_out, int64_t n, cudaStream_t st, int64_t& launches);
+
+// true when the write-once patch pipeline will run for this plan (assemble.cu)
+bool patch_path_available(const femb_plan* p, bool wk, bool wr);
 
 // patch programs (plan_patch.cu)
 int build_patches(femb_plan* p, int64_t& launches);

@@ -303,7 +303,7 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
     CUDA_TRY(cudaGetLastError());
     cudaFree(d_cand);  // the largest temporary: release it before the patch programs allocate theirs
     d_cand = nullptr;
-    TRY(build_patches(p, launches));
+    if (p->usePatch == 1) TRY(build_patches(p, launches));
     CUDA_TRY(cudaEventRecord(ev1, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
@@ -386,8 +386,10 @@ extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t valu
         if (p->finalized) return fail("femb_plan_set_option: team_warps must be set before finalize");
         if (value != 1 && value != 2) return fail("femb_plan_set_option: team_warps must be 1 or 2");
         p->teamWarps = (int)value;
-    } else if (!strcmp(name, "use_patches")) {
-        p->usePatch = value != 0;
+    } else if (!strcmp(name, "use_patches") || !strcmp(name, "assembly_path")) {
+        if (value < 0 || value > 1) return fail("femb_plan_set_option: assembly_path must be 0 (scatter) or 1 (patch pipeline)");
+        if (value == 1 && p->finalized && !p->patchesBuilt) return fail("femb_plan_set_option: the patch pipeline must be selected before finalize");
+        p->usePatch = (int)value;
     } else if (!strcmp(name, "debug_flags")) {
         p->debugFlags = (int)value;
 
@@ -422,11 +424,8 @@ extern "C" int64_t femb_plan_get_info(const femb_plan* p, const char* name) {
         for (auto& b : p->blocks) t = std::max<int64_t>(t, b.prog.maxColours);
         return t;
     }
-    if (!strcmp(name, "patch_path")) {
-        bool all = p->patchesBuilt && p->usePatch;
-        for (auto& b : p->blocks) all = all && b.prog.built;
-        return all ? 1 : 0;
-    }
+    if (!strcmp(name, "assembly_path")) return p->usePatch;
+    if (!strcmp(name, "patch_path")) return patch_path_available(p, true, true) ? 1 : 0;
     return -1;
 }
 

@@ -108,6 +108,8 @@ class AssemblyPlan:
     def pattern(self):
         """(indptr, indices) int64 of the CSR stiffness pattern; cached."""
         if self._pattern is None:
+            if self.nnz < 0:  # not finalized: let the library say so
+                check(self._lib.femb_plan_pattern(self._h, None, None))
             indptr = np.empty(self.numDOF + 1, dtype=np.int64)
             indices = np.empty(self.nnz, dtype=np.int64)
             check(self._lib.femb_plan_pattern(self._h, iptr(indptr), iptr(indices)))

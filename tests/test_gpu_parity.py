@@ -262,52 +262,49 @@ def test_full_size_properties(elType, n, label):
     np.testing.assert_allclose(p.computeFunction("Mass", "integrate", "sum"), MAT["rho"] * 3.0, rtol=1e-11)
     # idempotence: a second assembly reproduces the first exactly (write-once path: fixed summation order)
     K2 = p._assembleMatrix(np.zeros((N, 2)), applyBCs=False)
-    if elType != "quad9":
-        np.testing.assert_array_equal(K2.data, K.data)
+    np.testing.assert_array_equal(K2.data, K.data)
     assert np.abs(K2.data - K.data).max() < 1e-13 * scale
 
 
-# ---- the two assembly paths: write-once node patches vs slot-map scatter with FP64 atomics ---------------------------
-def _raw_plan(elType, coords, conn, hint=True, patchNodes=None, usePatches=1):
+# ---- the two assembly paths: write-once patch pipeline (default) and slot-map scatter with FP64 atomics ----------------
+PATHS = {"scatter": 0, "patch": 1}
+
+
+def _raw_plan(elType, coords, conn, hint=True, patchNodes=None, path="patch", teamWarps=None):
     el = ELEMENT_FOR[elType]()
     plan = AssemblyPlan(coords.shape[0])
     if hint:
         plan.setLocalityHint(coords)
+    plan.setOption("assembly_path", PATHS[path])
     if patchNodes is not None:
         plan.setOption("patch_nodes", patchNodes)
+    if teamWarps is not None:
+        plan.setOption("team_warps", teamWarps)
     N_, dN, w = el.tables()
     plan.addBlock(N_, dN, w, conn[elType])
     plan.finalize()
-    plan.setOption("use_patches", usePatches)
     return plan
 
 
-@pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29)])
-@pytest.mark.parametrize("hint", [True, False])
-@pytest.mark.parametrize("patchNodes", [5, 64, 128, 1000])  # rounded up to a multiple of 16 by the library
-def test_patch_path_matches_scatter_path_and_oracle(elType, n, hint, patchNodes):
+def _path_case(elType, n, seed=7):
     coords, conn = meshes.GENERATORS[elType](n, n - 3)
     N = coords.shape[0]
     numEl = conn[elType].shape[0]
-    rng = np.random.default_rng(7)
+    rng = np.random.default_rng(seed)
     states = 1e-3 * rng.random((N, 2))
     thick = rng.random(numEl) * 1e-2 + 1e-3
     loads = rng.random(2 * N)
     left = meshes.edge_nodes(coords, x=0.0)
     bcDOF = np.concatenate((2 * left, 2 * left[:3] + 1, 2 * left[:2]))  # with duplicates
     bcVal = rng.random(bcDOF.size) * 1e-4
+    return coords, conn, states, thick, loads, bcDOF, bcVal
+
+
+def _check_against_oracle(plan, elType, case, launchesExpected):
+    coords, conn, states, thick, loads, bcDOF, bcVal = case
     mat = make_cm(0).material()
-    plan = _raw_plan(elType, coords, conn, hint, patchNodes)
-    pn = -(-patchNodes // 16) * 16
-    assert plan.info("patch_nodes") == pn and plan.info("num_patches") == -(-N // pn)
-    onPatchPath = plan.info("patch_path") == 1
-    assert onPatchPath or patchNodes == 1000  # very large patches exceed shared memory: scatter path takes over
     K1, R1 = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
-    assert plan.lastLaunches == (1 if onPatchPath else 3)  # one fused kernel: no memset, no residual init, no BC pass
-    plan.setOption("use_patches", 0)
-    K0, R0 = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
-    assert plan.lastLaunches == 3
-    assert relerr(K1, K0) < 1e-13 and relerr(R1, R0) < 1e-13
+    assert plan.lastLaunches == launchesExpected
     blocks = oracle_blocks(conn)
     Ko = fo.assemble_matrix(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], bcDOF, dropZeros=False)
     Ko.sort_indices()
@@ -317,28 +314,61 @@ def test_patch_path_matches_scatter_path_and_oracle(elType, n, hint, patchNodes)
     np.testing.assert_array_equal(ix, Ko.indices)
     assert relerr(K1, Ko.data) < TOL and relerr(R1, Ro) < TOL
     # K-only and R-only variants, and no BCs
-    plan.setOption("use_patches", 1)
     K2, _ = plan.assemble(coords, states, thick, mat, None, None, False, None, wantR=False)
     _, R2 = plan.assemble(coords, states, thick, mat, None, None, False, loads, wantK=False)
     Kn = fo.assemble_matrix(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], None, dropZeros=False)
     Kn.sort_indices()
     Rn = fo.assemble_residual(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], loads)
     assert relerr(K2, Kn.data) < TOL and relerr(R2, Rn) < TOL
+    return K1, R1
+
+
+@pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29), ("quad9", 14)])
+def test_default_path_matches_scatter_path_and_oracle(elType, n):
+    """default: write-once patch pipeline for the 3/4-node families (1 launch), scatter kernels otherwise"""
+    case = _path_case(elType, n)
+    coords, conn = case[0], case[1]
+    plan = _raw_plan(elType, coords, conn)
+    onPatchPath = plan.info("patch_path") == 1
+    assert onPatchPath == (elType != "quad9")
+    K1, R1 = _check_against_oracle(plan, elType, case, launchesExpected=1 if onPatchPath else 3)
+    plan.setOption("assembly_path", 0)
+    mat = make_cm(0).material()
+    K0, R0 = plan.assemble(coords, case[2], case[3], mat, case[5], case[6], True, case[4])
+    assert plan.lastLaunches == 3
+    assert relerr(K1, K0) < 1e-13 and relerr(R1, R0) < 1e-13
     plan.close()
 
 
-def test_patch_path_is_deterministic():
+@pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29)])
+@pytest.mark.parametrize("hint", [True, False])
+@pytest.mark.parametrize("patchNodes,teamWarps", [(5, 1), (20, 1), (40, 2), (64, 2), (1000, 2)])
+def test_patch_pipeline_matches_oracle(elType, n, hint, patchNodes, teamWarps):
+    """opt-in path: persistent kernel of self-prefetching warp teams over node patches = 1 launch"""
+    case = _path_case(elType, n)
+    plan = _raw_plan(elType, case[0], case[1], hint, patchNodes, path="patch", teamWarps=teamWarps)
+    pn = -(-patchNodes // 4) * 4
+    assert plan.info("patch_nodes") == pn and plan.info("num_patches") == -(-case[0].shape[0] // pn)
+    onPatchPath = plan.info("patch_path") == 1
+    if not onPatchPath:  # patches with more elements than a team has threads fall back to the scatter kernels
+        assert plan.info("patch_elems_max") > 32 * teamWarps
+    _check_against_oracle(plan, elType, case, launchesExpected=1 if onPatchPath else 3)
+    plan.close()
+
+
+@pytest.mark.parametrize("path", ["patch"])
+def test_write_once_path_is_deterministic(path):
     """write-once assembly has a fixed summation order: two runs are bit-identical"""
     coords, conn = meshes.quad4_grid(200, 150)
     N = coords.shape[0]
     states = 1e-3 * np.random.default_rng(0).random((N, 2))
-    plan = _raw_plan("quad", coords, conn)
+    plan = _raw_plan("quad", coords, conn, path=path)
     mat = make_cm(0).material()
     K1, R1 = plan.assemble(coords, states, np.ones(30000), mat, applyBCs=False)
     K2, R2 = plan.assemble(coords, states, np.ones(30000), mat, applyBCs=False)
     np.testing.assert_array_equal(K1, K2)
     np.testing.assert_array_equal(R1, R2)
-    plan2 = _raw_plan("quad", coords, conn)  # a second plan build gives the same program
+    plan2 = _raw_plan("quad", coords, conn, path=path)  # a second plan build gives the same program
     K3, R3 = plan2.assemble(coords, states, np.ones(30000), mat, applyBCs=False)
     np.testing.assert_array_equal(K1, K3)
     np.testing.assert_array_equal(R1, R3)
@@ -347,8 +377,8 @@ def test_patch_path_is_deterministic():
 def test_isolated_nodes_get_minus_load():
     coords = np.array([[0.0, 0.0], [2.0, 0.1], [2.2, 1.0], [0.1, 1.5], [5.0, 5.0], [6.0, 7.0]])
     conn = {"quad": np.array([[0, 1, 2, 3]])}
-    for usePatches in (1, 0):
-        plan = _raw_plan("quad", coords, conn, usePatches=usePatches)
+    for path in ("patch", "scatter"):
+        plan = _raw_plan("quad", coords, conn, path=path)
         loads = np.arange(12.0)
         _, R = plan.assemble(coords, np.zeros((6, 2)), np.ones(1), make_cm(0).material(), applyBCs=False, loads=loads)
         np.testing.assert_allclose(R, -loads, atol=1e-3)  # zero state: R = -loads everywhere
@@ -422,7 +452,7 @@ def test_bad_inputs_raise():
     with pytest.raises(FembError, match="unsupported element family"):
         plan.addBlock(N[:1], dN[:1], w[:1], np.array([[0, 1, 2, 3]]))
     with pytest.raises(FembError, match="not finalized"):
-        plan.nnz and plan.pattern()
+        plan.pattern()
     plan.addBlock(N, dN, w, np.array([[0, 1, 2, 3]]))
     plan.finalize()
     with pytest.raises(ValueError):

@@ -10,6 +10,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 coords, conn = meshes.quad4_grid(n, n)
 N = coords.shape[0]; E = n * n
 plan = AssemblyPlan(N); plan.setLocalityHint(coords); team = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+plan.setOption("assembly_path", 1)
 plan.setOption("team_warps", team)
 if pn: plan.setOption("patch_nodes", pn)
 dbg = int(sys.argv[3]) if len(sys.argv) > 3 else 0
