@@ -477,3 +477,22 @@ def test_problem_level_nonlinear_newton_step():
     Ko.sort_indices()
     Ro = fo.assemble_residual(blocks, coords, states, np.ones(30), 1, MAT["E"], MAT["nu"], None, bcDOF, bcVal, nonlinear=True)
     assert relerr(K.data, Ko.data) < TOL and relerr(R, Ro) < TOL
+
+
+# ---- multi-GPU (needs >= 2 devices; the CPU suite covers the same logic over gloo) ------------------------------------
+def test_multi_gpu_partitioned_assembly_matches_single_gpu():
+    import subprocess
+    import sys
+
+    import torch
+
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (tests/test_dist_cpu.py covers the partition/exchange logic over gloo)")
+    from util import ROOT
+    import os
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tools", "check_multi_gpu.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "MULTI_GPU_PARITY_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
