@@ -1,5 +1,6 @@
 // Fused K + R assembly kernels and their C ABI.
 #include "assemble_pipe.cuh"
+#include "assemble_rows.cuh"
 #include "femb_internal.h"
 
 using namespace femb;
@@ -139,7 +140,7 @@ static constexpr int PIPE_SMEM_LIMIT = 227 * 1024;
 template <int NN, int NQ, bool NL, bool WK, bool WR, int TEAM>
 static int launch_pipe(const femb_plan* p, const BlockData& b, const DMat& D, pipe::Args A, cudaStream_t st) {
     const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
-    constexpr int numTeams = pipe::WARPS / TEAM;
+    constexpr int numTeams = pipe::Cfg<TEAM>::NUM_TEAMS;
     const pipe::SmemPlan S = pipe::smem_plan(numTeams, b.prog.maxBlobBytes, b.prog.maxLocal, b.prog.maxElems, b.prog.maxNodeBlocks, p->patchNodes, WK);
     A.inStride = S.inStride;
     A.offX = S.offX;
@@ -162,10 +163,43 @@ static int launch_pipe(const femb_plan* p, const BlockData& b, const DMat& D, pi
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(wanted, numSMs));
     if (A.stats && !NL && WK && WR) {  // measurement build of the headline variant only
         CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
-        pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, true><<<grid, pipe::THREADS, S.total, st>>>(tb, D, A);
+        pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, true><<<grid, pipe::Cfg<TEAM>::THREADS, S.total, st>>>(tb, D, A);
         return 0;
     }
-    pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, false><<<grid, pipe::THREADS, S.total, st>>>(tb, D, A);
+    pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, false><<<grid, pipe::Cfg<TEAM>::THREADS, S.total, st>>>(tb, D, A);
+    return 0;
+}
+
+template <int NN, int NQ, bool WR, int TEAM>
+static int launch_pipe2(const femb_plan* p, const BlockData& b, const DMat& D, pipe::Args A, cudaStream_t st) {
+    const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
+    constexpr int numTeams = pipe::Cfg2<TEAM>::NUM_TEAMS;
+    const pipe::SmemPlan S = pipe::smem_plan(numTeams, b.prog.maxBlobBytes, b.prog.maxLocal, b.prog.maxElems, b.prog.maxNodeBlocks, p->patchNodes, true);
+    A.inStride = S.inStride;
+    A.offX = S.offX;
+    A.offU = S.offU;
+    A.offL = S.offL;
+    A.offTH = S.offTH;
+    A.offMask = S.offMask;
+    A.accStride = S.accStride;
+    A.offRacc = S.offRacc;
+    A.teamStride = S.teamStride;
+    A.offTeams = S.offTeams;
+    static int numSMs = 0;
+    if (!numSMs) CUDA_TRY(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, p->device));
+    const int64_t wanted = (p->numPatches + numTeams - 1) / numTeams;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(wanted, numSMs));
+    if (A.stats && WR) {
+        CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe2<NN, NQ, WR, TEAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
+        pipe::k_assemble_pipe2<NN, NQ, WR, TEAM, true><<<grid, pipe::Cfg2<TEAM>::THREADS, S.total, st>>>(tb, D, A);
+        return 0;
+    }
+    static int configured = 0;
+    if (S.total > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe2<NN, NQ, WR, TEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
+        configured = S.total;
+    }
+    pipe::k_assemble_pipe2<NN, NQ, WR, TEAM, false><<<grid, pipe::Cfg2<TEAM>::THREADS, S.total, st>>>(tb, D, A);
     return 0;
 }
 
@@ -189,22 +223,69 @@ static int launch_pipe_variant(const femb_plan* p, const BlockData& b, const DMa
 template <int NN, int NQ>
 static int launch_pipe_team(const femb_plan* p, const BlockData& b, const DMat& D, const pipe::Args& A, bool nl, bool wk, bool wr,
                             cudaStream_t st) {
+    if constexpr (NN <= 4) {
+        if (p->splitElements && !nl && wk && p->teamWarps >= 2) {  // half an element per thread (linear model, K wanted)
+            if (p->teamWarps == 4) return wr ? launch_pipe2<NN, NQ, true, 4>(p, b, D, A, st) : launch_pipe2<NN, NQ, false, 4>(p, b, D, A, st);
+            return wr ? launch_pipe2<NN, NQ, true, 2>(p, b, D, A, st) : launch_pipe2<NN, NQ, false, 2>(p, b, D, A, st);
+        }
+    }
     if (p->teamWarps == 1) return launch_pipe_variant<NN, NQ, 1>(p, b, D, A, nl, wk, wr, st);
+    if (p->teamWarps == 4) return launch_pipe_variant<NN, NQ, 4>(p, b, D, A, nl, wk, wr, st);
     return launch_pipe_variant<NN, NQ, 2>(p, b, D, A, nl, wk, wr, st);
 }
 
 bool patch_path_available(const femb_plan* p, bool wk, bool /*wr*/) {
     if (p->usePatch != 1 || !p->patchesBuilt) return false;
-    const int numTeams = pipe::WARPS / p->teamWarps;
+    // worst case over the kernel variants that may run (element-per-thread and half-element-per-thread)
+    const int numTeams = std::max((p->teamWarps == 4) ? 3 : 10 / p->teamWarps, p->splitElements ? (16 / p->teamWarps) : 0);
+    const int elemCap = (p->splitElements && p->teamWarps >= 2) ? 16 * p->teamWarps : 32 * p->teamWarps;
     for (auto& b : p->blocks) {
         if (!b.prog.built) return false;
-        if (b.nn > 4 || b.prog.maxElems > 32 * p->teamWarps) return false;
+        if (b.nn > 4 || b.prog.maxElems > elemCap) return false;
         const int total = pipe::smem_plan(numTeams, b.prog.maxBlobBytes, b.prog.maxLocal, b.prog.maxElems, b.prog.maxNodeBlocks, p->patchNodes, wk).total;
         if (total > PIPE_SMEM_LIMIT) return false;
     }
     return true;
 }
 
+
+
+// =============================================================================================
+// row-owner path (assemble_rows.cuh): one thread per node row, redundant geometry, no atomics / barriers
+// =============================================================================================
+bool rows_path_available(const femb_plan* p) {
+    return p->usePatch == 2 && p->blocks.size() == 1 && p->blocks[0].nn <= 4 && p->d_connE && p->maxDeg <= rows::MAXD;
+}
+
+template <int NN, int NQ, bool NL, bool WK, bool WR>
+static int launch_rows(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
+    const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
+    const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * sizeof(double2);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    rows::k_assemble_rows<NN, NQ, NL, WK, WR><<<grid_for(p->numNodes, rows::BLOCK), rows::BLOCK, smem, st>>>(tb, D, A);
+    return 0;
+}
+
+template <int NN, int NQ>
+static int launch_rows_variant(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, bool nl, bool wk,
+                               bool wr, cudaStream_t st) {
+    if constexpr (NN <= 4) {
+        if (!nl) {
+            if (wk && wr) return launch_rows<NN, NQ, false, true, true>(p, b, D, A, st);
+            if (wk) return launch_rows<NN, NQ, false, true, false>(p, b, D, A, st);
+            return launch_rows<NN, NQ, false, false, true>(p, b, D, A, st);
+        }
+        if (wk && wr) return launch_rows<NN, NQ, true, true, true>(p, b, D, A, st);
+        if (wk) return launch_rows<NN, NQ, true, true, false>(p, b, D, A, st);
+        return launch_rows<NN, NQ, true, false, true>(p, b, D, A, st);
+    } else {
+        return fail("no row-owner kernel for %d-node elements", NN);
+    }
+}
 
 template <int NN, int NQ, bool ROW, bool NL, bool WK, bool WR>
 static void launch_assemble(const BlockData& b, const DMat& D, const AsmArgs& A, cudaStream_t st) {
@@ -249,10 +330,11 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
     const DMat D = make_dmat(*mat);
     const int64_t numDOF = femb_plan_num_dof(p), nnz = femb_plan_nnz(p);
     int64_t launches = 0;
-    const bool patchPath = patch_path_available(p, wk, wr);
+    const bool rowsPath = rows_path_available(p);
+    const bool patchPath = !rowsPath && patch_path_available(p, wk, wr);
     const bool multi = p->blocks.size() > 1;
     const bool bcs = applyBCs && p->nBC > 0;
-    if (!patchPath || multi) {  // scatter path, or several element types summing into the same rows
+    if (!(patchPath || rowsPath) || multi) {  // scatter path, or several element types summing into the same rows
         if (wk) CUDA_TRY(cudaMemsetAsync(d_K, 0, nnz * sizeof(double), st));
         if (wr) {
             k_init_residual<<<grid_for(numDOF, 256), 256, 0, st>>>(d_R, d_loads, numDOF);
@@ -271,7 +353,28 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
         CUDA_TRY(cudaEventRecord(ev->first, st));
     }
     for (auto& b : p->blocks) {
-        if (patchPath) {
+        if (rowsPath) {
+            rows::Args A;
+            A.numNodes = p->numNodes;
+            A.nrowptr = p->d_nrowptr;
+            A.ncols = p->d_ncols;
+            A.adjPtr = p->d_adjPtr;
+            A.adj = p->d_adj;
+            A.connE = p->d_connE;
+            A.coords = (const double2*)d_coords;
+            A.states = (const double2*)d_states;
+            A.thick = d_thick;
+            A.loads = (const double2*)d_loads;
+            A.bcMask = bcs ? p->d_bcMask : nullptr;
+            A.bcDof = p->d_bcDof;
+            A.bcVal = p->d_bcVal;
+            A.bcCount = p->d_bcCount;
+            A.nBC = (int)p->nBC;
+            A.maxDeg = p->maxDeg;
+            A.K = d_K;
+            A.R = d_R;
+            FEMB_DISPATCH_FAMILY(b.nn, b.nq, TRY((launch_rows_variant<NN, NQ>(p, b, D, A, mat->nonlinear != 0, wk, wr, st))));
+        } else if (patchPath) {
             pipe::Args A;
             A.numPatches = p->numPatches;
             A.PN = p->patchNodes;
@@ -309,7 +412,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
         launches++;
     }
     if (ev) CUDA_TRY(cudaEventRecord(ev->second, st));
-    if (bcs && (!patchPath || multi)) {
+    if (bcs && (!(patchPath || rowsPath) || multi)) {
         k_apply_bcs<<<grid_for(p->nBC * 32, 128), 128, 0, st>>>(p->nBC, p->d_bcDof, p->d_bcVal, p->d_bcCount, p->d_nrowptr,
                                                                p->d_ncols, d_states, wk ? d_K : nullptr,
                                                                wr ? d_R : nullptr);

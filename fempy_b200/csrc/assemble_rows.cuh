@@ -1,0 +1,235 @@
+// Row-owner assembly (sm_100a): one thread per node row, no atomics, no barriers, no inter-thread accumulation.
+//
+// Thread i owns the two DOF rows of node i.  It walks the node's (sorted) element adjacency; for every adjacent
+// element it re-evaluates the element geometry at the Gauss points and forms ONLY the node-row strip of K_e that
+// belongs to node i (4 node-pair blocks for a quad) plus its residual pair, and adds them into a private row of
+// accumulators in shared memory.  The element geometry is therefore evaluated once per (node, element) corner --
+// about 2.7x the minimal FP64 work -- which buys: independent threads at high occupancy (the thread never holds a
+// whole K_e), a fixed summation order (bit-reproducible), and every CSR value / residual entry written exactly once.
+//
+// Shared-memory accumulators: acc[m][t] (double2), m = k for DOF row 0 and deg + k for DOF row 1 of the thread's
+// node, stored at m*BLOCK + ((t + m) & (BLOCK-1)).  The swizzle keeps the read-modify-writes conflict-free when the
+// lanes of a warp use the same slot pattern (structured meshes) and makes the final row-by-row copy conflict-free:
+// the lanes of a warp then stream one node's 32*deg-byte run (both DOF rows are contiguous in the CSR values) per step.
+#pragma once
+#include "femb_internal.h"
+
+namespace rows {
+
+static constexpr int BLOCK = 128;
+static constexpr int MAXD = 12;  // largest node degree (neighbours incl. itself) this kernel handles
+
+struct Args {
+    long long numNodes;
+    const int* nrowptr;
+    const int* ncols;
+    const int* adjPtr;
+    const int* adj;          // element ids (single element block)
+    const int4* connE;       // element-major connectivity, padded to 4 nodes
+    const double2* coords;
+    const double2* states;
+    const double* thick;
+    const double2* loads;           // may be NULL
+    const unsigned char* bcMask;    // NULL: no BCs
+    const int* bcDof;
+    const double* bcVal;
+    const double* bcCount;
+    int nBC;
+    int maxDeg;
+    double* K;
+    double* R;
+};
+
+__device__ __forceinline__ void st_stream(double2* p, const double2 v) {  // K is written once and not re-read here
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y));
+}
+
+__device__ __forceinline__ int bc_find(const int* __restrict__ bcDof, int n, int dof) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (bcDof[mid] < dof) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int NN, int NQ, bool NL, bool WK, bool WR>
+__global__ void __launch_bounds__(BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const femb::DMat D,
+                                                        const Args A) {
+    using namespace femb;
+    static_assert(NN <= 4, "element-major connectivity holds at most 4 nodes");
+    extern __shared__ double2 acc[];  // [2*maxDeg][BLOCK], swizzled
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long i = (long long)blockIdx.x * BLOCK + tid;
+    const bool valid = i < A.numNodes;
+    const int off = valid ? __ldg(A.nrowptr + i) : 0;
+    const int deg = valid ? __ldg(A.nrowptr + i + 1) - off : 0;
+    auto slot = [&](int m) -> double2& { return acc[m * BLOCK + ((tid + m) & (BLOCK - 1))]; };
+
+    // sorted neighbour list of the row (positions of the element's nodes are found by counting smaller entries)
+    int cols[MAXD];
+#pragma unroll
+    for (int k = 0; k < MAXD; ++k) cols[k] = (k < deg) ? __ldg(A.ncols + off + k) : 0x7fffffff;
+    if (WK)
+        for (int m = 0; m < 2 * deg; ++m) slot(m) = make_double2(0.0, 0.0);
+    double rx = 0.0, ry = 0.0;
+
+    const int c0 = valid ? __ldg(A.adjPtr + i) : 0, c1 = valid ? __ldg(A.adjPtr + i + 1) : 0;
+    for (int c = c0; c < c1; ++c) {
+        const int e = __ldg(A.adj + c);
+        const int4 cn = __ldg(A.connE + e);
+        const int node[4] = {cn.x, cn.y, cn.z, cn.w};
+        double x[NN], y[NN], ux[NN], uy[NN];
+        int a = 0;
+#pragma unroll
+        for (int b = 0; b < NN; ++b) {
+            const double2 p = __ldg(A.coords + node[b]);
+            x[b] = p.x;
+            y[b] = p.y;
+            if (NL || WR) {
+                const double2 q = __ldg(A.states + node[b]);
+                ux[b] = q.x;
+                uy[b] = q.y;
+            } else {
+                ux[b] = uy[b] = 0.0;
+            }
+            a = (node[b] == (int)i) ? b : a;
+        }
+        const double theta = __ldg(A.thick + e);
+
+        // node-row strip of K_e: blocks (a, b), b = 0..NN-1, and the residual pair of node a
+        double Kr[NN][4];
+        double ra0 = 0.0, ra1 = 0.0;
+#pragma unroll
+        for (int b = 0; b < NN; ++b) Kr[b][0] = Kr[b][1] = Kr[b][2] = Kr[b][3] = 0.0;
+#pragma unroll
+        for (int p = 0; p < NQ; ++p) {
+            double G0[NN], G1[NN];
+            const double det = point_gradients<NN, NQ>(tb, p, x, y, G0, G1);
+            const double sc = tb.w[p] * det * theta;
+            double g0 = 0.0, g1 = 0.0;  // gradient of "my" shape function: runtime index -> selects, no dynamic registers
+#pragma unroll
+            for (int b = 0; b < NN; ++b) {
+                g0 = (b == a) ? G0[b] : g0;
+                g1 = (b == a) ? G1[b] : g1;
+            }
+            if (!NL) {
+                // linear model: accumulate the geometric sums sc * G_d,a * G_D,b; D is applied once below
+                if (WK || WR) {
+                    const double A0 = g0 * sc, A1 = g1 * sc;
+#pragma unroll
+                    for (int b = 0; b < NN; ++b) {
+                        Kr[b][0] = fma(A0, G0[b], Kr[b][0]);
+                        Kr[b][1] = fma(A0, G1[b], Kr[b][1]);
+                        Kr[b][2] = fma(A1, G0[b], Kr[b][2]);
+                        Kr[b][3] = fma(A1, G1[b], Kr[b][3]);
+                    }
+                }
+            } else {
+                double u[2][2];
+                state_gradient<NN>(G0, G1, ux, uy, u);
+                double Ba[3][2];
+                bmat<true>(g0, g1, u, Ba);
+                if (WR) {
+                    double sig[3];
+                    stresses<true>(D, u, sig);
+                    ra0 = fma(sc, Ba[0][0] * sig[0] + Ba[1][0] * sig[1] + Ba[2][0] * sig[2], ra0);
+                    ra1 = fma(sc, Ba[0][1] * sig[0] + Ba[1][1] * sig[1] + Ba[2][1] * sig[2], ra1);
+                }
+                if (WK) {
+                    double DBa[3][2];
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        DBa[0][s] = sc * (D.d00 * Ba[0][s] + D.d01 * Ba[1][s]);
+                        DBa[1][s] = sc * (D.d01 * Ba[0][s] + D.d11 * Ba[1][s]);
+                        DBa[2][s] = sc * (D.d22 * Ba[2][s]);
+                    }
+#pragma unroll
+                    for (int b = 0; b < NN; ++b) {
+                        double Bb[3][2];
+                        bmat<true>(G0[b], G1[b], u, Bb);
+#pragma unroll
+                        for (int s = 0; s < 2; ++s)
+#pragma unroll
+                            for (int S = 0; S < 2; ++S)
+                                Kr[b][2 * s + S] += DBa[0][s] * Bb[0][S] + DBa[1][s] * Bb[1][S] + DBa[2][s] * Bb[2][S];
+                    }
+                }
+            }
+        }
+        if (!NL) {  // [[D00 S00 + D22 S11, D01 S01 + D22 S10], [D01 S10 + D22 S01, D11 S11 + D22 S00]]
+#pragma unroll
+            for (int b = 0; b < NN; ++b) {
+                const double s00 = Kr[b][0], s01 = Kr[b][1], s10 = Kr[b][2], s11 = Kr[b][3];
+                Kr[b][0] = fma(D.d00, s00, D.d22 * s11);
+                Kr[b][1] = fma(D.d01, s01, D.d22 * s10);
+                Kr[b][2] = fma(D.d01, s10, D.d22 * s01);
+                Kr[b][3] = fma(D.d11, s11, D.d22 * s00);
+                if (WR) {  // R_a = sum_b K_ab q_b
+                    ra0 = fma(Kr[b][0], ux[b], fma(Kr[b][1], uy[b], ra0));
+                    ra1 = fma(Kr[b][2], ux[b], fma(Kr[b][3], uy[b], ra1));
+                }
+            }
+        }
+        rx += ra0;
+        ry += ra1;
+        if (WK) {
+#pragma unroll
+            for (int b = 0; b < NN; ++b) {
+                int kk = 0;  // position of node b in my sorted row = number of smaller column nodes
+#pragma unroll
+                for (int k = 0; k < MAXD; ++k) kk += (cols[k] < node[b]) ? 1 : 0;
+                double2& s0 = slot(kk);
+                double2& s1 = slot(deg + kk);
+                const double2 o0 = s0, o1 = s1;
+                s0 = make_double2(o0.x + Kr[b][0], o0.y + Kr[b][1]);
+                s1 = make_double2(o1.x + Kr[b][2], o1.y + Kr[b][3]);
+            }
+        }
+    }
+
+    // ---- BC rows, loads, residual ---------------------------------------------------------------------------
+    const unsigned m = (valid && A.bcMask) ? A.bcMask[i] : 0u;
+    if (m && WK) {  // constrained rows: zeros, occurrence count on the diagonal (AssemblyUtils.py:55-60)
+        int diagK = 0;
+#pragma unroll
+        for (int k = 0; k < MAXD; ++k) diagK += (cols[k] < (int)i) ? 1 : 0;
+        for (int r = 0; r < 2; ++r) {
+            if (m & (1u << r)) {
+                for (int k = 0; k < deg; ++k) slot(r * deg + k) = make_double2(0.0, 0.0);
+                const double cnt = A.bcCount[bc_find(A.bcDof, A.nBC, 2 * (int)i + r)];
+                slot(r * deg + diagK) = r ? make_double2(0.0, cnt) : make_double2(cnt, 0.0);
+            }
+        }
+    }
+    if (WR && valid) {
+        if (A.loads) {  // R = scatter(R_e) - loads (Problem.py:653)
+            const double2 f = __ldg(A.loads + i);
+            rx -= f.x;
+            ry -= f.y;
+        }
+        if (m) {  // R[bc] = u - c (AssemblyUtils.py:93)
+            const double2 u = __ldg(A.states + i);
+            if (m & 1u) rx = u.x - A.bcVal[bc_find(A.bcDof, A.nBC, 2 * (int)i)];
+            if (m & 2u) ry = u.y - A.bcVal[bc_find(A.bcDof, A.nBC, 2 * (int)i + 1)];
+        }
+        reinterpret_cast<double2*>(A.R)[i] = make_double2(rx, ry);
+    }
+
+    // ---- write-out: the lanes of a warp stream one node's contiguous 32*deg-byte run per step -------------------
+    if (WK) {
+        __syncwarp();
+        double2* K2 = reinterpret_cast<double2*>(A.K);
+        const int wbase = tid - lane;
+        for (int r = 0; r < 32; ++r) {
+            const int offR = __shfl_sync(0xffffffffu, off, r);
+            const int n2 = 2 * __shfl_sync(0xffffffffu, deg, r);
+            for (int mm = lane; mm < n2; mm += 32) {
+                const double2 v = acc[mm * BLOCK + ((wbase + r + mm) & (BLOCK - 1))];
+                st_stream(K2 + 2ll * offR + mm, v);
+            }
+        }
+    }
+}
+
+}  // namespace rows

@@ -94,14 +94,17 @@ struct femb_plan {
     // node patches (shared by all blocks)
     bool patchesBuilt = false;
     int patchNodes = 0;          // owned nodes per patch
-    int teamWarps = 2;           // warps that share a patch in the assembly kernel (1 or 2): a patch holds <= 32*teamWarps elements
+    int splitElements = 1;       // 1: linear K assemblies put half an element on each thread (patches hold <= 16*teamWarps elements)
+    int teamWarps = 4;           // warps that share a patch in the assembly kernel (1 or 2): a patch holds <= 32*teamWarps elements
     int64_t numPatches = 0;
     double* d_hintCoords = nullptr;  // optional locality hint (node coordinates at plan time)
     int* d_order = nullptr;      // patch order: owned nodes of patch p = order[p*patchNodes ...]
     int* d_nbStart = nullptr;    // (numNodes+1) prefix of node degrees in patch order = first node-block of a node
     long long* d_pipeStats = nullptr;  // measurement only
     int debugFlags = 0;                // measurement only
-    int usePatch = 1;            // assembly path: 1 write-once patch pipeline where available, 0 slot-map scatter with FP64 atomics
+    int usePatch = 2;            // assembly path: 2 row-owner kernel, 1 write-once patch pipeline, 0 slot-map scatter with FP64 atomics
+    int4* d_connE = nullptr;     // element-major connectivity (single-block plans; row-owner kernel)
+    int maxDeg = 0;              // largest node degree
     // boundary conditions, de-duplicated on the host with the reference's semantics
     int64_t nBC = 0;
     int* d_bcDof = nullptr;       // sorted ascending
@@ -148,6 +151,7 @@ static inline int need_final(const femb_plan* p, const char* who) {
 // out[0..n) = exclusive prefix sums of in[0..n); out[n] = total.  in and out must not alias.  Synchronises.
 int exclusive_scan(const int* d_in, int* d_out, int64_t n, cudaStream_t st, int64_t& launches);
 
+bool rows_path_available(const femb_plan* p);
 // true when the write-once patch pipeline will run for this plan (assemble.cu)
 bool patch_path_available(const femb_plan* p, bool wk, bool wr);
 

@@ -13,9 +13,11 @@
 //   ELEM     ne x int32         global element id (thickness lookup)
 //
 // The shared-memory accumulators of a patch mirror the global CSR layout: owned node r (nbStart = NODE.start,
-// deg) owns 4*deg doubles at offset 4*start: DOF row 0 = [k0.xx k0.xy k1.xx k1.xy ...], then DOF row 1.  A whole
+// deg) owns 2*deg double2 at double2 offset 2*start + r (one pad double2 per preceding node makes the row stride
+// an odd multiple of 16 bytes: conflict-free 128-bit accesses from neighbouring elements): DOF row 0 =
+// [k0.xx k0.xy | k1.xx k1.xy | ...], then DOF row 1.  A whole
 // node's accumulators are therefore one contiguous 32*deg-byte run that maps to K + 4*off: the write-out is a
-// straight 16-byte-per-thread copy, global index = shared index + 2*(off - start).
+// straight 16-byte-per-thread copy, global double2 index = 2*off + j for shared index 2*start + r + j.
 #pragma once
 
 struct BlobLayout {

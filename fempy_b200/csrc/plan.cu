@@ -141,6 +141,20 @@ __global__ void k_dof_pattern(long long numNodes, int s, const int* __restrict__
 }
 
 
+// element-major connectivity (padded to 4 nodes per element) for the row-owner kernel
+__global__ void k_conn_elem_major(const int* __restrict__ conn, long long E, int nn, int4* __restrict__ connE) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int v[4] = {-1, -1, -1, -1};
+    for (int a = 0; a < nn && a < 4; ++a) v[a] = conn[(long long)a * E + e];
+    connE[e] = make_int4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void k_max_int(const int* __restrict__ v, long long n, int* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicMax(out, v[i]);
+}
+
 __global__ void k_permute_mask(const int* __restrict__ order, const unsigned char* __restrict__ mask, long long N,
                                unsigned char* __restrict__ maskPerm) {
     const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,11 +313,23 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
         k_build_slots<<<grid_for(cnt, 256), 256, 0, st>>>(b.d_conn, b.numElems, b.nn, p->d_nrowptr, p->d_ncols, b.d_slot);
         launches++;
     }
+    {  // largest node degree + element-major connectivity for the row-owner kernel
+        CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
+        k_max_int<<<grid_for(N, 256), 256, 0, st>>>(d_deg, N, p->d_flag);
+        CUDA_TRY(cudaMemcpyAsync(&p->maxDeg, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        launches++;
+        if (p->blocks.size() == 1 && p->blocks[0].nn <= 4) {
+            auto& b = p->blocks[0];
+            CUDA_TRY(cudaMalloc(&p->d_connE, b.numElems * sizeof(int4)));
+            k_conn_elem_major<<<grid_for(b.numElems, 256), 256, 0, st>>>(b.d_conn, b.numElems, b.nn, p->d_connE);
+            launches++;
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     cudaFree(d_cand);  // the largest temporary: release it before the patch programs allocate theirs
     d_cand = nullptr;
-    if (p->usePatch == 1) TRY(build_patches(p, launches));
+    if (p->usePatch == 1 || !rows_path_available(p)) TRY(build_patches(p, launches));
     CUDA_TRY(cudaEventRecord(ev1, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
@@ -333,6 +359,7 @@ extern "C" void femb_plan_destroy(femb_plan* p) {
     dfree(p->d_ncols);
     dfree(p->d_adjPtr);
     dfree(p->d_adj);
+    dfree(p->d_connE);
     dfree(p->d_hintCoords);
     dfree(p->d_bcMask);
     dfree(p->d_bcMaskPerm);
@@ -384,10 +411,13 @@ extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t valu
         p->patchNodes = (int)value;
     } else if (!strcmp(name, "team_warps")) {
         if (p->finalized) return fail("femb_plan_set_option: team_warps must be set before finalize");
-        if (value != 1 && value != 2) return fail("femb_plan_set_option: team_warps must be 1 or 2");
+        if (value != 1 && value != 2 && value != 4) return fail("femb_plan_set_option: team_warps must be 1, 2 or 4");
         p->teamWarps = (int)value;
+    } else if (!strcmp(name, "split_elements")) {
+        if (p->finalized) return fail("femb_plan_set_option: split_elements must be set before finalize");
+        p->splitElements = value != 0;
     } else if (!strcmp(name, "use_patches") || !strcmp(name, "assembly_path")) {
-        if (value < 0 || value > 1) return fail("femb_plan_set_option: assembly_path must be 0 (scatter) or 1 (patch pipeline)");
+        if (value < 0 || value > 2) return fail("femb_plan_set_option: assembly_path must be 0 (scatter), 1 (patch pipeline) or 2 (row owner)");
         if (value == 1 && p->finalized && !p->patchesBuilt) return fail("femb_plan_set_option: the patch pipeline must be selected before finalize");
         p->usePatch = (int)value;
     } else if (!strcmp(name, "debug_flags")) {
@@ -404,6 +434,7 @@ extern "C" int64_t femb_plan_get_info(const femb_plan* p, const char* name) {
     if (!strcmp(name, "num_patches")) return p->numPatches;
     if (!strcmp(name, "patch_nodes")) return p->patchNodes;
     if (!strcmp(name, "team_warps")) return p->teamWarps;
+    if (!strcmp(name, "split_elements")) return p->splitElements;
     if (!strcmp(name, "patch_elems_total")) {
         int64_t t = 0;
         for (auto& b : p->blocks) t += b.prog.totalElems;
@@ -425,6 +456,8 @@ extern "C" int64_t femb_plan_get_info(const femb_plan* p, const char* name) {
         return t;
     }
     if (!strcmp(name, "assembly_path")) return p->usePatch;
+    if (!strcmp(name, "rows_path")) return rows_path_available(p) ? 1 : 0;
+    if (!strcmp(name, "max_degree")) return p->maxDeg;
     if (!strcmp(name, "patch_path")) return patch_path_available(p, true, true) ? 1 : 0;
     return -1;
 }

@@ -221,7 +221,7 @@ __global__ void k_blob_halo(const BlobArgs B) {
         atomicMax(&B.stats[0], L.bytes);
         atomicMax(&B.stats[1], nOwned + h);
         atomicMax(&B.stats[3], nnb);
-        if (2 * nnb > 65535) atomicExch(&B.stats[2], 1);
+        if (2 * nnb + nOwned > 65535) atomicExch(&B.stats[2], 1);
     }
 }
 
@@ -283,7 +283,7 @@ __global__ void k_blob_fill(const BlobArgs B, const int* __restrict__ blobPtr, u
             const int pos = B.nodePos[i];
             if (pos < pos0 || pos >= pos1) continue;
             const int off = B.nrowptr[i], deg = B.nrowptr[i + 1] - off;
-            info.rowBase[a] = (unsigned short)(2 * (B.nbStart[pos] - nb0));
+            info.rowBase[a] = (unsigned short)(2 * (B.nbStart[pos] - nb0) + (pos - pos0));  // + one pad double2 per preceding owned node
             info.deg[a] = (unsigned char)deg;
             for (int b = 0; b < B.nn; ++b) info.k[a * 4 + b] = (unsigned char)lower_bound_int(B.ncols + off, deg, nodes[b]);
             int colour = 0;
@@ -371,7 +371,7 @@ static int build_patches_once(femb_plan* p, int64_t& launches) {
     if (!any) return 0;
     const int64_t N = p->numNodes;
     cudaStream_t st = p->stream;
-    if (p->patchNodes <= 0) p->patchNodes = DEFAULT_PATCH_NODES_PER_WARP * p->teamWarps;
+    if (p->patchNodes <= 0) p->patchNodes = DEFAULT_PATCH_NODES_PER_WARP * p->teamWarps / ((p->splitElements && p->teamWarps >= 2) ? 2 : 1);
     p->patchNodes = std::min(1024, ((p->patchNodes + 3) / 4) * 4);  // multiple of 4: a patch's slice of the permuted BC mask is fetched 4 bytes at a time
     const int PN = p->patchNodes;
     p->numPatches = (N + PN - 1) / PN;
@@ -501,7 +501,7 @@ int build_patches(femb_plan* p, int64_t& launches) {
         TRY(build_patches_once(p, launches));
         int worst = 0;
         for (auto& b : p->blocks) worst = std::max(worst, b.prog.maxElems);
-        const int target = 32 * p->teamWarps;
+        const int target = (p->splitElements && p->teamWarps >= 2) ? 16 * p->teamWarps : 32 * p->teamWarps;
         if (userFixed || worst <= target || p->patchNodes <= 4) return 0;
         const int next = std::max(4, (int)((int64_t)p->patchNodes * target / worst) / 4 * 4);
         const int shrunk = (next >= p->patchNodes) ? p->patchNodes - 4 : next;

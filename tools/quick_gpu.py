@@ -10,7 +10,7 @@ for elType,n in (("quad",6),("quad",40),("triangle",33),("quad9",12),("quad",200
     left=meshes.edge_nodes(coords,x=0.0); bc=np.concatenate((2*left,2*left+1)); bv=rng.random(bc.size)*1e-4
     plan=AssemblyPlan(N); plan.setLocalityHint(coords); 
     Nn,dN,w=ELEMENT_FOR[elType]().tables(); plan.addBlock(Nn,dN,w,conn[elType]); plan.finalize()
-    print(elType,n,'path',plan.info('assembly_path'),'patch_path',plan.info("patch_path"),'patches',plan.info("num_patches"),'maxE',plan.info("patch_elems_max"),'blob',plan.info("patch_blob_bytes"),'PN',plan.info("patch_nodes"),'colours',plan.info("patch_colours_max"), flush=True)
+    print(elType,n,'path',plan.info('assembly_path'),'rows',plan.info('rows_path'),'maxdeg',plan.info('max_degree'),'patch_path',plan.info("patch_path"),'patches',plan.info("num_patches"),'maxE',plan.info("patch_elems_max"),'blob',plan.info("patch_blob_bytes"),'PN',plan.info("patch_nodes"),'colours',plan.info("patch_colours_max"), flush=True)
     mat=make_cm(0).material()
     K,R=plan.assemble(coords,states,thick,mat,bc,bv,True,loads)
     print(' launches',plan.lastLaunches, flush=True)
