@@ -16,15 +16,16 @@
 
 namespace rows {
 
-static constexpr int BLOCK = 128;
-static constexpr int MAXD = 12;  // largest node degree (neighbours incl. itself) this kernel handles
+static constexpr int POINT_UNROLL = 1;  // Gauss-point loop kept rolled: fewer live registers, 20+ warps per SM
+static constexpr int BLOCK = 32;
+static constexpr int MAXD = 48;  // largest node degree (neighbours incl. itself): shared-memory rows; the corner records hold 7-bit positions
 
 struct Args {
     long long numNodes;
     const int* nrowptr;
     const int* ncols;
     const int* adjPtr;
-    const int* adj;          // element ids (single element block)
+    const int2* corners;     // {element, a | k0<<4 | k1<<11 | k2<<18 | k3<<25} per (node, adjacent element)
     const int4* connE;       // element-major connectivity, padded to 4 nodes
     const double2* coords;
     const double2* states;
@@ -53,8 +54,8 @@ __device__ __forceinline__ int bc_find(const int* __restrict__ bcDof, int n, int
     return lo;
 }
 
-template <int NN, int NQ, bool NL, bool WK, bool WR>
-__global__ void __launch_bounds__(BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const femb::DMat D,
+template <int NN, int NQ, bool NL, bool WK, bool WR, bool PF>
+__global__ void __launch_bounds__(BLOCK, (PF ? 384 : 640) / BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const femb::DMat D,
                                                         const Args A) {
     using namespace femb;
     static_assert(NN <= 4, "element-major connectivity holds at most 4 nodes");
@@ -62,47 +63,67 @@ __global__ void __launch_bounds__(BLOCK) k_assemble_rows(const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31;
     const long long i = (long long)blockIdx.x * BLOCK + tid;
     const bool valid = i < A.numNodes;
-    const int off = valid ? __ldg(A.nrowptr + i) : 0;
+    const int off = __ldg(A.nrowptr + (valid ? i : A.numNodes));  // tail lanes: end of the values, degree 0
     const int deg = valid ? __ldg(A.nrowptr + i + 1) - off : 0;
     auto slot = [&](int m) -> double2& { return acc[m * BLOCK + ((tid + m) & (BLOCK - 1))]; };
 
-    // sorted neighbour list of the row (positions of the element's nodes are found by counting smaller entries)
-    int cols[MAXD];
-#pragma unroll
-    for (int k = 0; k < MAXD; ++k) cols[k] = (k < deg) ? __ldg(A.ncols + off + k) : 0x7fffffff;
     if (WK)
         for (int m = 0; m < 2 * deg; ++m) slot(m) = make_double2(0.0, 0.0);
     double rx = 0.0, ry = 0.0;
 
-    const int c0 = valid ? __ldg(A.adjPtr + i) : 0, c1 = valid ? __ldg(A.adjPtr + i + 1) : 0;
-    for (int c = c0; c < c1; ++c) {
-        const int e = __ldg(A.adj + c);
-        const int4 cn = __ldg(A.connE + e);
+    // corner c+1's inputs are fetched while corner c is being evaluated (one set of registers ahead)
+    struct CornerIn {
+        int e;
+        unsigned packed;
+        double2 X[NN], U[NN];
+        int node[NN];
+        double theta;
+    };
+    auto fetch = [&](int c, CornerIn& in) {
+        const int2 rec = __ldg(A.corners + c);
+        in.e = rec.x;
+        in.packed = (unsigned)rec.y;
+        const int4 cn = __ldg(A.connE + rec.x);
         const int node[4] = {cn.x, cn.y, cn.z, cn.w};
-        double x[NN], y[NN], ux[NN], uy[NN];
-        int a = 0;
 #pragma unroll
         for (int b = 0; b < NN; ++b) {
-            const double2 p = __ldg(A.coords + node[b]);
-            x[b] = p.x;
-            y[b] = p.y;
-            if (NL || WR) {
-                const double2 q = __ldg(A.states + node[b]);
-                ux[b] = q.x;
-                uy[b] = q.y;
+            in.X[b] = __ldg(A.coords + node[b]);
+            if (NL) in.U[b] = __ldg(A.states + node[b]);  // linear model: fetched after the strip (short live range)
+            in.node[b] = node[b];
+        }
+        in.theta = __ldg(A.thick + rec.x);
+    };
+    const int c0 = valid ? __ldg(A.adjPtr + i) : 0, c1 = valid ? __ldg(A.adjPtr + i + 1) : 0;
+    CornerIn cur, nxt;
+    if (PF && c0 < c1) fetch(c0, cur);
+    for (int c = c0; c < c1; ++c) {
+        if (PF) {
+            if (c + 1 < c1) fetch(c + 1, nxt);
+        } else {
+            fetch(c, cur);
+        }
+        const unsigned packed = cur.packed;
+        const int a = packed & 0xf;
+        double x[NN], y[NN], ux[NN], uy[NN];
+#pragma unroll
+        for (int b = 0; b < NN; ++b) {
+            x[b] = cur.X[b].x;
+            y[b] = cur.X[b].y;
+            if (NL) {
+                ux[b] = cur.U[b].x;
+                uy[b] = cur.U[b].y;
             } else {
                 ux[b] = uy[b] = 0.0;
             }
-            a = (node[b] == (int)i) ? b : a;
         }
-        const double theta = __ldg(A.thick + e);
+        const double theta = cur.theta;
 
         // node-row strip of K_e: blocks (a, b), b = 0..NN-1, and the residual pair of node a
         double Kr[NN][4];
         double ra0 = 0.0, ra1 = 0.0;
 #pragma unroll
         for (int b = 0; b < NN; ++b) Kr[b][0] = Kr[b][1] = Kr[b][2] = Kr[b][3] = 0.0;
-#pragma unroll
+#pragma unroll POINT_UNROLL
         for (int p = 0; p < NQ; ++p) {
             double G0[NN], G1[NN];
             const double det = point_gradients<NN, NQ>(tb, p, x, y, G0, G1);
@@ -166,8 +187,9 @@ __global__ void __launch_bounds__(BLOCK) k_assemble_rows(const __grid_constant__
                 Kr[b][2] = fma(D.d01, s10, D.d22 * s01);
                 Kr[b][3] = fma(D.d11, s11, D.d22 * s00);
                 if (WR) {  // R_a = sum_b K_ab q_b
-                    ra0 = fma(Kr[b][0], ux[b], fma(Kr[b][1], uy[b], ra0));
-                    ra1 = fma(Kr[b][2], ux[b], fma(Kr[b][3], uy[b], ra1));
+                    const double2 q = __ldg(A.states + cur.node[b]);
+                    ra0 = fma(Kr[b][0], q.x, fma(Kr[b][1], q.y, ra0));
+                    ra1 = fma(Kr[b][2], q.x, fma(Kr[b][3], q.y, ra1));
                 }
             }
         }
@@ -176,9 +198,7 @@ __global__ void __launch_bounds__(BLOCK) k_assemble_rows(const __grid_constant__
         if (WK) {
 #pragma unroll
             for (int b = 0; b < NN; ++b) {
-                int kk = 0;  // position of node b in my sorted row = number of smaller column nodes
-#pragma unroll
-                for (int k = 0; k < MAXD; ++k) kk += (cols[k] < node[b]) ? 1 : 0;
+                const int kk = (packed >> (4 + 7 * b)) & 0x7f;  // position of node b in my sorted row (plan time)
                 double2& s0 = slot(kk);
                 double2& s1 = slot(deg + kk);
                 const double2 o0 = s0, o1 = s1;
@@ -186,14 +206,14 @@ __global__ void __launch_bounds__(BLOCK) k_assemble_rows(const __grid_constant__
                 s1 = make_double2(o1.x + Kr[b][2], o1.y + Kr[b][3]);
             }
         }
+        if (PF) cur = nxt;
     }
 
     // ---- BC rows, loads, residual ---------------------------------------------------------------------------
     const unsigned m = (valid && A.bcMask) ? A.bcMask[i] : 0u;
     if (m && WK) {  // constrained rows: zeros, occurrence count on the diagonal (AssemblyUtils.py:55-60)
-        int diagK = 0;
-#pragma unroll
-        for (int k = 0; k < MAXD; ++k) diagK += (cols[k] < (int)i) ? 1 : 0;
+        int diagK = 0;  // position of the node in its own sorted row
+        for (int k = 0; k < deg; ++k) diagK += (__ldg(A.ncols + off + k) < (int)i) ? 1 : 0;
         for (int r = 0; r < 2; ++r) {
             if (m & (1u << r)) {
                 for (int k = 0; k < deg; ++k) slot(r * deg + k) = make_double2(0.0, 0.0);
@@ -216,18 +236,27 @@ __global__ void __launch_bounds__(BLOCK) k_assemble_rows(const __grid_constant__
         reinterpret_cast<double2*>(A.R)[i] = make_double2(rx, ry);
     }
 
-    // ---- write-out: the lanes of a warp stream one node's contiguous 32*deg-byte run per step -------------------
+    // ---- write-out --------------------------------------------------------------------------------------------
+    // The rows of the warp's 32 consecutive nodes are one contiguous run of the CSR values (both DOF rows of a node
+    // are adjacent and rows are stored in node order), so the warp streams [2*off_first, 2*off_last + 2*deg_last) in
+    // 512-byte steps.  A byte table maps a position of the run to the lane that owns it.
     if (WK) {
-        __syncwarp();
+        unsigned char* owner = reinterpret_cast<unsigned char*>(acc + 2 * A.maxDeg * BLOCK);
         double2* K2 = reinterpret_cast<double2*>(A.K);
+        const int base = __shfl_sync(0xffffffffu, off, 0);
+        const int start = 2 * (off - base);  // my first position in the run
+        unsigned char* mine = owner + 2 * A.maxDeg * (tid - lane) + start;
+        for (int m = 0; m < 2 * deg; ++m) mine[m] = (unsigned char)lane;
+        const int total = __shfl_sync(0xffffffffu, start + 2 * deg, 31);  // invalid tail lanes hold off = deg = 0
+        __syncwarp();
         const int wbase = tid - lane;
-        for (int r = 0; r < 32; ++r) {
-            const int offR = __shfl_sync(0xffffffffu, off, r);
-            const int n2 = 2 * __shfl_sync(0xffffffffu, deg, r);
-            for (int mm = lane; mm < n2; mm += 32) {
-                const double2 v = acc[mm * BLOCK + ((wbase + r + mm) & (BLOCK - 1))];
-                st_stream(K2 + 2ll * offR + mm, v);
-            }
+        owner += 2 * A.maxDeg * wbase;  // one table per warp
+        for (int f0 = 0; f0 < total; f0 += 32) {
+            const int f = f0 + lane;
+            const bool ok = f < total;
+            const int r = ok ? owner[f] : 0;
+            const int mm = f - __shfl_sync(0xffffffffu, start, r);
+            if (ok) st_stream(K2 + 2ll * base + f, acc[mm * BLOCK + ((wbase + r + mm) & (BLOCK - 1))]);
         }
     }
 }

@@ -38,6 +38,16 @@ __host__ __device__ constexpr int point_unroll() {
     return (NN * NQ <= 81) ? NQ : 1;
 }
 
+// 1/d to within an ulp or two: hardware seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps; the IEEE-exact
+// division costs ~25 instructions per Gauss point and the result feeds a 1e-12 tolerance
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return r;
+}
+
 // G0[a] = dN_a/dx, G1[a] = dN_a/dy at Gauss point p; returns signed detJ
 template <int NN, int NQ>
 __device__ __forceinline__ double point_gradients(const Tables<NN, NQ>& tb, int p, const double (&x)[NN],
@@ -51,7 +61,7 @@ __device__ __forceinline__ double point_gradients(const Tables<NN, NQ>& tb, int 
         J11 = fma(tb.dN[p][1][a], y[a], J11);
     }
     const double det = J00 * J11 - J01 * J10;
-    const double idet = 1.0 / det;
+    const double idet = fast_rcp(det);
     const double i00 = idet * J11, i11 = idet * J00, i01 = -idet * J01, i10 = -idet * J10;
 #pragma unroll
     for (int a = 0; a < NN; ++a) {

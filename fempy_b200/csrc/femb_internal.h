@@ -104,6 +104,7 @@ struct femb_plan {
     int debugFlags = 0;                // measurement only
     int usePatch = 2;            // assembly path: 2 row-owner kernel, 1 write-once patch pipeline, 0 slot-map scatter with FP64 atomics
     int4* d_connE = nullptr;     // element-major connectivity (single-block plans; row-owner kernel)
+    int2* d_corners = nullptr;   // per (node, adjacent element): {element, a | k0<<4 | k1<<11 | k2<<18 | k3<<25} (row-owner kernel)
     int maxDeg = 0;              // largest node degree
     // boundary conditions, de-duplicated on the host with the reference's semantics
     int64_t nBC = 0;

@@ -150,6 +150,33 @@ __global__ void k_conn_elem_major(const int* __restrict__ conn, long long E, int
     connE[e] = make_int4(v[0], v[1], v[2], v[3]);
 }
 
+// corner records of the row-owner kernel: for every (node, adjacent element) the element id and, packed in one word,
+// the node's local index a in the element (4 bits) and the position k_b (7 bits each) of each element node in the
+// node's sorted neighbour list
+__global__ void k_corners(long long N, const int* __restrict__ nrowptr, const int* __restrict__ ncols,
+                          const int* __restrict__ adjPtr, const int* __restrict__ adj, const int4* __restrict__ connE, int nn,
+                          int2* __restrict__ corners) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int off = nrowptr[i], deg = nrowptr[i + 1] - off;
+    for (int c = adjPtr[i]; c < adjPtr[i + 1]; ++c) {
+        const int e = adj[c];
+        const int4 cn = connE[e];
+        const int node[4] = {cn.x, cn.y, cn.z, cn.w};
+        unsigned packed = 0;
+        for (int b = 0; b < nn; ++b) {
+            if (node[b] == (int)i) packed |= (unsigned)b;
+            int lo = 0, hi = deg;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ncols[off + mid] < node[b]) lo = mid + 1; else hi = mid;
+            }
+            packed |= (unsigned)lo << (4 + 7 * b);
+        }
+        corners[c] = make_int2(e, (int)packed);
+    }
+}
+
 __global__ void k_max_int(const int* __restrict__ v, long long n, int* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicMax(out, v[i]);
@@ -322,14 +349,16 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
             auto& b = p->blocks[0];
             CUDA_TRY(cudaMalloc(&p->d_connE, b.numElems * sizeof(int4)));
             k_conn_elem_major<<<grid_for(b.numElems, 256), 256, 0, st>>>(b.d_conn, b.numElems, b.nn, p->d_connE);
-            launches++;
+            CUDA_TRY(cudaMalloc(&p->d_corners, std::max<int64_t>(totalAdj, 1) * sizeof(int2)));
+            k_corners<<<grid_for(N, 128), 128, 0, st>>>(N, p->d_nrowptr, p->d_ncols, d_adjPtr, d_adj, p->d_connE, b.nn, p->d_corners);
+            launches += 2;
         }
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     cudaFree(d_cand);  // the largest temporary: release it before the patch programs allocate theirs
     d_cand = nullptr;
-    if (p->usePatch == 1 || !rows_path_available(p)) TRY(build_patches(p, launches));
+    if (p->usePatch == 1) TRY(build_patches(p, launches));  // the patch pipeline is opt-in: its programs are the costly part of a plan
     CUDA_TRY(cudaEventRecord(ev1, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
@@ -360,6 +389,7 @@ extern "C" void femb_plan_destroy(femb_plan* p) {
     dfree(p->d_adjPtr);
     dfree(p->d_adj);
     dfree(p->d_connE);
+    dfree(p->d_corners);
     dfree(p->d_hintCoords);
     dfree(p->d_bcMask);
     dfree(p->d_bcMaskPerm);
