@@ -195,7 +195,7 @@ def run_ours(args, rank, world, local_rank):
     plan.setOption("team_warps", args.team_warps)
     if args.debug_flags:
         plan.setOption("debug_flags", args.debug_flags)
-    plan.setOption("split_elements", 0 if args.no_split else 1)
+    plan.setOption("split_elements", 1 if args.split else 0)
     if args.patch_nodes:
         plan.setOption("patch_nodes", args.patch_nodes)
     plan.addBlock(N_, dN, w, wl["conn"][elType])
@@ -448,8 +448,8 @@ def main():
     ap.add_argument("--flush-write-only", action="store_true", help="L2 flush by the 512 MB write alone (leaves dirty lines for the timed kernel to evict)")
     ap.add_argument("--patch-nodes", type=int, default=0, help="owned nodes per patch (0 = library default)")
     ap.add_argument("--debug-flags", type=int, default=0, help="kernel experiment switches (exploration only)")
-    ap.add_argument("--no-split", action="store_true", help="one thread per element instead of two")
-    ap.add_argument("--team-warps", type=int, default=4, help="warps sharing a patch in the assembly kernel (1, 2 or 4)")
+    ap.add_argument("--split", action="store_true", help="patch pipeline: two threads per element (exploration only)")
+    ap.add_argument("--team-warps", type=int, default=2, help="warps sharing a patch in the assembly kernel (1, 2 or 4)")
     ap.add_argument("--path", default="rows", choices=["rows", "patch", "scatter"],
                     help="assembly path: row-owner kernel (default), write-once patch pipeline, or slot-map scatter with FP64 atomics")
     args = ap.parse_args()

@@ -257,23 +257,17 @@ bool rows_path_available(const femb_plan* p) {
     return p->usePatch == 2 && p->blocks.size() == 1 && p->blocks[0].nn <= 4 && p->d_connE && p->d_corners && p->maxDeg <= rows::MAXD;
 }
 
-template <int NN, int NQ, bool NL, bool WK, bool WR, bool PF>
-static int launch_rows_pf(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
+template <int NN, int NQ, bool NL, bool WK, bool WR>
+static int launch_rows(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
     const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
     const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * (sizeof(double2) + 1);  // accumulators + write-out owner table
     static size_t configured = 0;
     if (smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    rows::k_assemble_rows<NN, NQ, NL, WK, WR, PF><<<grid_for(p->numNodes, rows::BLOCK), rows::BLOCK, smem, st>>>(tb, D, A);
+    rows::k_assemble_rows<NN, NQ, NL, WK, WR><<<grid_for(p->numNodes, rows::BLOCK), rows::BLOCK, smem, st>>>(tb, D, A);
     return 0;
-}
-
-template <int NN, int NQ, bool NL, bool WK, bool WR>
-static int launch_rows(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
-    if (p->debugFlags & 1) return launch_rows_pf<NN, NQ, NL, WK, WR, true>(p, b, D, A, st);
-    return launch_rows_pf<NN, NQ, NL, WK, WR, false>(p, b, D, A, st);
 }
 
 template <int NN, int NQ>

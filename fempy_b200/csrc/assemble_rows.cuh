@@ -54,8 +54,8 @@ __device__ __forceinline__ int bc_find(const int* __restrict__ bcDof, int n, int
     return lo;
 }
 
-template <int NN, int NQ, bool NL, bool WK, bool WR, bool PF>
-__global__ void __launch_bounds__(BLOCK, (PF ? 384 : 640) / BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const femb::DMat D,
+template <int NN, int NQ, bool NL, bool WK, bool WR>
+__global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const femb::DMat D,
                                                         const Args A) {
     using namespace femb;
     static_assert(NN <= 4, "element-major connectivity holds at most 4 nodes");
@@ -71,52 +71,28 @@ __global__ void __launch_bounds__(BLOCK, (PF ? 384 : 640) / BLOCK) k_assemble_ro
         for (int m = 0; m < 2 * deg; ++m) slot(m) = make_double2(0.0, 0.0);
     double rx = 0.0, ry = 0.0;
 
-    // corner c+1's inputs are fetched while corner c is being evaluated (one set of registers ahead)
-    struct CornerIn {
-        int e;
-        unsigned packed;
-        double2 X[NN], U[NN];
-        int node[NN];
-        double theta;
-    };
-    auto fetch = [&](int c, CornerIn& in) {
+    const int c0 = valid ? __ldg(A.adjPtr + i) : 0, c1 = valid ? __ldg(A.adjPtr + i + 1) : 0;
+    for (int c = c0; c < c1; ++c) {
         const int2 rec = __ldg(A.corners + c);
-        in.e = rec.x;
-        in.packed = (unsigned)rec.y;
+        const unsigned packed = (unsigned)rec.y;
+        const int a = packed & 0xf;
         const int4 cn = __ldg(A.connE + rec.x);
         const int node[4] = {cn.x, cn.y, cn.z, cn.w};
-#pragma unroll
-        for (int b = 0; b < NN; ++b) {
-            in.X[b] = __ldg(A.coords + node[b]);
-            if (NL) in.U[b] = __ldg(A.states + node[b]);  // linear model: fetched after the strip (short live range)
-            in.node[b] = node[b];
-        }
-        in.theta = __ldg(A.thick + rec.x);
-    };
-    const int c0 = valid ? __ldg(A.adjPtr + i) : 0, c1 = valid ? __ldg(A.adjPtr + i + 1) : 0;
-    CornerIn cur, nxt;
-    if (PF && c0 < c1) fetch(c0, cur);
-    for (int c = c0; c < c1; ++c) {
-        if (PF) {
-            if (c + 1 < c1) fetch(c + 1, nxt);
-        } else {
-            fetch(c, cur);
-        }
-        const unsigned packed = cur.packed;
-        const int a = packed & 0xf;
         double x[NN], y[NN], ux[NN], uy[NN];
 #pragma unroll
         for (int b = 0; b < NN; ++b) {
-            x[b] = cur.X[b].x;
-            y[b] = cur.X[b].y;
+            const double2 X = __ldg(A.coords + node[b]);
+            x[b] = X.x;
+            y[b] = X.y;
             if (NL) {
-                ux[b] = cur.U[b].x;
-                uy[b] = cur.U[b].y;
-            } else {
+                const double2 U = __ldg(A.states + node[b]);
+                ux[b] = U.x;
+                uy[b] = U.y;
+            } else {  // linear model: the states are fetched after the strip (short live range)
                 ux[b] = uy[b] = 0.0;
             }
         }
-        const double theta = cur.theta;
+        const double theta = __ldg(A.thick + rec.x);
 
         // node-row strip of K_e: blocks (a, b), b = 0..NN-1, and the residual pair of node a
         double Kr[NN][4];
@@ -187,7 +163,7 @@ __global__ void __launch_bounds__(BLOCK, (PF ? 384 : 640) / BLOCK) k_assemble_ro
                 Kr[b][2] = fma(D.d01, s10, D.d22 * s01);
                 Kr[b][3] = fma(D.d11, s11, D.d22 * s00);
                 if (WR) {  // R_a = sum_b K_ab q_b
-                    const double2 q = __ldg(A.states + cur.node[b]);
+                    const double2 q = __ldg(A.states + node[b]);
                     ra0 = fma(Kr[b][0], q.x, fma(Kr[b][1], q.y, ra0));
                     ra1 = fma(Kr[b][2], q.x, fma(Kr[b][3], q.y, ra1));
                 }
@@ -206,7 +182,6 @@ __global__ void __launch_bounds__(BLOCK, (PF ? 384 : 640) / BLOCK) k_assemble_ro
                 s1 = make_double2(o1.x + Kr[b][2], o1.y + Kr[b][3]);
             }
         }
-        if (PF) cur = nxt;
     }
 
     // ---- BC rows, loads, residual ---------------------------------------------------------------------------

@@ -266,11 +266,12 @@ def test_full_size_properties(elType, n, label):
     assert np.abs(K2.data - K.data).max() < 1e-13 * scale
 
 
-# ---- the two assembly paths: write-once patch pipeline (default) and slot-map scatter with FP64 atomics ----------------
-PATHS = {"scatter": 0, "patch": 1}
+# ---- the assembly paths: row-owner kernel (default), write-once patch pipeline (opt-in), slot-map scatter with FP64
+#      atomics (general fallback: several element blocks, 6/9/10/16-node families) ---------------------------------------
+PATHS = {"scatter": 0, "patch": 1, "rows": 2}
 
 
-def _raw_plan(elType, coords, conn, hint=True, patchNodes=None, path="patch", teamWarps=None):
+def _raw_plan(elType, coords, conn, hint=True, patchNodes=None, path="rows", teamWarps=None):
     el = ELEMENT_FOR[elType]()
     plan = AssemblyPlan(coords.shape[0])
     if hint:
@@ -325,13 +326,14 @@ def _check_against_oracle(plan, elType, case, launchesExpected):
 
 @pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29), ("quad9", 14)])
 def test_default_path_matches_scatter_path_and_oracle(elType, n):
-    """default: write-once patch pipeline for the 3/4-node families (1 launch), scatter kernels otherwise"""
+    """default: row-owner kernel for the 3/4-node families (1 launch), scatter kernels otherwise"""
     case = _path_case(elType, n)
     coords, conn = case[0], case[1]
     plan = _raw_plan(elType, coords, conn)
-    onPatchPath = plan.info("patch_path") == 1
-    assert onPatchPath == (elType != "quad9")
-    K1, R1 = _check_against_oracle(plan, elType, case, launchesExpected=1 if onPatchPath else 3)
+    assert plan.info("assembly_path") == 2
+    onRowsPath = plan.info("rows_path") == 1
+    assert onRowsPath == (elType != "quad9")
+    K1, R1 = _check_against_oracle(plan, elType, case, launchesExpected=1 if onRowsPath else 3)
     plan.setOption("assembly_path", 0)
     mat = make_cm(0).material()
     K0, R0 = plan.assemble(coords, case[2], case[3], mat, case[5], case[6], True, case[4])
@@ -356,7 +358,42 @@ def test_patch_pipeline_matches_oracle(elType, n, hint, patchNodes, teamWarps):
     plan.close()
 
 
-@pytest.mark.parametrize("path", ["patch"])
+def _renumbered(case, seed=3):
+    """the same mesh with randomly permuted node numbers (no locality in the numbering, irregular row order)"""
+    coords, conn, states, thick, loads, bcDOF, bcVal = case
+    N = coords.shape[0]
+    perm = np.random.default_rng(seed).permutation(N)  # new id of old node
+    inv = np.argsort(perm)
+    conn2 = {k: perm[v] for k, v in conn.items()}
+    loads2 = loads.reshape(N, 2)[inv].ravel()
+    bc2 = 2 * perm[bcDOF // 2] + bcDOF % 2
+    return coords[inv], conn2, states[inv], thick, loads2, bc2, bcVal
+
+
+@pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29)])
+@pytest.mark.parametrize("renumber", [False, True])
+def test_row_owner_kernel_matches_oracle(elType, n, renumber):
+    """default path: one thread per node row, every K value and R entry written exactly once = 1 launch"""
+    case = _path_case(elType, n)
+    if renumber:
+        case = _renumbered(case)
+    plan = _raw_plan(elType, case[0], case[1], path="rows")
+    assert plan.info("rows_path") == 1 and plan.info("num_patches") == 0  # no patch programs are built for this path
+    _check_against_oracle(plan, elType, case, launchesExpected=1)
+    # Green-strain model through the same kernel family
+    coords, conn, states, thick, loads, bcDOF, bcVal = case
+    matNL = make_cm(1, linear=False).material()
+    K, R = plan.assemble(coords, 50 * states, thick, matNL, bcDOF, bcVal, True, loads)
+    assert plan.lastLaunches == 1
+    blocks = oracle_blocks(conn)
+    Ko = fo.assemble_matrix(blocks, coords, 50 * states, thick, 1, MAT["E"], MAT["nu"], bcDOF, nonlinear=True, dropZeros=False)
+    Ko.sort_indices()
+    Ro = fo.assemble_residual(blocks, coords, 50 * states, thick, 1, MAT["E"], MAT["nu"], loads, bcDOF, bcVal, nonlinear=True)
+    assert relerr(K, Ko.data) < TOL and relerr(R, Ro) < TOL
+    plan.close()
+
+
+@pytest.mark.parametrize("path", ["rows", "patch"])
 def test_write_once_path_is_deterministic(path):
     """write-once assembly has a fixed summation order: two runs are bit-identical"""
     coords, conn = meshes.quad4_grid(200, 150)
@@ -377,7 +414,7 @@ def test_write_once_path_is_deterministic(path):
 def test_isolated_nodes_get_minus_load():
     coords = np.array([[0.0, 0.0], [2.0, 0.1], [2.2, 1.0], [0.1, 1.5], [5.0, 5.0], [6.0, 7.0]])
     conn = {"quad": np.array([[0, 1, 2, 3]])}
-    for path in ("patch", "scatter"):
+    for path in ("rows", "patch", "scatter"):
         plan = _raw_plan("quad", coords, conn, path=path)
         loads = np.arange(12.0)
         _, R = plan.assemble(coords, np.zeros((6, 2)), np.ones(1), make_cm(0).material(), applyBCs=False, loads=loads)
