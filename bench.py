@@ -335,7 +335,7 @@ def run_ours_multi(args, rank, world, local_rank, dev):
     cm = Constitutive.IsoPlaneStress(MAT["E"], MAT["nu"], MAT["rho"], MAT["t"])
 
     t0 = time.perf_counter()
-    part = Partition(N, conn, rank, world)
+    part = Partition(N, conn, rank, world, mode=args.dist_mode)
     asm = GpuLocalAssembler(part, {"quad": Elements.QuadElement2D(1).tables()}, coords, cm.material(), local_rank)
     da = DistributedAssembly(part, asm, dev)
     da.set_bcs(bcDOF, bcVal)
@@ -419,10 +419,11 @@ def run_ours_multi(args, rank, world, local_rank, dev):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "elements": numEl, "dof": 2 * N, "nnz": int(counts[4].item()),
                        "l2": "flushed between timed steps (512 MB write)", "partition": "contiguous node ranges; element -> owner of its lowest node",
-                       "collective": "NCCL batched send/recv of interface-row partial sums", "interface_bytes_per_step": int(counts[2].item())},
+                       "collective": ("none: boundary elements are evaluated by every rank owning one of their nodes (owner-computes rows)" if args.dist_mode == "halo"
+                                      else "NCCL batched send/recv of interface-row partial sums"), "interface_bytes_per_step": int(counts[2].item())},
             "nnz_per_s": counts[4].item() / (ms_per_step * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_assemble_pipe on rank 0's local mesh", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": "k_assemble_rows on rank 0's local mesh", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": peak_src},
             "e2e": {"value": numEl / float(e2e_t.item()), "unit": "elements/s", "ms_per_step": 1e3 * float(e2e_t.item()),
                     "h2d_bytes_per_step": int(counts[0].item()), "d2h_bytes_per_step": int(counts[1].item()),
@@ -447,6 +448,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--flush-write-only", action="store_true", help="L2 flush by the 512 MB write alone (leaves dirty lines for the timed kernel to evict)")
     ap.add_argument("--patch-nodes", type=int, default=0, help="owned nodes per patch (0 = library default)")
+    ap.add_argument("--dist-mode", default="halo", choices=["halo", "exchange"], help="multi-GPU: redundant boundary elements (no exchange) or unique elements + NCCL interface exchange")
     ap.add_argument("--debug-flags", type=int, default=0, help="kernel experiment switches (exploration only)")
     ap.add_argument("--split", action="store_true", help="patch pipeline: two threads per element (exploration only)")
     ap.add_argument("--team-warps", type=int, default=2, help="warps sharing a patch in the assembly kernel (1, 2 or 4)")

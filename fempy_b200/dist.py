@@ -4,16 +4,21 @@ The reference has no distributed code, so the only compatibility target is the f
 
 * nodes are owned in contiguous global-id ranges; rank r owns DOF rows [2*n0_r, 2*n1_r) and returns that row
   block with GLOBAL column indices, so stacking the rank blocks reproduces the single-GPU pattern bit for bit;
-* every element is assigned to exactly one rank -- the owner of its lowest-numbered node -- so no element is
-  evaluated twice;
-* an element touching nodes of a higher rank produces contributions to rows it does not own.  Those
-  "interface" partial sums (K entries and residual entries) are the ONLY data exchanged at assembly time:
-  one batched send/recv per neighbour over NCCL, followed by an indexed add into the owner's row block.
+* each rank runs the single-GPU kernel on a LOCAL mesh made of every element that touches one of its owned nodes,
+  so the pattern AND the values of the owned rows are complete on the rank that owns them.
 
-Each rank runs the single-GPU fused kernel on a LOCAL mesh made of every element that touches one of its owned
-nodes (so the pattern of the owned rows is complete); the elements of that mesh that belong to another rank get
-thickness 0 and contribute nothing.  The slot positions of the interface entries inside the owner's row block
-are negotiated once, at plan time, by exchanging (row, column) DOF pairs.
+Two ways to treat the elements that straddle a partition boundary:
+
+``mode="halo"`` (default, no data-path collective): every rank evaluates all elements of its local mesh, i.e. a
+  boundary element is evaluated by each rank owning one of its nodes (one element layer per boundary: 0.2% extra
+  work for a 512-wide strip).  The owner-computes rule of the row-owner kernel then finishes every owned row
+  locally; the rows of halo nodes are incomplete and simply not returned.  Nothing is exchanged at assembly time.
+
+``mode="exchange"``: every element is assigned to exactly one rank -- the owner of its lowest-numbered node --
+  and gets thickness 0 elsewhere.  Contributions to rows of a higher rank ("interface" partial sums of K and R)
+  are sent to the owner: one batched send/recv per neighbour over NCCL, then an indexed add.  The slot positions
+  of the interface entries inside the owner's row block are negotiated once, at plan time, by exchanging
+  (row, column) DOF pairs.  Kept for meshes whose boundary layers are thick (high-order or 3D-like adjacency).
 
 The local assembler is injectable (``assembler=``): the GPU path uses ``GpuLocalAssembler`` (AssemblyPlan on the
 rank's device); the CPU tests drive the same partition / exchange logic over gloo with an oracle-based assembler.
@@ -32,7 +37,10 @@ def node_ranges(numNodes, world):
 class Partition:
     """Host-side description of one rank's share of the mesh (pure numpy)."""
 
-    def __init__(self, numNodes, connectivity, rank, world):
+    def __init__(self, numNodes, connectivity, rank, world, mode="halo"):
+        if mode not in ("halo", "exchange"):
+            raise ValueError("mode must be 'halo' or 'exchange'")
+        self.mode = mode
         self.rank, self.world, self.numNodes = rank, world, int(numNodes)
         self.bounds = node_ranges(numNodes, world)
         self.n0, self.n1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
@@ -45,7 +53,7 @@ class Partition:
             ids = np.flatnonzero(touches)
             owner = np.searchsorted(self.bounds, conn[ids].min(axis=1), side="right") - 1
             self.elemIds[elType] = ids
-            self.active[elType] = owner == rank
+            self.active[elType] = np.ones(ids.size, dtype=bool) if mode == "halo" else owner == rank
             nodeSets.append(conn[ids].reshape(-1))
         # local numbering = rank order of the global ids: monotone, so sorted CSR columns stay sorted
         self.localNodes = np.unique(np.concatenate(nodeSets))
@@ -57,7 +65,7 @@ class Partition:
         self.numActiveElems = int(sum(m.sum() for m in self.active.values()))
 
     def local_thickness(self, thickness, typeOffsets):
-        """Thickness of the local mesh's elements; 0 for the elements another rank evaluates."""
+        """Thickness of the local mesh's elements; in exchange mode 0 for the elements another rank evaluates."""
         out = []
         for t, ids in self.elemIds.items():
             th = np.asarray(thickness, dtype=np.float64)[typeOffsets[t] + ids].copy()
@@ -78,7 +86,7 @@ class Partition:
 
 
 class DistributedAssembly:
-    """Per-rank driver: local fused assembly + interface exchange -> this rank's CSR row block.
+    """Per-rank driver: local fused assembly (+ interface exchange in exchange mode) -> this rank's CSR row block.
 
     assembler must provide:
         pattern() -> (indptr, indices) of the LOCAL mesh (int64, local DOF numbering)
@@ -108,9 +116,10 @@ class DistributedAssembly:
         import torch.distributed as dist
 
         p = self.part
-        # interface rows: DOF rows of nodes above my range that my ACTIVE elements touch
+        # interface rows: DOF rows of nodes above my range that my ACTIVE elements touch (none in halo mode:
+        # the owner evaluates those elements itself)
         ghostNodes = set()
-        for t, conn in p.localConn.items():
+        for t, conn in ({} if p.mode == "halo" else p.localConn).items():
             act = conn[p.active[t]]
             ghostNodes.update(np.unique(act[act >= p.ownedLo + p.numOwned]).tolist())
         ghostNodes = np.array(sorted(ghostNodes), dtype=np.int64)
@@ -126,7 +135,7 @@ class DistributedAssembly:
             self.sendR[int(s)] = dofRows.astype(np.int64)
             outgoing[int(s)] = (p.global_dofs(rowOfPos), p.global_dofs(self.indices[pos]), p.global_dofs(dofRows))
         # every rank learns what it will receive (tiny: interface entries only)
-        if p.world > 1:
+        if p.world > 1 and p.mode != "halo":
             gathered = [None] * p.world
             dist.all_gather_object(gathered, outgoing, group=self.group)
         else:

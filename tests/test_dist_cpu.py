@@ -59,7 +59,7 @@ def _mesh(kind):
     return coords, {"quad": conn[col < 4], "triangle": np.vstack((rest[:, [0, 1, 2]], rest[:, [0, 2, 3]]))}
 
 
-def _worker(rank, world, port, kind, applyBCs):
+def _worker(rank, world, port, kind, applyBCs, mode):
     import torch
     import torch.distributed as dist
 
@@ -84,7 +84,7 @@ def _worker(rank, world, port, kind, applyBCs):
         bcDOF = np.concatenate((2 * left, 2 * left + 1, [2 * (N - 1), 2 * (N - 1)]))  # incl. a duplicate on the last node
         bcVal = rng.random(bcDOF.size) * 1e-4
 
-        part = Partition(N, conn, rank, world)
+        part = Partition(N, conn, rank, world, mode=mode)
         assert part.numOwned == part.n1 - part.n0 and np.array_equal(part.localNodes[part.ownedLo : part.ownedLo + part.numOwned], np.arange(part.n0, part.n1))
         asm = OracleLocalAssembler(part, coords)
         da = DistributedAssembly(part, asm, torch.device("cpu"))
@@ -107,8 +107,12 @@ def _worker(rank, world, port, kind, applyBCs):
             indices = np.concatenate([g[1] for g in gathered])
             data = np.concatenate([g[2] for g in gathered])
             R = np.concatenate([g[3] for g in gathered])
-            assert sum(g[4] for g in gathered) == e0  # every element evaluated exactly once
-            assert all(g[5] > 0 for g in gathered[:-1])  # every rank but the last sends interface rows upward
+            if mode == "exchange":
+                assert sum(g[4] for g in gathered) == e0  # every element evaluated exactly once
+                assert all(g[5] > 0 for g in gathered[:-1])  # every rank but the last sends interface rows upward
+            else:
+                assert sum(g[4] for g in gathered) > e0  # boundary elements are evaluated by every rank that needs them
+                assert all(g[5] == 0 for g in gathered)  # and nothing is exchanged
             np.testing.assert_array_equal(indptr, Kref.indptr)  # bit-exact global pattern
             np.testing.assert_array_equal(indices, Kref.indices)
             assert np.abs(data - Kref.data).max() < 1e-12 * np.abs(Kref.data).max()
@@ -120,10 +124,13 @@ def _worker(rank, world, port, kind, applyBCs):
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("kind", ["quad", "triangle", "mixed"])
 @pytest.mark.parametrize("applyBCs", [True, False])
-def test_partitioned_assembly_matches_single_process(world, kind, applyBCs):
+@pytest.mark.parametrize("mode", ["halo", "exchange"])
+def test_partitioned_assembly_matches_single_process(world, kind, applyBCs, mode):
+    if mode == "exchange" and world == 3 and not applyBCs:
+        pytest.skip("covered by the other exchange cases (keeps the CPU suite short)")
     import torch.multiprocessing as mp
 
-    mp.spawn(_worker, args=(world, _free_port(), kind, applyBCs), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), kind, applyBCs, mode), nprocs=world, join=True)
 
 
 def test_partition_properties():
@@ -137,8 +144,10 @@ def test_partition_properties():
     for world in (1, 2, 4, 8):
         total = 0
         for r in range(world):
-            p = Partition(N, conn, r, world)
+            p = Partition(N, conn, r, world, mode="exchange")
             total += p.numActiveElems
+            h = Partition(N, conn, r, world)  # default: halo mode evaluates every element touching an owned node
+            assert h.mode == "halo" and h.active["quad"].all() and h.numActiveElems == h.elemIds["quad"].size
             ids = p.elemIds["quad"][p.active["quad"]]
             owners[ids] += 1
             assert np.all(np.diff(p.localNodes) > 0)  # monotone local numbering

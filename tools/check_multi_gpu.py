@@ -16,7 +16,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-for elType, n in (("quad", 96), ("triangle", 70)):
+for mode, elType, n in (("halo", "quad", 96), ("halo", "triangle", 70), ("exchange", "quad", 96), ("exchange", "triangle", 70)):
     coords, conn = meshes.GENERATORS[elType](n, n + 13)
     N = coords.shape[0]
     numEl = conn[elType].shape[0]
@@ -29,7 +29,7 @@ for elType, n in (("quad", 96), ("triangle", 70)):
     bcVal = rng.random(bcDOF.size) * 1e-4
     el = Elements.QuadElement2D(1) if elType == "quad" else Elements.TriElement2D(1)
     mat = Constitutive.IsoPlaneStress(70e9, 0.3, 2700.0, 1.0).material()
-    part = Partition(N, conn, rank, world)
+    part = Partition(N, conn, rank, world, mode=mode)
     asm = GpuLocalAssembler(part, {elType: el.tables()}, coords, mat, local)
     da = DistributedAssembly(part, asm, dev)
     da.set_bcs(bcDOF, bcVal)
