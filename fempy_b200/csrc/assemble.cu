@@ -360,6 +360,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.ncols = p->d_ncols;
             A.adjPtr = p->d_adjPtr;
             A.corners = p->d_corners;
+            A.zero = 0;
             A.connE = p->d_connE;
             A.coords = (const double2*)d_coords;
             A.states = (const double2*)d_states;

@@ -16,6 +16,11 @@
 
 namespace rows {
 
+#ifndef ROWS_KNOCK
+#define ROWS_KNOCK 0  // measurement builds only (tools/knock_variants.sh): bit mask of kernel stages replaced by stubs
+#endif
+static constexpr int KNOCK = ROWS_KNOCK;  // 1 zero-fill, 2 node-data gathers, 4 corner/connectivity loads, 8 write-out, 16 one Gauss point,
+                                          // 32 accumulator read-modify-writes, 64 D application / residual product
 static constexpr int POINT_UNROLL = 1;  // Gauss-point loop kept rolled: fewer live registers, 20+ warps per SM
 static constexpr int BLOCK = 32;
 static constexpr int MAXD = 48;  // largest node degree (neighbours incl. itself): shared-memory rows; the corner records hold 7-bit positions
@@ -37,6 +42,7 @@ struct Args {
     const double* bcCount;
     int nBC;
     int maxDeg;
+    int zero;                // always 0: a runtime-uniform index that keeps constants out of FP64 operand slots
     double* K;
     double* R;
 };
@@ -55,7 +61,7 @@ __device__ __forceinline__ int bc_find(const int* __restrict__ bcDof, int n, int
 }
 
 template <int NN, int NQ, bool NL, bool WK, bool WR>
-__global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const femb::DMat D,
+__global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const __grid_constant__ femb::DMat D,
                                                         const Args A) {
     using namespace femb;
     static_assert(NN <= 4, "element-major connectivity holds at most 4 nodes");
@@ -67,21 +73,22 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
     const int deg = valid ? __ldg(A.nrowptr + i + 1) - off : 0;
     auto slot = [&](int m) -> double2& { return acc[m * BLOCK + ((tid + m) & (BLOCK - 1))]; };
 
-    if (WK)
+    if (WK && !(KNOCK & 1))
         for (int m = 0; m < 2 * deg; ++m) slot(m) = make_double2(0.0, 0.0);
     double rx = 0.0, ry = 0.0;
 
     const int c0 = valid ? __ldg(A.adjPtr + i) : 0, c1 = valid ? __ldg(A.adjPtr + i + 1) : 0;
     for (int c = c0; c < c1; ++c) {
-        const int2 rec = __ldg(A.corners + c);
+        const int2 rec = (KNOCK & 4) ? make_int2(c & 0xffff, ((c - c0) & 3) | (1 << 11) | (2 << 18) | (3 << 25)) : __ldg(A.corners + c);
         const unsigned packed = (unsigned)rec.y;
         const int a = packed & 0xf;
-        const int4 cn = __ldg(A.connE + rec.x);
+        const int4 cn = (KNOCK & 4) ? make_int4((int)i, (int)i + 1, (int)i + 2, (int)i + 3) : __ldg(A.connE + rec.x);
         const int node[4] = {cn.x, cn.y, cn.z, cn.w};
         double x[NN], y[NN], ux[NN], uy[NN];
 #pragma unroll
         for (int b = 0; b < NN; ++b) {
-            const double2 X = __ldg(A.coords + node[b]);
+            const double2 X = (KNOCK & 2) ? make_double2(0.01 * (node[b] & 511) + ((b == 1 || b == 2) ? 0.01 : 0.0), 1e-5 * node[b] + (b >= 2 ? 0.01 : 0.0))
+                                          : __ldg(A.coords + node[b]);
             x[b] = X.x;
             y[b] = X.y;
             if (NL) {
@@ -92,7 +99,7 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
                 ux[b] = uy[b] = 0.0;
             }
         }
-        const double theta = __ldg(A.thick + rec.x);
+        const double theta = (KNOCK & 2) ? 1.0 + 1e-9 * rec.x : __ldg(A.thick + rec.x);
 
         // node-row strip of K_e: blocks (a, b), b = 0..NN-1, and the residual pair of node a
         double Kr[NN][4];
@@ -100,7 +107,39 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
 #pragma unroll
         for (int b = 0; b < NN; ++b) Kr[b][0] = Kr[b][1] = Kr[b][2] = Kr[b][3] = 0.0;
 #pragma unroll POINT_UNROLL
-        for (int p = 0; p < NQ; ++p) {
+        for (int p = 0; p < ((KNOCK & 16) ? 1 : NQ); ++p) {
+            if (!NL) {
+                // Linear model, division-free gradients: with adj = det * J^-1 and Gh = adj * dN (so G = Gh / det),
+                //   sc * G_a G_b = (w * theta / det) * Gh_a Gh_b,
+                // so only the scalar w*theta/det carries the reciprocal.  The gradient of "my" shape function comes
+                // from the table with a per-thread index (constant-bank load) instead of register selects, and the
+                // tables are read through uniform registers (rolled loop): FP64 instructions with a constant-bank
+                // operand issue at half rate on sm_100 (tools/micro/fp64_micro2.cu).
+                double J00 = 0.0, J01 = 0.0, J10 = 0.0, J11 = 0.0;
+#pragma unroll
+                for (int b = 0; b < NN; ++b) {
+                    J00 = fma(tb.dN[p][0][b], x[b], J00);
+                    J01 = fma(tb.dN[p][0][b], y[b], J01);
+                    J10 = fma(tb.dN[p][1][b], x[b], J10);
+                    J11 = fma(tb.dN[p][1][b], y[b], J11);
+                }
+                const double det = J00 * J11 - J01 * J10;
+                const double sc = tb.w[p] * theta * fast_rcp(det);
+                const double da0 = tb.dN[p][0][a], da1 = tb.dN[p][1][a];
+                const double A0 = (J11 * da0 - J01 * da1) * sc, A1 = (J00 * da1 - J10 * da0) * sc;
+                if (WK || WR) {
+#pragma unroll
+                    for (int b = 0; b < NN; ++b) {
+                        const double g0 = J11 * tb.dN[p][0][b] - J01 * tb.dN[p][1][b];
+                        const double g1 = J00 * tb.dN[p][1][b] - J10 * tb.dN[p][0][b];
+                        Kr[b][0] = fma(A0, g0, Kr[b][0]);
+                        Kr[b][1] = fma(A0, g1, Kr[b][1]);
+                        Kr[b][2] = fma(A1, g0, Kr[b][2]);
+                        Kr[b][3] = fma(A1, g1, Kr[b][3]);
+                    }
+                }
+                continue;
+            }
             double G0[NN], G1[NN];
             const double det = point_gradients<NN, NQ>(tb, p, x, y, G0, G1);
             const double sc = tb.w[p] * det * theta;
@@ -154,16 +193,18 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
                 }
             }
         }
-        if (!NL) {  // [[D00 S00 + D22 S11, D01 S01 + D22 S10], [D01 S10 + D22 S01, D11 S11 + D22 S00]]
+        if (!NL && !(KNOCK & 64)) {  // [[D00 S00 + D22 S11, D01 S01 + D22 S10], [D01 S10 + D22 S01, D11 S11 + D22 S00]]
+            const double* Dv = &D.d00 + A.zero;  // runtime-uniform offset (0): the entries arrive in uniform registers
+            const double d00 = Dv[0], d01 = Dv[1], d11 = Dv[2], d22 = Dv[3];
 #pragma unroll
             for (int b = 0; b < NN; ++b) {
                 const double s00 = Kr[b][0], s01 = Kr[b][1], s10 = Kr[b][2], s11 = Kr[b][3];
-                Kr[b][0] = fma(D.d00, s00, D.d22 * s11);
-                Kr[b][1] = fma(D.d01, s01, D.d22 * s10);
-                Kr[b][2] = fma(D.d01, s10, D.d22 * s01);
-                Kr[b][3] = fma(D.d11, s11, D.d22 * s00);
+                Kr[b][0] = fma(d00, s00, d22 * s11);
+                Kr[b][1] = fma(d01, s01, d22 * s10);
+                Kr[b][2] = fma(d01, s10, d22 * s01);
+                Kr[b][3] = fma(d11, s11, d22 * s00);
                 if (WR) {  // R_a = sum_b K_ab q_b
-                    const double2 q = __ldg(A.states + node[b]);
+                    const double2 q = (KNOCK & 2) ? make_double2(1e-3, 1e-4 * node[b]) : __ldg(A.states + node[b]);
                     ra0 = fma(Kr[b][0], q.x, fma(Kr[b][1], q.y, ra0));
                     ra1 = fma(Kr[b][2], q.x, fma(Kr[b][3], q.y, ra1));
                 }
@@ -171,7 +212,10 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
         }
         rx += ra0;
         ry += ra1;
-        if (WK) {
+        if (KNOCK & 32) {  // keep the strip alive without touching shared memory
+#pragma unroll
+            for (int b = 0; b < NN; ++b) rx += Kr[b][0] + Kr[b][1] + Kr[b][2] + Kr[b][3];
+        } else if (WK) {
 #pragma unroll
             for (int b = 0; b < NN; ++b) {
                 const int kk = (packed >> (4 + 7 * b)) & 0x7f;  // position of node b in my sorted row (plan time)
@@ -215,7 +259,7 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
     // The rows of the warp's 32 consecutive nodes are one contiguous run of the CSR values (both DOF rows of a node
     // are adjacent and rows are stored in node order), so the warp streams [2*off_first, 2*off_last + 2*deg_last) in
     // 512-byte steps.  A byte table maps a position of the run to the lane that owns it.
-    if (WK) {
+    if (WK && !(KNOCK & 8)) {
         unsigned char* owner = reinterpret_cast<unsigned char*>(acc + 2 * A.maxDeg * BLOCK);
         double2* K2 = reinterpret_cast<double2*>(A.K);
         const int base = __shfl_sync(0xffffffffu, off, 0);
