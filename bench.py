@@ -170,6 +170,15 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (None if absent)."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except OSError:
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
 
@@ -257,7 +266,8 @@ def run_ours(args, rank, world, local_rank):
     kernel_ms = kernel_ms_sum / max(kernel_calls, 1)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": {"rows": "k_assemble_rows (one thread per node row, redundant element geometry, private swizzled smem row, coalesced warp write-out; BCs and loads fused)",
+                "traffic": ncu_traffic("k_assemble_rows") if (args.path == "rows" and args.config == "c2" and args.nx is None) else None,
+                "kernel": {"rows": "k_assemble_rows (one thread per node row, redundant element geometry, private swizzled smem row, coalesced warp write-out; BCs and loads fused)",
                            "patch": "k_assemble_pipe (persistent self-prefetching warp teams over node patches)",
                            "scatter": "k_assemble_sym (fused K_e/R_e evaluation + RED.F64 scatter)"}[args.path], "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_element": alg_bytes / numEl,
