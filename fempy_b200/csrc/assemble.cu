@@ -361,6 +361,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.adjPtr = p->d_adjPtr;
             A.corners = p->d_corners;
             A.zero = 0;
+            A.stats = p->d_pipeStats;
             A.connE = p->d_connE;
             A.coords = (const double2*)d_coords;
             A.states = (const double2*)d_states;
@@ -438,6 +439,9 @@ extern "C" int femb_plan_pipe_stats(femb_plan* p, int32_t enable, int64_t* out, 
     if (enable) {
         TRY(dalloc(&p->d_pipeStats, n));
         CUDA_TRY(cudaMemset(p->d_pipeStats, 0, n * sizeof(long long)));
+        const long long big = 0x7fffffffffffffffll;  // slots 3 and 5 hold minima (row-owner trace builds)
+        CUDA_TRY(cudaMemcpy(p->d_pipeStats + 3, &big, sizeof(big), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(p->d_pipeStats + 5, &big, sizeof(big), cudaMemcpyHostToDevice));
     } else {
         dfree(p->d_pipeStats);
     }

@@ -19,6 +19,9 @@ namespace rows {
 #ifndef ROWS_KNOCK
 #define ROWS_KNOCK 0  // measurement builds only (tools/knock_variants.sh): bit mask of kernel stages replaced by stubs
 #endif
+#ifndef ROWS_TRACE
+#define ROWS_TRACE 0  // measurement builds only: warp lifetime statistics into Args::stats
+#endif
 static constexpr int KNOCK = ROWS_KNOCK;  // 1 zero-fill, 2 node-data gathers, 4 corner/connectivity loads, 8 write-out, 16 one Gauss point,
                                           // 32 accumulator read-modify-writes, 64 D application / residual product
 static constexpr int POINT_UNROLL = 1;  // Gauss-point loop kept rolled: fewer live registers, 20+ warps per SM
@@ -42,6 +45,7 @@ struct Args {
     const double* bcCount;
     int nBC;
     int maxDeg;
+    long long* stats;        // measurement builds only (ROWS_TRACE, tools/rows_trace.py): warp lifetimes
     int zero;                // always 0: a runtime-uniform index that keeps constants out of FP64 operand slots
     double* K;
     double* R;
@@ -66,6 +70,10 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
     using namespace femb;
     static_assert(NN <= 4, "element-major connectivity holds at most 4 nodes");
     extern __shared__ double2 acc[];  // [2*maxDeg][BLOCK], swizzled
+#if ROWS_TRACE
+    long long tStart = clock64(), gStart;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gStart));
+#endif
     const int tid = threadIdx.x, lane = tid & 31;
     const long long i = (long long)blockIdx.x * BLOCK + tid;
     const bool valid = i < A.numNodes;
@@ -278,6 +286,21 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
             if (ok) st_stream(K2 + 2ll * base + f, acc[mm * BLOCK + ((wbase + r + mm) & (BLOCK - 1))]);
         }
     }
+#if ROWS_TRACE
+    if (A.stats && lane == 0) {  // [0] sum of warp lifetimes (cycles) [1] warps [2] longest [3] first start (ns) [4] last end (ns) [5] shortest
+        long long gEnd;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gEnd));
+        const long long life = clock64() - tStart;
+        atomicAdd((unsigned long long*)A.stats + 0, (unsigned long long)life);
+        atomicAdd((unsigned long long*)A.stats + 1, 1ull);
+        atomicMax(A.stats + 2, life);
+        atomicMin(A.stats + 3, gStart);
+        atomicMax(A.stats + 4, gEnd);
+        atomicMin(A.stats + 5, life);
+        atomicAdd((unsigned long long*)A.stats + 16 + min(63, (int)((gStart - A.stats[3]) / 1000)), 1ull);  // starts per us
+        atomicAdd((unsigned long long*)A.stats + 96 + min(63, (int)(life / 2000)), 1ull);                  // lifetimes per 2000 cycles
+    }
+#endif
 }
 
 }  // namespace rows
