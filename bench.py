@@ -233,7 +233,7 @@ def run_ours(args, rank, world, local_rank):
             flushRead.sum()
 
     def step():
-        plan.assembleDev(d_coords, d_states, d_thick, mat, True, d_loads, d_K, d_R)
+        plan.assembleDev(d_coords, d_states, d_thick, mat, not args.no_bcs, d_loads, d_K, d_R)
 
     for _ in range(args.warmup):
         flush_l2()
@@ -459,6 +459,7 @@ def main():
     ap.add_argument("--flush-write-only", action="store_true", help="L2 flush by the 512 MB write alone (leaves dirty lines for the timed kernel to evict)")
     ap.add_argument("--patch-nodes", type=int, default=0, help="owned nodes per patch (0 = library default)")
     ap.add_argument("--dist-mode", default="halo", choices=["halo", "exchange"], help="multi-GPU: redundant boundary elements (no exchange) or unique elements + NCCL interface exchange")
+    ap.add_argument("--no-bcs", action="store_true", help="device-timed steps without boundary conditions (exploration only)")
     ap.add_argument("--debug-flags", type=int, default=0, help="kernel experiment switches (exploration only)")
     ap.add_argument("--split", action="store_true", help="patch pipeline: two threads per element (exploration only)")
     ap.add_argument("--team-warps", type=int, default=2, help="warps sharing a patch in the assembly kernel (1, 2 or 4)")

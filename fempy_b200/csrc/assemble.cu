@@ -260,7 +260,8 @@ bool rows_path_available(const femb_plan* p) {
 template <int NN, int NQ, bool NL, bool WK, bool WR>
 static int launch_rows(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
     const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
-    const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * (sizeof(double2) + 1);  // accumulators + write-out owner table
+    // accumulator rows + residual pairs + write-out owner table
+    const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * (sizeof(double2) + 1) + rows::BLOCK * sizeof(double2);
     static size_t configured = 0;
     if (smem > configured) {
         CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -367,11 +368,9 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.states = (const double2*)d_states;
             A.thick = d_thick;
             A.loads = (const double2*)d_loads;
-            A.bcMask = bcs ? p->d_bcMask : nullptr;
-            A.bcDof = p->d_bcDof;
-            A.bcVal = p->d_bcVal;
-            A.bcCount = p->d_bcCount;
-            A.nBC = (int)p->nBC;
+            A.bcInfo = bcs ? p->d_bcInfo : nullptr;
+            A.bcNodeCnt = (const double2*)p->d_bcNodeCnt;
+            A.bcNodeVal = (const double2*)p->d_bcNodeVal;
             A.maxDeg = p->maxDeg;
             A.K = d_K;
             A.R = d_R;

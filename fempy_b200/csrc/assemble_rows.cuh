@@ -39,11 +39,9 @@ struct Args {
     const double2* states;
     const double* thick;
     const double2* loads;           // may be NULL
-    const unsigned char* bcMask;    // NULL: no BCs
-    const int* bcDof;
-    const double* bcVal;
-    const double* bcCount;
-    int nBC;
+    const int* bcInfo;              // NULL: no BCs; per node (index of the constrained node + 1) << 2 | DOF bits
+    const double2* bcNodeCnt;       // per constrained node: diagonal values (occurrence counts) of DOF 0 / DOF 1
+    const double2* bcNodeVal;       // per constrained node: prescribed values
     int maxDeg;
     long long* stats;        // measurement builds only (ROWS_TRACE, tools/rows_trace.py): warp lifetimes
     int zero;                // always 0: a runtime-uniform index that keeps constants out of FP64 operand slots
@@ -53,15 +51,6 @@ struct Args {
 
 __device__ __forceinline__ void st_stream(double2* p, const double2 v) {  // K is written once and not re-read here
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y));
-}
-
-__device__ __forceinline__ int bc_find(const int* __restrict__ bcDof, int n, int dof) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (bcDof[mid] < dof) lo = mid + 1; else hi = mid;
-    }
-    return lo;
 }
 
 template <int NN, int NQ, bool NL, bool WK, bool WR>
@@ -83,7 +72,8 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
 
     if (WK && !(KNOCK & 1))
         for (int m = 0; m < 2 * deg; ++m) slot(m) = make_double2(0.0, 0.0);
-    double rx = 0.0, ry = 0.0;
+    double2& racc = acc[2 * A.maxDeg * BLOCK + tid];  // residual pair of the node: kept in shared memory, not in registers
+    if (WR) racc = make_double2(0.0, 0.0);
 
     const int c0 = valid ? __ldg(A.adjPtr + i) : 0, c1 = valid ? __ldg(A.adjPtr + i + 1) : 0;
     for (int c = c0; c < c1; ++c) {
@@ -218,11 +208,13 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
                 }
             }
         }
-        rx += ra0;
-        ry += ra1;
+        if (WR) {
+            const double2 o = racc;
+            racc = make_double2(o.x + ra0, o.y + ra1);
+        }
         if (KNOCK & 32) {  // keep the strip alive without touching shared memory
 #pragma unroll
-            for (int b = 0; b < NN; ++b) rx += Kr[b][0] + Kr[b][1] + Kr[b][2] + Kr[b][3];
+            for (int b = 0; b < NN; ++b) racc.x += Kr[b][0] + Kr[b][1] + Kr[b][2] + Kr[b][3];
         } else if (WK) {
 #pragma unroll
             for (int b = 0; b < NN; ++b) {
@@ -237,28 +229,32 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
     }
 
     // ---- BC rows, loads, residual ---------------------------------------------------------------------------
-    const unsigned m = (valid && A.bcMask) ? A.bcMask[i] : 0u;
+    // A warp waits for its slowest lane, so the (rare) constrained nodes take everything from per-constrained-node
+    // arrays built by femb_plan_set_bcs: one level of loads behind bcInfo.
+    const unsigned info = (valid && A.bcInfo) ? (unsigned)__ldg(A.bcInfo + i) : 0u;
+    const unsigned m = info & 3u;
     if (m && WK) {  // constrained rows: zeros, occurrence count on the diagonal (AssemblyUtils.py:55-60)
+        const double2 cnt = __ldg(A.bcNodeCnt + (info >> 2) - 1);
         int diagK = 0;  // position of the node in its own sorted row
         for (int k = 0; k < deg; ++k) diagK += (__ldg(A.ncols + off + k) < (int)i) ? 1 : 0;
         for (int r = 0; r < 2; ++r) {
             if (m & (1u << r)) {
                 for (int k = 0; k < deg; ++k) slot(r * deg + k) = make_double2(0.0, 0.0);
-                const double cnt = A.bcCount[bc_find(A.bcDof, A.nBC, 2 * (int)i + r)];
-                slot(r * deg + diagK) = r ? make_double2(0.0, cnt) : make_double2(cnt, 0.0);
+                slot(r * deg + diagK) = r ? make_double2(0.0, cnt.y) : make_double2(cnt.x, 0.0);
             }
         }
     }
     if (WR && valid) {
+        double rx = racc.x, ry = racc.y;
         if (A.loads) {  // R = scatter(R_e) - loads (Problem.py:653)
             const double2 f = __ldg(A.loads + i);
             rx -= f.x;
             ry -= f.y;
         }
         if (m) {  // R[bc] = u - c (AssemblyUtils.py:93)
-            const double2 u = __ldg(A.states + i);
-            if (m & 1u) rx = u.x - A.bcVal[bc_find(A.bcDof, A.nBC, 2 * (int)i)];
-            if (m & 2u) ry = u.y - A.bcVal[bc_find(A.bcDof, A.nBC, 2 * (int)i + 1)];
+            const double2 u = __ldg(A.states + i), val = __ldg(A.bcNodeVal + (info >> 2) - 1);
+            if (m & 1u) rx = u.x - val.x;
+            if (m & 2u) ry = u.y - val.y;
         }
         reinterpret_cast<double2*>(A.R)[i] = make_double2(rx, ry);
     }
@@ -268,7 +264,7 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
     // are adjacent and rows are stored in node order), so the warp streams [2*off_first, 2*off_last + 2*deg_last) in
     // 512-byte steps.  A byte table maps a position of the run to the lane that owns it.
     if (WK && !(KNOCK & 8)) {
-        unsigned char* owner = reinterpret_cast<unsigned char*>(acc + 2 * A.maxDeg * BLOCK);
+        unsigned char* owner = reinterpret_cast<unsigned char*>(acc + 2 * A.maxDeg * BLOCK + BLOCK);
         double2* K2 = reinterpret_cast<double2*>(A.K);
         const int base = __shfl_sync(0xffffffffu, off, 0);
         const int start = 2 * (off - base);  // my first position in the run

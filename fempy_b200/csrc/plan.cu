@@ -392,6 +392,9 @@ extern "C" void femb_plan_destroy(femb_plan* p) {
     dfree(p->d_corners);
     dfree(p->d_hintCoords);
     dfree(p->d_bcMask);
+    dfree(p->d_bcInfo);
+    dfree(p->d_bcNodeCnt);
+    dfree(p->d_bcNodeVal);
     dfree(p->d_bcMaskPerm);
     dfree(p->d_pipeStats);
     free_patches(p);
@@ -589,6 +592,30 @@ extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const doubl
     for (size_t i = 0; i < n; ++i) mask[dofs[i] >> 1] |= (unsigned char)(1u << (dofs[i] & 1));
     TRY(dalloc(&p->d_bcMask, (size_t)p->numNodes));
     CUDA_TRY(cudaMemcpyAsync(p->d_bcMask, mask.data(), mask.size(), cudaMemcpyHostToDevice, p->stream));
+    {  // row-owner kernel: per node (index of the constrained node + 1) << 2 | DOF bits (0 = unconstrained) and, per
+       // constrained node, the diagonal values (occurrence counts) and the prescribed values of its two DOFs
+        std::vector<int> info((size_t)p->numNodes, 0);
+        std::vector<double> cnt2, val2;
+        for (size_t i = 0; i < n; ++i) {
+            const size_t node = (size_t)(dofs[i] >> 1);
+            if (!info[node]) {
+                info[node] = (int)((cnt2.size() / 2 + 1) << 2) | mask[node];
+                cnt2.push_back(0.0); cnt2.push_back(0.0);
+                val2.push_back(0.0); val2.push_back(0.0);
+            }
+            const size_t j = (size_t)(info[node] >> 2) - 1;
+            cnt2[2 * j + (dofs[i] & 1)] = counts[i];
+            val2[2 * j + (dofs[i] & 1)] = vals[i];
+        }
+        dfree(p->d_bcInfo); dfree(p->d_bcNodeCnt); dfree(p->d_bcNodeVal);
+        TRY(dalloc(&p->d_bcInfo, (size_t)p->numNodes));
+        TRY(dalloc(&p->d_bcNodeCnt, cnt2.size()));
+        TRY(dalloc(&p->d_bcNodeVal, val2.size()));
+        CUDA_TRY(cudaMemcpyAsync(p->d_bcInfo, info.data(), info.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        CUDA_TRY(cudaMemcpyAsync(p->d_bcNodeCnt, cnt2.data(), cnt2.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        CUDA_TRY(cudaMemcpyAsync(p->d_bcNodeVal, val2.data(), val2.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));  // the host vectors go out of scope
+    }
     if (p->patchesBuilt && p->d_order) {  // the same mask in patch order: each patch bulk-copies its slice
         const size_t padded = (size_t)p->numPatches * p->patchNodes;
         TRY(dalloc(&p->d_bcMaskPerm, padded));
