@@ -39,7 +39,7 @@ struct Args {
     const double2* states;
     const double* thick;
     const double2* loads;           // may be NULL
-    const int* bcInfo;              // NULL: no BCs; per node (index of the constrained node + 1) << 2 | DOF bits
+    const int* bcInfo;              // NULL: no BCs; per node (index of the constrained node + 1) << 9 | position in its own row << 2 | DOF bits
     const double2* bcNodeCnt;       // per constrained node: diagonal values (occurrence counts) of DOF 0 / DOF 1
     const double2* bcNodeVal;       // per constrained node: prescribed values
     int maxDeg;
@@ -234,9 +234,8 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
     const unsigned info = (valid && A.bcInfo) ? (unsigned)__ldg(A.bcInfo + i) : 0u;
     const unsigned m = info & 3u;
     if (m && WK) {  // constrained rows: zeros, occurrence count on the diagonal (AssemblyUtils.py:55-60)
-        const double2 cnt = __ldg(A.bcNodeCnt + (info >> 2) - 1);
-        int diagK = 0;  // position of the node in its own sorted row
-        for (int k = 0; k < deg; ++k) diagK += (__ldg(A.ncols + off + k) < (int)i) ? 1 : 0;
+        const double2 cnt = __ldg(A.bcNodeCnt + (info >> 9) - 1);
+        const int diagK = (info >> 2) & 0x7f;  // position of the node in its own sorted row
         for (int r = 0; r < 2; ++r) {
             if (m & (1u << r)) {
                 for (int k = 0; k < deg; ++k) slot(r * deg + k) = make_double2(0.0, 0.0);
@@ -252,7 +251,7 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
             ry -= f.y;
         }
         if (m) {  // R[bc] = u - c (AssemblyUtils.py:93)
-            const double2 u = __ldg(A.states + i), val = __ldg(A.bcNodeVal + (info >> 2) - 1);
+            const double2 u = __ldg(A.states + i), val = __ldg(A.bcNodeVal + (info >> 9) - 1);
             if (m & 1u) rx = u.x - val.x;
             if (m & 2u) ry = u.y - val.y;
         }

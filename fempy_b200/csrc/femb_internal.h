@@ -112,7 +112,7 @@ struct femb_plan {
     double* d_bcVal = nullptr;    // last value given for the DOF
     double* d_bcCount = nullptr;  // number of occurrences (diagonal value)
     unsigned char* d_bcMask = nullptr;  // (numNodes) bit r set when DOF 2*node + r is constrained
-    int* d_bcInfo = nullptr;        // (numNodes) (index of the constrained node + 1) << 2 | DOF bits; 0 = unconstrained
+    int* d_bcInfo = nullptr;        // (numNodes) (index of the constrained node + 1) << 9 | position in own row << 2 | DOF bits; 0 = unconstrained
     double* d_bcNodeCnt = nullptr;  // per constrained node: diagonal values (occurrence counts) of its two DOFs
     double* d_bcNodeVal = nullptr;  // per constrained node: prescribed values of its two DOFs
     unsigned char* d_bcMaskPerm = nullptr;  // the same mask in patch order (padded to a multiple of 16 nodes)

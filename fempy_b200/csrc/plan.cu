@@ -188,6 +188,17 @@ __global__ void k_permute_mask(const int* __restrict__ order, const unsigned cha
     if (pos < N) maskPerm[pos] = mask[order[pos]];
 }
 
+// adds the position of each constrained node in its own sorted row to its bcInfo word: (index + 1) << 9 | diagK << 2 | bits
+__global__ void k_bc_diag(long long N, const int* __restrict__ nrowptr, const int* __restrict__ ncols, int* __restrict__ info) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int v = info[i];
+    if (!v) return;
+    int diagK = 0;
+    for (int c = nrowptr[i]; c < nrowptr[i + 1]; ++c) diagK += (ncols[c] < (int)i) ? 1 : 0;
+    info[i] = ((v >> 2) << 9) | (diagK << 2) | (v & 3);
+}
+
 __global__ void k_check_bcs(long long nBC, const int* __restrict__ bcDof, const int* __restrict__ nrowptr, int* flag) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nBC) return;
@@ -592,7 +603,7 @@ extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const doubl
     for (size_t i = 0; i < n; ++i) mask[dofs[i] >> 1] |= (unsigned char)(1u << (dofs[i] & 1));
     TRY(dalloc(&p->d_bcMask, (size_t)p->numNodes));
     CUDA_TRY(cudaMemcpyAsync(p->d_bcMask, mask.data(), mask.size(), cudaMemcpyHostToDevice, p->stream));
-    {  // row-owner kernel: per node (index of the constrained node + 1) << 2 | DOF bits (0 = unconstrained) and, per
+    {  // row-owner kernel: per node (index of the constrained node + 1) << 9 | diagK << 2 | DOF bits (0 = unconstrained) and, per
        // constrained node, the diagonal values (occurrence counts) and the prescribed values of its two DOFs
         std::vector<int> info((size_t)p->numNodes, 0);
         std::vector<double> cnt2, val2;
@@ -614,6 +625,7 @@ extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const doubl
         CUDA_TRY(cudaMemcpyAsync(p->d_bcInfo, info.data(), info.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         CUDA_TRY(cudaMemcpyAsync(p->d_bcNodeCnt, cnt2.data(), cnt2.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         CUDA_TRY(cudaMemcpyAsync(p->d_bcNodeVal, val2.data(), val2.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        k_bc_diag<<<grid_for(p->numNodes, 256), 256, 0, p->stream>>>(p->numNodes, p->d_nrowptr, p->d_ncols, p->d_bcInfo);
         CUDA_TRY(cudaStreamSynchronize(p->stream));  // the host vectors go out of scope
     }
     if (p->patchesBuilt && p->d_order) {  // the same mask in patch order: each patch bulk-copies its slice
