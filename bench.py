@@ -204,7 +204,6 @@ def run_ours(args, rank, world, local_rank):
     plan.setOption("team_warps", args.team_warps)
     if args.debug_flags:
         plan.setOption("debug_flags", args.debug_flags)
-    plan.setOption("split_elements", 1 if args.split else 0)
     if args.patch_nodes:
         plan.setOption("patch_nodes", args.patch_nodes)
     plan.addBlock(N_, dN, w, wl["conn"][elType])
@@ -305,7 +304,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step), "clocks": clocks,
         "plan_build": {"device_ms": plan.buildMs, "wall_ms": plan_wall_ms},
-        "path": {"assembly_path": args.path, "rows_path": plan.info("rows_path"), "max_degree": plan.info("max_degree"), "write_once_patches": plan.info("patch_path"), "patch_nodes": plan.info("patch_nodes"), "team_warps": plan.info("team_warps"), "split_elements": plan.info("split_elements"), "num_patches": plan.info("num_patches"),
+        "path": {"assembly_path": args.path, "rows_path": plan.info("rows_path"), "max_degree": plan.info("max_degree"), "write_once_patches": plan.info("patch_path"), "patch_nodes": plan.info("patch_nodes"), "team_warps": plan.info("team_warps"), "num_patches": plan.info("num_patches"),
                  "patch_elems_total": plan.info("patch_elems_total"), "patch_elems_max": plan.info("patch_elems_max"),
                  "patch_colours_max": plan.info("patch_colours_max"), "patch_blob_bytes": plan.info("patch_blob_bytes")},
     }  # fmt: skip
@@ -461,8 +460,7 @@ def main():
     ap.add_argument("--dist-mode", default="halo", choices=["halo", "exchange"], help="multi-GPU: redundant boundary elements (no exchange) or unique elements + NCCL interface exchange")
     ap.add_argument("--no-bcs", action="store_true", help="device-timed steps without boundary conditions (exploration only)")
     ap.add_argument("--debug-flags", type=int, default=0, help="kernel experiment switches (exploration only)")
-    ap.add_argument("--split", action="store_true", help="patch pipeline: two threads per element (exploration only)")
-    ap.add_argument("--team-warps", type=int, default=2, help="warps sharing a patch in the assembly kernel (1, 2 or 4)")
+    ap.add_argument("--team-warps", type=int, default=2, help="warps sharing a patch in the patch-pipeline kernel (1 or 2)")
     ap.add_argument("--path", default="rows", choices=["rows", "patch", "scatter"],
                     help="assembly path: row-owner kernel (default), write-once patch pipeline, or slot-map scatter with FP64 atomics")
     args = ap.parse_args()

@@ -170,39 +170,6 @@ static int launch_pipe(const femb_plan* p, const BlockData& b, const DMat& D, pi
     return 0;
 }
 
-template <int NN, int NQ, bool WR, int TEAM>
-static int launch_pipe2(const femb_plan* p, const BlockData& b, const DMat& D, pipe::Args A, cudaStream_t st) {
-    const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
-    constexpr int numTeams = pipe::Cfg2<TEAM>::NUM_TEAMS;
-    const pipe::SmemPlan S = pipe::smem_plan(numTeams, b.prog.maxBlobBytes, b.prog.maxLocal, b.prog.maxElems, b.prog.maxNodeBlocks, p->patchNodes, true);
-    A.inStride = S.inStride;
-    A.offX = S.offX;
-    A.offU = S.offU;
-    A.offL = S.offL;
-    A.offTH = S.offTH;
-    A.offMask = S.offMask;
-    A.accStride = S.accStride;
-    A.offRacc = S.offRacc;
-    A.teamStride = S.teamStride;
-    A.offTeams = S.offTeams;
-    static int numSMs = 0;
-    if (!numSMs) CUDA_TRY(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, p->device));
-    const int64_t wanted = (p->numPatches + numTeams - 1) / numTeams;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(wanted, numSMs));
-    if (A.stats && WR) {
-        CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe2<NN, NQ, WR, TEAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
-        pipe::k_assemble_pipe2<NN, NQ, WR, TEAM, true><<<grid, pipe::Cfg2<TEAM>::THREADS, S.total, st>>>(tb, D, A);
-        return 0;
-    }
-    static int configured = 0;
-    if (S.total > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe2<NN, NQ, WR, TEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
-        configured = S.total;
-    }
-    pipe::k_assemble_pipe2<NN, NQ, WR, TEAM, false><<<grid, pipe::Cfg2<TEAM>::THREADS, S.total, st>>>(tb, D, A);
-    return 0;
-}
-
 template <int NN, int NQ, int TEAM>
 static int launch_pipe_variant(const femb_plan* p, const BlockData& b, const DMat& D, const pipe::Args& A, bool nl, bool wk,
                                bool wr, cudaStream_t st) {
@@ -223,22 +190,14 @@ static int launch_pipe_variant(const femb_plan* p, const BlockData& b, const DMa
 template <int NN, int NQ>
 static int launch_pipe_team(const femb_plan* p, const BlockData& b, const DMat& D, const pipe::Args& A, bool nl, bool wk, bool wr,
                             cudaStream_t st) {
-    if constexpr (NN <= 4) {
-        if (p->splitElements && !nl && wk && p->teamWarps >= 2) {  // half an element per thread (linear model, K wanted)
-            if (p->teamWarps == 4) return wr ? launch_pipe2<NN, NQ, true, 4>(p, b, D, A, st) : launch_pipe2<NN, NQ, false, 4>(p, b, D, A, st);
-            return wr ? launch_pipe2<NN, NQ, true, 2>(p, b, D, A, st) : launch_pipe2<NN, NQ, false, 2>(p, b, D, A, st);
-        }
-    }
     if (p->teamWarps == 1) return launch_pipe_variant<NN, NQ, 1>(p, b, D, A, nl, wk, wr, st);
-    if (p->teamWarps == 4) return launch_pipe_variant<NN, NQ, 4>(p, b, D, A, nl, wk, wr, st);
     return launch_pipe_variant<NN, NQ, 2>(p, b, D, A, nl, wk, wr, st);
 }
 
 bool patch_path_available(const femb_plan* p, bool wk, bool /*wr*/) {
     if (p->usePatch != 1 || !p->patchesBuilt) return false;
-    // worst case over the kernel variants that may run (element-per-thread and half-element-per-thread)
-    const int numTeams = std::max((p->teamWarps == 4) ? 3 : 10 / p->teamWarps, p->splitElements ? (16 / p->teamWarps) : 0);
-    const int elemCap = (p->splitElements && p->teamWarps >= 2) ? 16 * p->teamWarps : 32 * p->teamWarps;
+    const int numTeams = 10 / p->teamWarps;
+    const int elemCap = 32 * p->teamWarps;  // one thread per element
     for (auto& b : p->blocks) {
         if (!b.prog.built) return false;
         if (b.nn > 4 || b.prog.maxElems > elemCap) return false;

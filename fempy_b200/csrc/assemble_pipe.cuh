@@ -86,13 +86,6 @@ __device__ __forceinline__ void team_sync(int team) {
     }
 }
 
-template <int TEAM>
-struct Cfg2 {  // half-element threads: ~100 registers => 20 warps per SM
-    static constexpr int WARPS = (16 / TEAM) * TEAM;
-    static constexpr int THREADS = WARPS * 32;
-    static constexpr int NUM_TEAMS = WARPS / TEAM;
-};
-
 struct Args {
     long long numPatches;
     int PN;
@@ -435,312 +428,6 @@ __global__ void __launch_bounds__(Cfg<TEAM>::THREADS, 1) k_assemble_pipe(const _
             for (int r = tid; r < nOwned; r += TT) {
                 const int gi = lnode[r];
                 double2 s = racc[r];
-                double2* rr = reinterpret_cast<double2*>(A.R) + gi;
-                if (A.accumulate) {
-                    const double2 o = *rr;
-                    *rr = make_double2(o.x + s.x, o.y + s.y);
-                } else {
-                    if (A.loads) {  // R = scatter(R_e) - loads (Problem.py:653)
-                        const double2 f = Ls[r];
-                        s.x -= f.x;
-                        s.y -= f.y;
-                    }
-                    const unsigned m = haveMask ? mask[r] : 0u;
-                    if (m) {  // R[bc] = u - c (AssemblyUtils.py:93)
-                        const double2 u = Us[r];
-                        if (m & 1u) s.x = u.x - A.bcVal[bc_find(A.bcDof, A.nBC, 2 * gi)];
-                        if (m & 2u) s.y = u.y - A.bcVal[bc_find(A.bcDof, A.nBC, 2 * gi + 1)];
-                    }
-                    *rr = s;
-                }
-            }
-        }
-        if (timed) { const long long c1 = clock64(); cOut += c1 - c0; c0 = c1; }
-    }
-    if (timed) {
-        long long* st = A.stats + 16ll * blockIdx.x + 6 * team;
-        st[0] = clock64() - tStart;
-        st[1] = n;
-        st[2] = cWait;
-        st[3] = cCompute;
-        st[4] = cScatter;
-        st[5] = cOut;
-    }
-}
-
-// Same pipeline with every element split over TWO threads (linear model, K wanted): warps [0, TEAM/2) of a team hold
-// the first half of the node pairs of elements t = tid, warps [TEAM/2, TEAM) the second half (element_half).  About
-// half the registers per thread => twice the resident warps; a patch holds <= 16*TEAM elements.
-template <int NN, int NQ, bool WR, int TEAM, bool TIMED>
-__global__ void __launch_bounds__(Cfg2<TEAM>::THREADS, 1) k_assemble_pipe2(const __grid_constant__ femb::Tables<NN, NQ> tb,
-                                                              const femb::DMat D, const Args A) {
-    using namespace femb;
-    static_assert(NN <= 4, "scatter records hold at most 4 nodes per element");
-    constexpr int NUM_TEAMS = Cfg2<TEAM>::NUM_TEAMS;
-    constexpr int TT = TEAM * 32;  // threads of a team
-    constexpr int HT = TT / 2;     // max elements of a patch
-    constexpr bool NL = false, WK = true;
-    constexpr bool NEED_U = WR;
-    constexpr int NH = half_size<NN>();
-
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-
-    const int warp = threadIdx.x >> 5;
-    const int team = warp / TEAM;
-    if (team >= NUM_TEAMS) return;
-    const int tid = threadIdx.x - team * TT;
-    uint64_t* blobBar = bars + team * NI;
-    if (tid == 0) {
-        for (int i = 0; i < NI; ++i) mbar_init(&blobBar[i], 1);
-        fence_barrier_init();
-    }
-    team_sync<TEAM>(team);
-
-    unsigned char* teamSmem = smem + A.offTeams + team * A.teamStride;
-    unsigned char* accBytes = teamSmem + NI * A.inStride;
-    double2* acc2 = reinterpret_cast<double2*>(accBytes);
-    double2* racc0 = reinterpret_cast<double2*>(accBytes + A.offRacc);  // residual partial sums of the two halves
-    double2* racc1 = racc0 + A.PN;
-
-    const long long slot = (long long)blockIdx.x * NUM_TEAMS + team;
-    const long long step = (long long)gridDim.x * NUM_TEAMS;
-    const int n = (slot < A.numPatches) ? (int)((A.numPatches - slot + step - 1) / step) : 0;
-    const bool haveMask = A.maskPerm != nullptr;
-
-    auto issue_blob = [&](int k, int begin, int end) {  // one thread: bulk copy of patch k's blob into stage k % NI
-        const uint32_t bytes = 16u * (uint32_t)(end - begin);
-        mbar_arrive_expect_tx(&blobBar[k % NI], bytes);
-        bulk_g2s(teamSmem + (k % NI) * A.inStride, A.blob + 16ll * begin, bytes, &blobBar[k % NI]);
-    };
-    auto blob_range = [&](int k, int& begin, int& end) {  // plain loads, consumed an iteration later
-        const long long p = slot + (long long)k * step;
-        begin = (k < n) ? __ldg(A.blobPtr + p) : 0;
-        end = (k < n) ? __ldg(A.blobPtr + p + 1) : 0;
-    };
-    auto issue_gathers = [&](int k) {  // whole team: per-node / per-element inputs of patch k (blob must have landed)
-        unsigned char* in = teamSmem + (k % NI) * A.inStride;
-        mbar_wait(&blobBar[k % NI], (k / NI) & 1);
-        const int* hdr = reinterpret_cast<const int*>(in);
-        const int ne = hdr[0], nOwned = hdr[1], nLocal = hdr[2];
-        const BlobLayout L = blob_layout(NN, ne, nOwned, nLocal, hdr[3]);
-        const int* lnode = reinterpret_cast<const int*>(in + L.offLNODE);
-        const int* elem = reinterpret_cast<const int*>(in + L.offELEM);
-        double2* Xs = reinterpret_cast<double2*>(in + A.offX);
-        double2* Us = reinterpret_cast<double2*>(in + A.offU);
-        double2* Ls = reinterpret_cast<double2*>(in + A.offL);
-        double* THs = reinterpret_cast<double*>(in + A.offTH);
-        for (int l = tid; l < nLocal; l += TT) {
-            const int g = lnode[l];
-            cp_async16(&Xs[l], A.coords + g);
-            if (NEED_U) cp_async16(&Us[l], A.states + g);
-            if (WR && A.loads && l < nOwned) cp_async16(&Ls[l], A.loads + g);
-        }
-        for (int t = tid; t < ne; t += TT) cp_async8(&THs[t], A.thick + elem[t]);
-        if (haveMask) {
-            const long long p = slot + (long long)k * step;
-            for (int m = tid; m < A.PN / 4; m += TT) cp_async4(in + A.offMask + 4 * m, A.maskPerm + p * A.PN + 4 * m);
-        }
-    };
-
-    // ---- prologue: blobs of patches 0 and 1 in flight, gathers of patch 0 issued -------------------------------
-    int nextBegin = 0, nextEnd = 0;  // blob range of patch k + 2, loaded while patch k - 1 is processed
-    if (tid == 0) {
-        int b0, e0, b1, e1;
-        blob_range(0, b0, e0);
-        blob_range(1, b1, e1);
-        if (n > 0) issue_blob(0, b0, e0);
-        if (n > 1) issue_blob(1, b1, e1);
-        blob_range(2, nextBegin, nextEnd);
-    }
-    if (n > 0) issue_gathers(0);
-
-    long long cWait = 0, cCompute = 0, cScatter = 0, cOut = 0;
-    const bool timed = TIMED && A.stats && tid == 0 && team < 2;
-    const long long tStart = clock64();
-
-    for (int k = 0; k < n; ++k) {
-        long long c0 = timed ? clock64() : 0;
-        unsigned char* in = teamSmem + (k % NI) * A.inStride;
-        cp_async_wait_all();     // this thread's share of the gathers of patch k
-        team_sync<TEAM>(team);   // ... everyone's; also: the previous write-out no longer reads acc / stage (k-1) % NI
-        if (tid == 0) {
-            if (k + 2 < n) {
-                fence_proxy_async();  // generic-proxy reads of stage (k-1) % NI are done before the bulk engine overwrites it
-                issue_blob(k + 2, nextBegin, nextEnd);
-            }
-            blob_range(k + 3, nextBegin, nextEnd);
-        }
-        if (k + 1 < n) issue_gathers(k + 1);
-        if (timed) { const long long c1 = clock64(); cWait += c1 - c0; c0 = c1; }
-
-        const int* hdr = reinterpret_cast<const int*>(in);
-        const int ne = hdr[0], nOwned = hdr[1], nnb = hdr[3];
-        const BlobLayout L = blob_layout(NN, ne, nOwned, hdr[2], nnb);
-        const int* lnode = reinterpret_cast<const int*>(in + L.offLNODE);
-        const int2* node = reinterpret_cast<const int2*>(in + L.offNODE);
-        const unsigned short* nbRow = reinterpret_cast<const unsigned short*>(in + L.offNBROW);
-        const ElemInfo* einfo = reinterpret_cast<const ElemInfo*>(in + L.offEINFO);
-        const unsigned short* conn = reinterpret_cast<const unsigned short*>(in + L.offCONN);
-        const double2* Xs = reinterpret_cast<const double2*>(in + A.offX);
-        const double2* Us = reinterpret_cast<const double2*>(in + A.offU);
-        const double2* Ls = reinterpret_cast<const double2*>(in + A.offL);
-        const double* THs = reinterpret_cast<const double*>(in + A.offTH);
-        const unsigned char* mask = in + A.offMask;
-
-        // ---- zero the accumulators ----------------------------------------------------------------------------
-        if (WK)
-            for (int idx = tid; idx < 2 * nnb + nOwned; idx += TT) acc2[idx] = make_double2(0.0, 0.0);
-        if (WR)
-            for (int r = tid; r < nOwned; r += TT) racc0[r] = racc1[r] = make_double2(0.0, 0.0);
-
-        // ---- half an element per thread: node-pair blocks + partial residual in registers, then scatter -----------------
-        const int h = (tid >= HT) ? 1 : 0;
-        const int t = tid - h * HT;
-        const bool active = t < ne;
-        const uint4 i0 = reinterpret_cast<const uint4*>(einfo + (active ? t : 0))[0];
-        const uint4 i1 = reinterpret_cast<const uint4*>(einfo + (active ? t : 0))[1];
-        const unsigned rowBasePk[2] = {i0.x, i0.y};
-        const unsigned degPk = i0.z;
-        const unsigned colourPk = active ? i0.w : 0xffffffffu;
-        const unsigned kPk[4] = {i1.x, i1.y, i1.z, i1.w};
-        int ln[NN];
-        double x[NN], y[NN];
-#pragma unroll
-        for (int a = 0; a < NN; ++a) {
-            ln[a] = active ? conn[a * ne + t] : 0;
-            const double2 c = Xs[ln[a]];
-            x[a] = c.x;
-            y[a] = c.y;
-        }
-        const double theta = active ? THs[t] : 0.0;
-        auto body = [&](auto HC) {
-            constexpr int H = decltype(HC)::value;
-            double B[NH][4];
-            element_half<NN, NQ, H>(tb, D, x, y, theta, B);
-            double Rp[NN][2];
-            if (WR) {  // partial R_e = (this half's blocks) q_e
-                double ux[NN], uy[NN];
-#pragma unroll
-                for (int a = 0; a < NN; ++a) {
-                    const double2 q = Us[ln[a]];
-                    ux[a] = q.x;
-                    uy[a] = q.y;
-                    Rp[a][0] = Rp[a][1] = 0.0;
-                }
-#pragma unroll
-                for (int a = 0; a < NN; ++a) {
-#pragma unroll
-                    for (int b = 0; b < NN; ++b) {
-                        double v[4];
-                        if (half_block<NN, H>(B, a, b, v)) {
-                            Rp[a][0] = fma(v[0], ux[b], fma(v[1], uy[b], Rp[a][0]));
-                            Rp[a][1] = fma(v[2], ux[b], fma(v[3], uy[b], Rp[a][1]));
-                        }
-                    }
-                }
-            }
-            team_sync<TEAM>(team);  // accumulators are zero
-            double2* racc = H ? racc1 : racc0;
-#pragma unroll
-            for (int a = 0; a < NN; ++a) {
-                const int numColours = hdr[4 + a];
-                const int colour = (colourPk >> (8 * a)) & 0xff;
-                for (int c = 0; c < numColours; ++c) {
-                    if (colour == c) {
-                        double2* row0 = acc2 + ((rowBasePk[a >> 1] >> (16 * (a & 1))) & 0xffff);
-                        const int deg = (degPk >> (8 * a)) & 0xff;
-                        const unsigned kpack = kPk[a];
-                        double2 s0[NN], s1[NN];
-                        double v[NN][4];
-                        bool mine[NN];
-#pragma unroll
-                        for (int b = 0; b < NN; ++b) {  // this half's blocks of row a are distinct: batch the loads
-                            mine[b] = half_block<NN, H>(B, a, b, v[b]);
-                            if (mine[b]) {
-                                const int kk = (kpack >> (8 * b)) & 0xff;
-                                s0[b] = row0[kk];
-                                s1[b] = row0[kk + deg];
-                            }
-                        }
-#pragma unroll
-                        for (int b = 0; b < NN; ++b) {
-                            if (mine[b]) {
-                                const int kk = (kpack >> (8 * b)) & 0xff;
-                                row0[kk] = make_double2(s0[b].x + v[b][0], s0[b].y + v[b][1]);
-                                row0[kk + deg] = make_double2(s1[b].x + v[b][2], s1[b].y + v[b][3]);
-                            }
-                        }
-                        if (WR) {
-                            const double2 s = racc[ln[a]];
-                            racc[ln[a]] = make_double2(s.x + Rp[a][0], s.y + Rp[a][1]);
-                        }
-                    }
-                    team_sync<TEAM>(team);
-                }
-            }
-        };
-        if (h == 0) body(std::integral_constant<int, 0>{});
-        else body(std::integral_constant<int, 1>{});
-        if (timed) { const long long c1 = clock64(); cCompute += c1 - c0; c0 = c1; }
-
-        // ---- constrained rows: zeros, occurrence count on the diagonal (AssemblyUtils.py:55-60) --------------------
-        if (haveMask) {
-            if (WK) {
-                for (int r = tid; r < nOwned; r += TT) {
-                    const unsigned m = mask[r];
-                    if (m) {
-                        const int2 nd = node[r];
-                        const int start = nd.y & 0xffff, deg = (nd.y >> 16) & 0xff, diagK = (nd.y >> 24) & 0xff;
-                        double* rows = reinterpret_cast<double*>(acc2 + 2 * start + r);
-                        const int gi = lnode[r];
-                        for (int c = 0; c < 2; ++c) {
-                            if (m & (1u << c)) {
-                                for (int q = 0; q < 2 * deg; ++q) rows[c * 2 * deg + q] = 0.0;
-                                rows[c * 2 * deg + 2 * diagK + c] = A.bcCount[bc_find(A.bcDof, A.nBC, 2 * gi + c)];
-                            }
-                        }
-                    }
-                }
-            }
-            team_sync<TEAM>(team);
-        }
-        if (timed) { const long long c1 = clock64(); cScatter += c1 - c0; c0 = c1; }
-
-        // ---- write-out: the accumulators mirror the CSR rows, so this is a 16-byte-per-thread streaming copy --------
-        if (WK && !(A.debug & 16)) {
-            double2* K2 = reinterpret_cast<double2*>(A.K);
-            const int total = 2 * nnb;
-            for (int base = tid; base < total; base += 4 * TT) {  // four 16-byte pieces in flight per thread
-                int rr[4];
-                int2 nd[4];
-                double2 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) rr[u] = (base + u * TT < total) ? nbRow[(base + u * TT) >> 1] : 0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    nd[u] = node[rr[u]];
-                    v[u] = acc2[min(base + u * TT, total - 1) + rr[u]];  // one pad double2 per preceding owned node
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int sidx = base + u * TT;
-                    if (sidx < total) {
-                        const long long g = 2ll * nd[u].x + (sidx - 2 * (nd[u].y & 0xffff));
-                        if (!A.accumulate) {
-                            st_stream(K2 + g, v[u].x, v[u].y);
-                        } else {
-                            const double2 o = K2[g];
-                            K2[g] = make_double2(o.x + v[u].x, o.y + v[u].y);
-                        }
-                    }
-                }
-            }
-        }
-        if (WR && !(A.debug & 32)) {
-            for (int r = tid; r < nOwned; r += TT) {
-                const int gi = lnode[r];
-                double2 s = make_double2(racc0[r].x + racc1[r].x, racc0[r].y + racc1[r].y);
                 double2* rr = reinterpret_cast<double2*>(A.R) + gi;
                 if (A.accumulate) {
                     const double2 o = *rr;

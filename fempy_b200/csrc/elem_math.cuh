@@ -272,99 +272,6 @@ __device__ __forceinline__ void sym_block(const double (&Kd)[NN][3], const doubl
 
 
 // ---------------------------------------------------------------------------------------------
-// Half an element per thread (linear model): the NN(NN+1)/2 symmetric node pairs (a <= b, row-major,
-// diagonal included) are split between two threads, H = 0 takes the first half, H = 1 the rest.  Each
-// thread repeats the (cheap) geometry and accumulates only the geometric sums of ITS pairs, so it needs
-// about half the registers of element_sym -- twice as many warps fit on an SM.
-//   B[q - begin][4] = 2x2 block of pair q = (a, b), row-major [xx xy yx yy]  (for a == b: xy == yx)
-// ---------------------------------------------------------------------------------------------
-template <int NN>
-__host__ __device__ constexpr int pairq(int a, int b) {  // a <= b
-    return a * NN - a * (a - 1) / 2 + (b - a);
-}
-template <int NN, int H>
-__host__ __device__ constexpr int half_begin() {
-    return H == 0 ? 0 : (NN * (NN + 1) / 2) / 2;
-}
-template <int NN, int H>
-__host__ __device__ constexpr int half_end() {
-    return H == 0 ? (NN * (NN + 1) / 2) / 2 : NN * (NN + 1) / 2;
-}
-template <int NN, int H>
-__host__ __device__ constexpr bool half_owns(int a, int b) {  // a <= b
-    return pairq<NN>(a, b) >= half_begin<NN, H>() && pairq<NN>(a, b) < half_end<NN, H>();
-}
-template <int NN>
-__host__ __device__ constexpr int half_size() {
-    return NN * (NN + 1) / 2 - (NN * (NN + 1) / 2) / 2;
-}
-
-template <int NN, int NQ, int H>
-__device__ __forceinline__ void element_half(const Tables<NN, NQ>& tb, const DMat& D, const double (&x)[NN],
-                                             const double (&y)[NN], const double theta, double (&B)[half_size<NN>()][4]) {
-    constexpr int Q0 = half_begin<NN, H>();
-#pragma unroll
-    for (int q = 0; q < half_size<NN>(); ++q) B[q][0] = B[q][1] = B[q][2] = B[q][3] = 0.0;
-#pragma unroll(point_unroll<NN, NQ>())
-    for (int p = 0; p < NQ; ++p) {
-        double G0[NN], G1[NN];
-        const double det = point_gradients<NN, NQ>(tb, p, x, y, G0, G1);
-        const double sc = tb.w[p] * det * theta;
-#pragma unroll
-        for (int a = 0; a < NN; ++a) {
-            const double A0 = G0[a] * sc, A1 = G1[a] * sc;
-#pragma unroll
-            for (int b = a; b < NN; ++b) {
-                if (half_owns<NN, H>(a, b)) {
-                    double(&s)[4] = B[pairq<NN>(a, b) - Q0];
-                    s[0] = fma(A0, G0[b], s[0]);
-                    s[1] = fma(A0, G1[b], s[1]);
-                    if (a != b) s[2] = fma(A1, G0[b], s[2]);
-                    s[3] = fma(A1, G1[b], s[3]);
-                }
-            }
-        }
-    }
-    // apply D once:  [[D00 S00 + D22 S11, D01 S01 + D22 S10], [D01 S10 + D22 S01, D11 S11 + D22 S00]]
-#pragma unroll
-    for (int a = 0; a < NN; ++a) {
-#pragma unroll
-        for (int b = a; b < NN; ++b) {
-            if (half_owns<NN, H>(a, b)) {
-                double(&s)[4] = B[pairq<NN>(a, b) - Q0];
-                const double s00 = s[0], s01 = s[1], s10 = (a == b) ? s[1] : s[2], s11 = s[3];
-                s[0] = fma(D.d00, s00, D.d22 * s11);
-                s[1] = fma(D.d01, s01, D.d22 * s10);
-                s[2] = fma(D.d01, s10, D.d22 * s01);
-                s[3] = fma(D.d11, s11, D.d22 * s00);
-            }
-        }
-    }
-}
-
-// block (a, b) of the element matrix as seen by half H: returns false if H does not hold it
-template <int NN, int H>
-__device__ __forceinline__ bool half_block(const double (&B)[half_size<NN>()][4], int a, int b, double (&v)[4]) {
-    constexpr int Q0 = half_begin<NN, H>();
-    if (a <= b) {
-        if (!half_owns<NN, H>(a, b)) return false;
-        const double(&s)[4] = B[pairq<NN>(a, b) - Q0];
-        v[0] = s[0];
-        v[1] = s[1];
-        v[2] = s[2];
-        v[3] = s[3];
-    } else {
-        if (!half_owns<NN, H>(b, a)) return false;
-        const double(&s)[4] = B[pairq<NN>(b, a) - Q0];
-        v[0] = s[0];
-        v[1] = s[2];
-        v[2] = s[1];
-        v[3] = s[3];
-    }
-    return true;
-}
-
-// ---------------------------------------------------------------------------------------------
 // One node-row strip of an element, one thread: Krow[b][4] = block (a,b) for all b, Ra[2].
 // Used for the larger families (9+ nodes) where a whole element does not fit in registers.
 // ---------------------------------------------------------------------------------------------

@@ -94,7 +94,6 @@ struct femb_plan {
     // node patches (shared by all blocks)
     bool patchesBuilt = false;
     int patchNodes = 0;          // owned nodes per patch
-    int splitElements = 0;       // 1: linear K assemblies put half an element on each thread (patches hold <= 16*teamWarps elements)
     int teamWarps = 2;           // warps that share a patch in the assembly kernel (1 or 2): a patch holds <= 32*teamWarps elements
     int64_t numPatches = 0;
     double* d_hintCoords = nullptr;  // optional locality hint (node coordinates at plan time)

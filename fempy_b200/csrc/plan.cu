@@ -455,11 +455,8 @@ extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t valu
         p->patchNodes = (int)value;
     } else if (!strcmp(name, "team_warps")) {
         if (p->finalized) return fail("femb_plan_set_option: team_warps must be set before finalize");
-        if (value != 1 && value != 2 && value != 4) return fail("femb_plan_set_option: team_warps must be 1, 2 or 4");
+        if (value != 1 && value != 2) return fail("femb_plan_set_option: team_warps must be 1 or 2");
         p->teamWarps = (int)value;
-    } else if (!strcmp(name, "split_elements")) {
-        if (p->finalized) return fail("femb_plan_set_option: split_elements must be set before finalize");
-        p->splitElements = value != 0;
     } else if (!strcmp(name, "use_patches") || !strcmp(name, "assembly_path")) {
         if (value < 0 || value > 2) return fail("femb_plan_set_option: assembly_path must be 0 (scatter), 1 (patch pipeline) or 2 (row owner)");
         if (value == 1 && p->finalized && !p->patchesBuilt) return fail("femb_plan_set_option: the patch pipeline must be selected before finalize");
@@ -478,7 +475,6 @@ extern "C" int64_t femb_plan_get_info(const femb_plan* p, const char* name) {
     if (!strcmp(name, "num_patches")) return p->numPatches;
     if (!strcmp(name, "patch_nodes")) return p->patchNodes;
     if (!strcmp(name, "team_warps")) return p->teamWarps;
-    if (!strcmp(name, "split_elements")) return p->splitElements;
     if (!strcmp(name, "patch_elems_total")) {
         int64_t t = 0;
         for (auto& b : p->blocks) t += b.prog.totalElems;

@@ -371,7 +371,7 @@ static int build_patches_once(femb_plan* p, int64_t& launches) {
     if (!any) return 0;
     const int64_t N = p->numNodes;
     cudaStream_t st = p->stream;
-    if (p->patchNodes <= 0) p->patchNodes = DEFAULT_PATCH_NODES_PER_WARP * p->teamWarps / ((p->splitElements && p->teamWarps >= 2) ? 2 : 1);
+    if (p->patchNodes <= 0) p->patchNodes = DEFAULT_PATCH_NODES_PER_WARP * p->teamWarps;
     p->patchNodes = std::min(1024, ((p->patchNodes + 3) / 4) * 4);  // multiple of 4: a patch's slice of the permuted BC mask is fetched 4 bytes at a time
     const int PN = p->patchNodes;
     p->numPatches = (N + PN - 1) / PN;
@@ -501,7 +501,7 @@ int build_patches(femb_plan* p, int64_t& launches) {
         TRY(build_patches_once(p, launches));
         int worst = 0;
         for (auto& b : p->blocks) worst = std::max(worst, b.prog.maxElems);
-        const int target = (p->splitElements && p->teamWarps >= 2) ? 16 * p->teamWarps : 32 * p->teamWarps;
+        const int target = 32 * p->teamWarps;  // one thread per element
         if (userFixed || worst <= target || p->patchNodes <= 4) return 0;
         const int next = std::max(4, (int)((int64_t)p->patchNodes * target / worst) / 4 * 4);
         const int shrunk = (next >= p->patchNodes) ? p->patchNodes - 4 : next;

@@ -12,7 +12,6 @@ N = coords.shape[0]; E = n * n
 plan = AssemblyPlan(N); plan.setLocalityHint(coords); team = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 plan.setOption("assembly_path", 1)
 plan.setOption("team_warps", team)
-plan.setOption("split_elements", int(sys.argv[5]) if len(sys.argv) > 5 else 1)
 if pn: plan.setOption("patch_nodes", pn)
 dbg = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 Nn, dN, w = Elements.QuadElement2D(1).tables(); plan.addBlock(Nn, dN, w, conn["quad"]); plan.finalize()
