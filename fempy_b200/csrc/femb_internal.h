@@ -106,6 +106,9 @@ struct femb_plan {
     int2* d_corners = nullptr;   // per (node, adjacent element): {element, a | k0<<4 | k1<<11 | k2<<18 | k3<<25} (row-owner kernel)
     int maxDeg = 0;              // largest node degree
     // boundary conditions, de-duplicated on the host with the reference's semantics
+    std::vector<int64_t> bcRawDof;  // the lists as last given (identical lists are not processed again)
+    std::vector<double> bcRawVal;
+    bool bcValid = false;
     int64_t nBC = 0;
     int* d_bcDof = nullptr;       // sorted ascending
     double* d_bcVal = nullptr;    // last value given for the DOF

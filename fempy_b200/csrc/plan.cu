@@ -552,6 +552,12 @@ extern "C" int femb_plan_pattern(femb_plan* p, int64_t* indptr, int64_t* indices
 extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const double* bcVal, int64_t nBC) {
     TRY(need_final(p, "femb_plan_set_bcs"));
     TRY(use_device(p));
+    // The host-pointer API passes the BC lists on every call (the reference rebuilds them per assembly,
+    // Problem.py:471-483); identical lists are recognised and cost nothing after the first call.
+    if (nBC > 0 && bcDof && bcVal && p->bcValid && (int64_t)p->bcRawDof.size() == nBC &&
+        !memcmp(p->bcRawDof.data(), bcDof, nBC * sizeof(int64_t)) && !memcmp(p->bcRawVal.data(), bcVal, nBC * sizeof(double)))
+        return 0;
+    p->bcValid = false;
     dfree(p->d_bcDof);
     dfree(p->d_bcVal);
     dfree(p->d_bcCount);
@@ -643,5 +649,8 @@ extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const doubl
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     if (flag) return fail("femb_plan_set_bcs: a BC is applied to a node that belongs to no element (no diagonal entry in the pattern)");
     p->nBC = (int64_t)n;
+    p->bcRawDof.assign(bcDof, bcDof + nBC);
+    p->bcRawVal.assign(bcVal, bcVal + nBC);
+    p->bcValid = true;
     return 0;
 }
