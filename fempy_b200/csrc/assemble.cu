@@ -213,7 +213,11 @@ bool patch_path_available(const femb_plan* p, bool wk, bool /*wr*/) {
 // row-owner path (assemble_rows.cuh): one thread per node row, redundant geometry, no atomics / barriers
 // =============================================================================================
 bool rows_path_available(const femb_plan* p) {
-    return p->usePatch == 2 && p->blocks.size() == 1 && p->blocks[0].nn <= 4 && p->d_connE && p->d_corners && p->maxDeg <= rows::MAXD;
+    if (p->usePatch != 2 || p->blocks.size() != 1 || !p->d_connE || !p->d_corners || p->maxDeg > rows::MAXD) return false;
+    const int nn = p->blocks[0].nn;  // 16-node quads stay on the scatter kernels (strip of 64 doubles per thread)
+    if (nn > 12) return false;
+    const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * (sizeof(double2) + 1) + rows::BLOCK * sizeof(double2);
+    return smem <= 200 * 1024;
 }
 
 template <int NN, int NQ, bool NL, bool WK, bool WR>
@@ -233,7 +237,7 @@ static int launch_rows(const femb_plan* p, const BlockData& b, const DMat& D, co
 template <int NN, int NQ>
 static int launch_rows_variant(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, bool nl, bool wk,
                                bool wr, cudaStream_t st) {
-    if constexpr (NN <= 4) {
+    if constexpr (NN <= 12) {
         if (!nl) {
             if (wk && wr) return launch_rows<NN, NQ, false, true, true>(p, b, D, A, st);
             if (wk) return launch_rows<NN, NQ, false, true, false>(p, b, D, A, st);

@@ -33,8 +33,8 @@ struct Args {
     const int* nrowptr;
     const int* ncols;
     const int* adjPtr;
-    const int2* corners;     // {element, a | k0<<4 | k1<<11 | k2<<18 | k3<<25} per (node, adjacent element)
-    const int4* connE;       // element-major connectivity, padded to 4 nodes
+    const void* corners;     // corner records (plan.cu: k_corners): int2 for NN <= 4, int4 for NN <= 12
+    const int4* connE;       // element-major connectivity, ceil(NN/4) words per element
     const double2* coords;
     const double2* states;
     const double* thick;
@@ -53,11 +53,19 @@ __device__ __forceinline__ void st_stream(double2* p, const double2 v) {  // K i
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y));
 }
 
+// resident threads per SM the register allocation aims at: 20 warps for the 3/4-node families (<= 96 registers),
+// 12 for 6 nodes, 8 for 9/10 nodes (the node-row strip alone is 4*NN doubles)
+template <int NN, bool NL>
+__host__ __device__ constexpr int resident_threads() {
+    return NN <= 4 ? (NL ? 512 : 640) : (NN <= 6 ? 384 : 256);
+}
+
 template <int NN, int NQ, bool NL, bool WK, bool WR>
-__global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const __grid_constant__ femb::DMat D,
+__global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const __grid_constant__ femb::DMat D,
                                                         const Args A) {
     using namespace femb;
-    static_assert(NN <= 4, "element-major connectivity holds at most 4 nodes");
+    static_assert(NN <= 12, "corner records hold at most 12 slot positions");
+    constexpr int CW = (NN + 3) / 4;  // connectivity words per element
     extern __shared__ double2 acc[];  // [2*maxDeg][BLOCK], swizzled
 #if ROWS_TRACE
     long long tStart = clock64(), gStart;
@@ -77,11 +85,30 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
 
     const int c0 = valid ? __ldg(A.adjPtr + i) : 0, c1 = valid ? __ldg(A.adjPtr + i + 1) : 0;
     for (int c = c0; c < c1; ++c) {
-        const int2 rec = (KNOCK & 4) ? make_int2(c & 0xffff, ((c - c0) & 3) | (1 << 11) | (2 << 18) | (3 << 25)) : __ldg(A.corners + c);
-        const unsigned packed = (unsigned)rec.y;
-        const int a = packed & 0xf;
-        const int4 cn = (KNOCK & 4) ? make_int4((int)i, (int)i + 1, (int)i + 2, (int)i + 3) : __ldg(A.connE + rec.x);
-        const int node[4] = {cn.x, cn.y, cn.z, cn.w};
+        int e, a, node[4 * CW];
+        unsigned kw[CW];  // slot positions: 7-bit fields from bit 4 (NN <= 4) or bytes
+        if constexpr (NN <= 4) {
+            const int2 rec = (KNOCK & 4) ? make_int2(c & 0xffff, ((c - c0) & 3) | (1 << 11) | (2 << 18) | (3 << 25))
+                                         : __ldg(reinterpret_cast<const int2*>(A.corners) + c);
+            e = rec.x;
+            kw[0] = (unsigned)rec.y;
+            a = rec.y & 0xf;
+        } else {
+            const int4 rec = __ldg(reinterpret_cast<const int4*>(A.corners) + c);
+            e = rec.x & 0x0fffffff;
+            a = (int)((unsigned)rec.x >> 28);
+            kw[0] = (unsigned)rec.y;
+            if (CW > 1) kw[1] = (unsigned)rec.z;
+            if (CW > 2) kw[CW - 1] = (unsigned)rec.w;
+        }
+#pragma unroll
+        for (int w = 0; w < CW; ++w) {
+            const int4 cn = (KNOCK & 4) ? make_int4((int)i, (int)i + 1, (int)i + 2, (int)i + 3) : __ldg(A.connE + (long long)e * CW + w);
+            node[4 * w] = cn.x;
+            node[4 * w + 1] = cn.y;
+            node[4 * w + 2] = cn.z;
+            node[4 * w + 3] = cn.w;
+        }
         double x[NN], y[NN], ux[NN], uy[NN];
 #pragma unroll
         for (int b = 0; b < NN; ++b) {
@@ -97,7 +124,7 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
                 ux[b] = uy[b] = 0.0;
             }
         }
-        const double theta = (KNOCK & 2) ? 1.0 + 1e-9 * rec.x : __ldg(A.thick + rec.x);
+        const double theta = (KNOCK & 2) ? 1.0 + 1e-9 * e : __ldg(A.thick + e);
 
         // node-row strip of K_e: blocks (a, b), b = 0..NN-1, and the residual pair of node a
         double Kr[NN][4];
@@ -218,7 +245,7 @@ __global__ void __launch_bounds__(BLOCK, (NL ? 512 : 640) / BLOCK) k_assemble_ro
         } else if (WK) {
 #pragma unroll
             for (int b = 0; b < NN; ++b) {
-                const int kk = (packed >> (4 + 7 * b)) & 0x7f;  // position of node b in my sorted row (plan time)
+                const int kk = (NN <= 4) ? (kw[0] >> (4 + 7 * b)) & 0x7f : (kw[b >> 2] >> (8 * (b & 3))) & 0xff;  // position of node b in my sorted row (plan time)
                 double2& s0 = slot(kk);
                 double2& s1 = slot(deg + kk);
                 const double2 o0 = s0, o1 = s1;

@@ -102,8 +102,8 @@ struct femb_plan {
     long long* d_pipeStats = nullptr;  // measurement only
     int debugFlags = 0;                // measurement only
     int usePatch = 2;            // assembly path: 2 row-owner kernel, 1 write-once patch pipeline, 0 slot-map scatter with FP64 atomics
-    int4* d_connE = nullptr;     // element-major connectivity (single-block plans; row-owner kernel)
-    int2* d_corners = nullptr;   // per (node, adjacent element): {element, a | k0<<4 | k1<<11 | k2<<18 | k3<<25} (row-owner kernel)
+    int4* d_connE = nullptr;     // element-major connectivity, ceil(nn/4) words per element (single-block plans; row-owner kernel)
+    void* d_corners = nullptr;   // per (node, adjacent element) corner record, int2 (nn <= 4) or int4 (plan.cu: k_corners)
     int maxDeg = 0;              // largest node degree
     // boundary conditions, de-duplicated on the host with the reference's semantics
     std::vector<int64_t> bcRawDof;  // the lists as last given (identical lists are not processed again)

@@ -141,39 +141,46 @@ __global__ void k_dof_pattern(long long numNodes, int s, const int* __restrict__
 }
 
 
-// element-major connectivity (padded to 4 nodes per element) for the row-owner kernel
+// element-major connectivity for the row-owner kernel: ceil(nn/4) int4 words per element, padded with -1
 __global__ void k_conn_elem_major(const int* __restrict__ conn, long long E, int nn, int4* __restrict__ connE) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    int v[4] = {-1, -1, -1, -1};
-    for (int a = 0; a < nn && a < 4; ++a) v[a] = conn[(long long)a * E + e];
-    connE[e] = make_int4(v[0], v[1], v[2], v[3]);
+    const int cw = (nn + 3) / 4;
+    for (int w = 0; w < cw; ++w) {
+        int v[4] = {-1, -1, -1, -1};
+        for (int a = 4 * w; a < nn && a < 4 * w + 4; ++a) v[a - 4 * w] = conn[(long long)a * E + e];
+        connE[e * cw + w] = make_int4(v[0], v[1], v[2], v[3]);
+    }
 }
 
-// corner records of the row-owner kernel: for every (node, adjacent element) the element id and, packed in one word,
-// the node's local index a in the element (4 bits) and the position k_b (7 bits each) of each element node in the
-// node's sorted neighbour list
+// Corner records of the row-owner kernel: for every (node, adjacent element), in adjacency order, the element id, the
+// node's local index a in the element and the position k_b of each element node in the node's sorted neighbour list.
+//   nn <= 4: int2 {e, a | k_0 << 4 | k_1 << 11 | k_2 << 18 | k_3 << 25}            (7-bit positions)
+//   nn <= 12: int4 {e | a << 28, k_0..k_3, k_4..k_7, k_8..k_11}                      (one byte per position)
 __global__ void k_corners(long long N, const int* __restrict__ nrowptr, const int* __restrict__ ncols,
                           const int* __restrict__ adjPtr, const int* __restrict__ adj, const int4* __restrict__ connE, int nn,
-                          int2* __restrict__ corners) {
+                          void* __restrict__ corners) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int off = nrowptr[i], deg = nrowptr[i + 1] - off;
+    const int cw = (nn + 3) / 4;
     for (int c = adjPtr[i]; c < adjPtr[i + 1]; ++c) {
         const int e = adj[c];
-        const int4 cn = connE[e];
-        const int node[4] = {cn.x, cn.y, cn.z, cn.w};
-        unsigned packed = 0;
+        unsigned a = 0, packed = 0, kb[3] = {0u, 0u, 0u};
         for (int b = 0; b < nn; ++b) {
-            if (node[b] == (int)i) packed |= (unsigned)b;
+            const int4 cn = connE[(long long)e * cw + (b >> 2)];
+            const int node = (b & 3) == 0 ? cn.x : (b & 3) == 1 ? cn.y : (b & 3) == 2 ? cn.z : cn.w;
+            if (node == (int)i) a = (unsigned)b;
             int lo = 0, hi = deg;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (ncols[off + mid] < node[b]) lo = mid + 1; else hi = mid;
+                if (ncols[off + mid] < node) lo = mid + 1; else hi = mid;
             }
-            packed |= (unsigned)lo << (4 + 7 * b);
+            if (nn <= 4) packed |= (unsigned)lo << (4 + 7 * b);
+            else kb[b >> 2] |= (unsigned)lo << (8 * (b & 3));
         }
-        corners[c] = make_int2(e, (int)packed);
+        if (nn <= 4) reinterpret_cast<int2*>(corners)[c] = make_int2(e, (int)(packed | a));
+        else reinterpret_cast<int4*>(corners)[c] = make_int4((int)((unsigned)e | (a << 28)), (int)kb[0], (int)kb[1], (int)kb[2]);
     }
 }
 
@@ -356,11 +363,12 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
         k_max_int<<<grid_for(N, 256), 256, 0, st>>>(d_deg, N, p->d_flag);
         CUDA_TRY(cudaMemcpyAsync(&p->maxDeg, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         launches++;
-        if (p->blocks.size() == 1 && p->blocks[0].nn <= 4) {
+        if (p->blocks.size() == 1 && p->blocks[0].nn <= 12 && p->blocks[0].numElems < (1ll << 28)) {
             auto& b = p->blocks[0];
-            CUDA_TRY(cudaMalloc(&p->d_connE, b.numElems * sizeof(int4)));
+            const int cw = (b.nn + 3) / 4;
+            CUDA_TRY(cudaMalloc(&p->d_connE, b.numElems * cw * sizeof(int4)));
             k_conn_elem_major<<<grid_for(b.numElems, 256), 256, 0, st>>>(b.d_conn, b.numElems, b.nn, p->d_connE);
-            CUDA_TRY(cudaMalloc(&p->d_corners, std::max<int64_t>(totalAdj, 1) * sizeof(int2)));
+            CUDA_TRY(cudaMalloc(&p->d_corners, std::max<int64_t>(totalAdj, 1) * (b.nn <= 4 ? sizeof(int2) : sizeof(int4))));
             k_corners<<<grid_for(N, 128), 128, 0, st>>>(N, p->d_nrowptr, p->d_ncols, d_adjPtr, d_adj, p->d_connE, b.nn, p->d_corners);
             launches += 2;
         }

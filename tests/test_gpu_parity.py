@@ -326,13 +326,13 @@ def _check_against_oracle(plan, elType, case, launchesExpected):
 
 @pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29), ("quad9", 14)])
 def test_default_path_matches_scatter_path_and_oracle(elType, n):
-    """default: row-owner kernel for the 3/4-node families (1 launch), scatter kernels otherwise"""
+    """default: row-owner kernel for single-block meshes of 3/4/6/9/10-node elements (1 launch); scatter kernels otherwise"""
     case = _path_case(elType, n)
     coords, conn = case[0], case[1]
     plan = _raw_plan(elType, coords, conn)
     assert plan.info("assembly_path") == 2
     onRowsPath = plan.info("rows_path") == 1
-    assert onRowsPath == (elType != "quad9")
+    assert onRowsPath
     K1, R1 = _check_against_oracle(plan, elType, case, launchesExpected=1 if onRowsPath else 3)
     plan.setOption("assembly_path", 0)
     mat = make_cm(0).material()
