@@ -340,24 +340,47 @@ __device__ __forceinline__ void element_row(const Tables<NN, NQ>& tb, const DMat
 }
 
 // ---------------------------------------------------------------------------------------------
-// Element function at the Gauss points + reduction (Element.py:163-273)
+// Element functions at the Gauss points (Element.py:163-273, IsoPlaneStress.py:187-227): mass density or von Mises
+// stress, plus signed detJ for the "integrate" reduction.
+// The state gradient needs no per-node dN/dx: with H = sum_b dN_b (x) q_b (reference-space gradient of the state) and
+// adj = det * J^-1, u' = adj . H / det.  The point loop is kept rolled so that the tables reach the FP64 pipe through
+// uniform registers (an FP64 instruction with a constant-bank operand issues at half rate on sm_100).
 // ---------------------------------------------------------------------------------------------
 template <int NN, int NQ, bool NL>
-__device__ __forceinline__ void element_function(const Tables<NN, NQ>& tb, const DMat& D, const int func,
-                                                 const double (&x)[NN], const double (&y)[NN], const double (&ux)[NN],
-                                                 const double (&uy)[NN], double (&vals)[NQ], double (&dets)[NQ]) {
+__device__ __forceinline__ void point_function(const Tables<NN, NQ>& tb, const DMat& D, const int func, const int p,
+                                               const double (&x)[NN], const double (&y)[NN], const double (&ux)[NN],
+                                               const double (&uy)[NN], double& val, double& detOut) {
+    {
+        double J00 = 0.0, J01 = 0.0, J10 = 0.0, J11 = 0.0;
 #pragma unroll
-    for (int p = 0; p < NQ; ++p) {
-        double G0[NN], G1[NN];
-        dets[p] = point_gradients<NN, NQ>(tb, p, x, y, G0, G1);
-        if (func == 0) {
-            vals[p] = D.rho;
-        } else {
-            double u[2][2], sig[3];
-            state_gradient<NN>(G0, G1, ux, uy, u);
-            stresses<NL>(D, u, sig);
-            vals[p] = von_mises(D, sig);
+        for (int b = 0; b < NN; ++b) {
+            J00 = fma(tb.dN[p][0][b], x[b], J00);
+            J01 = fma(tb.dN[p][0][b], y[b], J01);
+            J10 = fma(tb.dN[p][1][b], x[b], J10);
+            J11 = fma(tb.dN[p][1][b], y[b], J11);
         }
+        const double det = J00 * J11 - J01 * J10;
+        double v = D.rho;
+        if (func != 0) {
+            double H00 = 0.0, H01 = 0.0, H10 = 0.0, H11 = 0.0;  // H[k][s] = sum_b dN_b/dxi_k * q_b[s]
+#pragma unroll
+            for (int b = 0; b < NN; ++b) {
+                H00 = fma(tb.dN[p][0][b], ux[b], H00);
+                H01 = fma(tb.dN[p][0][b], uy[b], H01);
+                H10 = fma(tb.dN[p][1][b], ux[b], H10);
+                H11 = fma(tb.dN[p][1][b], uy[b], H11);
+            }
+            const double r = fast_rcp(det);
+            double u[2][2], sig[3];  // u[s][d] = d u_s / d x_d = (adj . H)[d][s] / det, adj = [[J11, -J01], [-J10, J00]]
+            u[0][0] = (J11 * H00 - J01 * H10) * r;
+            u[0][1] = (J00 * H10 - J10 * H00) * r;
+            u[1][0] = (J11 * H01 - J01 * H11) * r;
+            u[1][1] = (J00 * H11 - J10 * H01) * r;
+            stresses<NL>(D, u, sig);
+            v = von_mises(D, sig);
+        }
+        val = v;
+        detOut = det;
     }
 }
 

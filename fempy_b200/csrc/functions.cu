@@ -44,30 +44,20 @@ __global__ void __launch_bounds__(128) k_function(const __grid_constant__ Tables
         ux[a] = q.x;
         uy[a] = q.y;
     }
-    double vals[NQ], dets[NQ];
-    element_function<NN, NQ, NL>(tb, D, func, x, y, ux, uy, vals, dets);
-    if (reduction == FEMB_REDUCE_NONE) {
-#pragma unroll
-        for (int p = 0; p < NQ; ++p) F.out[e * NQ + p] = vals[p];
-        return;
-    }
+    // rolled loop over the Gauss points, reduction on the fly (Element.py:221-273)
     double r = 0.0;
-    if (reduction == FEMB_REDUCE_SUM || reduction == FEMB_REDUCE_MEAN) {
-#pragma unroll
-        for (int p = 0; p < NQ; ++p) r += vals[p];
-        if (reduction == FEMB_REDUCE_MEAN) r /= (double)NQ;
-    } else if (reduction == FEMB_REDUCE_INTEGRATE) {
-#pragma unroll
-        for (int p = 0; p < NQ; ++p) r = fma(vals[p] * dets[p], tb.w[p], r);
-    } else if (reduction == FEMB_REDUCE_MIN) {
-        r = vals[0];
-#pragma unroll
-        for (int p = 1; p < NQ; ++p) r = fmin(r, vals[p]);
-    } else {
-        r = vals[0];
-#pragma unroll
-        for (int p = 1; p < NQ; ++p) r = fmax(r, vals[p]);
+#pragma unroll 1
+    for (int p = 0; p < NQ; ++p) {
+        double v, det;
+        point_function<NN, NQ, NL>(tb, D, func, p, x, y, ux, uy, v, det);
+        if (reduction == FEMB_REDUCE_NONE) F.out[e * NQ + p] = v;
+        else if (reduction == FEMB_REDUCE_SUM || reduction == FEMB_REDUCE_MEAN) r += v;
+        else if (reduction == FEMB_REDUCE_INTEGRATE) r = fma(v * det, tb.w[p], r);
+        else if (reduction == FEMB_REDUCE_MIN) r = p ? fmin(r, v) : v;
+        else r = p ? fmax(r, v) : v;
     }
+    if (reduction == FEMB_REDUCE_NONE) return;
+    if (reduction == FEMB_REDUCE_MEAN) r /= (double)NQ;
     F.out[e] = r;
 }
 
