@@ -213,25 +213,31 @@ bool patch_path_available(const femb_plan* p, bool wk, bool /*wr*/) {
 // row-owner path (assemble_rows.cuh): one thread per node row, redundant geometry, no atomics / barriers
 // =============================================================================================
 bool rows_path_available(const femb_plan* p) {
-    if (p->usePatch != 2 || p->blocks.size() != 1 || !p->d_connE || !p->d_corners || p->maxDeg > rows::MAXD) return false;
-    const int nn = p->blocks[0].nn;  // 16-node quads stay on the scatter kernels (strip of 64 doubles per thread)
-    if (nn > 12) return false;
+    // every block needs corner records (<= 12 nodes per element: 16-node quads stay on the scatter kernels, their strip
+    // alone is 64 doubles per thread)
+    if (p->usePatch != 2 || !p->rowsBuilt || p->maxDeg > rows::MAXD) return false;
     const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * (sizeof(double2) + 1) + rows::BLOCK * sizeof(double2);
     return smem <= 200 * 1024;
 }
 
-template <int NN, int NQ, bool NL, bool WK, bool WR>
-static int launch_rows(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
+template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB>
+static int launch_rows_mb(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
     const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
     // accumulator rows + residual pairs + write-out owner table
     const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * (sizeof(double2) + 1) + rows::BLOCK * sizeof(double2);
     static size_t configured = 0;
     if (smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    rows::k_assemble_rows<NN, NQ, NL, WK, WR><<<grid_for(p->numNodes, rows::BLOCK), rows::BLOCK, smem, st>>>(tb, D, A);
+    rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB><<<grid_for(p->numNodes, rows::BLOCK), rows::BLOCK, smem, st>>>(tb, D, A);
     return 0;
+}
+
+template <int NN, int NQ, bool NL, bool WK, bool WR>
+static int launch_rows(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
+    if (p->blocks.size() > 1) return launch_rows_mb<NN, NQ, NL, WK, WR, true>(p, b, D, A, st);
+    return launch_rows_mb<NN, NQ, NL, WK, WR, false>(p, b, D, A, st);
 }
 
 template <int NN, int NQ>
@@ -298,7 +304,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
     const bool patchPath = !rowsPath && patch_path_available(p, wk, wr);
     const bool multi = p->blocks.size() > 1;
     const bool bcs = applyBCs && p->nBC > 0;
-    if (!(patchPath || rowsPath) || multi) {  // scatter path, or several element types summing into the same rows
+    if (!rowsPath && (!patchPath || multi)) {  // scatter path, or several element types summing into the same rows
         if (wk) CUDA_TRY(cudaMemsetAsync(d_K, 0, nnz * sizeof(double), st));
         if (wr) {
             k_init_residual<<<grid_for(numDOF, 256), 256, 0, st>>>(d_R, d_loads, numDOF);
@@ -322,11 +328,16 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.numNodes = p->numNodes;
             A.nrowptr = p->d_nrowptr;
             A.ncols = p->d_ncols;
-            A.adjPtr = p->d_adjPtr;
-            A.corners = p->d_corners;
+            const size_t k = &b - &p->blocks[0];
+            A.cBegin = p->d_blockAdj + k * (size_t)p->numNodes;
+            A.cEnd = p->d_blockAdj + (k + 1) * (size_t)p->numNodes;
+            A.elemOffset = (int)b.elemOffset;
+            A.accumulate = k > 0;
+            A.finalise = k + 1 == p->blocks.size();
+            A.corners = b.d_corners;
             A.zero = 0;
             A.stats = p->d_pipeStats;
-            A.connE = p->d_connE;
+            A.connE = b.d_connE;
             A.coords = (const double2*)d_coords;
             A.states = (const double2*)d_states;
             A.thick = d_thick;
@@ -376,7 +387,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
         launches++;
     }
     if (ev) CUDA_TRY(cudaEventRecord(ev->second, st));
-    if (bcs && (!(patchPath || rowsPath) || multi)) {
+    if (bcs && !rowsPath && (!patchPath || multi)) {
         k_apply_bcs<<<grid_for(p->nBC * 32, 128), 128, 0, st>>>(p->nBC, p->d_bcDof, p->d_bcVal, p->d_bcCount, p->d_nrowptr,
                                                                p->d_ncols, d_states, wk ? d_K : nullptr,
                                                                wr ? d_R : nullptr);

@@ -32,7 +32,11 @@ struct Args {
     long long numNodes;
     const int* nrowptr;
     const int* ncols;
-    const int* adjPtr;
+    const int* cBegin;       // per node: first / one-past-last corner of this element block (global corner numbers)
+    const int* cEnd;
+    int elemOffset;          // first global element id of the block (thickness is indexed by global element id)
+    int accumulate;          // 1: K and R already hold the contributions of earlier element blocks
+    int finalise;            // 1: last block -- apply loads and boundary conditions
     const void* corners;     // corner records (plan.cu: k_corners): int2 for NN <= 4, int4 for NN <= 12
     const int4* connE;       // element-major connectivity, ceil(NN/4) words per element
     const double2* coords;
@@ -60,13 +64,17 @@ __host__ __device__ constexpr int resident_threads() {
     return NN <= 4 ? (NL ? 512 : 640) : (NN <= 6 ? 384 : 256);
 }
 
-template <int NN, int NQ, bool NL, bool WK, bool WR>
+// MB: the plan has several element blocks (one launch per block: later blocks add to what earlier ones left in K and R,
+// the last one applies loads and boundary conditions); single-block plans compile those switches away
+template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB>
 __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const __grid_constant__ femb::DMat D,
                                                         const Args A) {
     using namespace femb;
     static_assert(NN <= 12, "corner records hold at most 12 slot positions");
     constexpr int CW = (NN + 3) / 4;  // connectivity words per element
     extern __shared__ double2 acc[];  // [2*maxDeg][BLOCK], swizzled
+    const bool accumulate = MB && A.accumulate, finalise = !MB || A.finalise;
+    const int elemOffset = MB ? A.elemOffset : 0;
 #if ROWS_TRACE
     long long tStart = clock64(), gStart;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gStart));
@@ -78,12 +86,42 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     const int deg = valid ? __ldg(A.nrowptr + i + 1) - off : 0;
     auto slot = [&](int m) -> double2& { return acc[m * BLOCK + ((tid + m) & (BLOCK - 1))]; };
 
-    if (WK && !(KNOCK & 1))
-        for (int m = 0; m < 2 * deg; ++m) slot(m) = make_double2(0.0, 0.0);
+    // The rows of the warp's 32 consecutive nodes are one contiguous run of the CSR values (both DOF rows of a node
+    // are adjacent and rows are stored in node order): [2*off_first, 2*off_last + 2*deg_last) in double2 units.  A byte
+    // table maps a position of the run to the lane that owns it; the warp streams the run in 512-byte steps when it
+    // writes the rows out (and when it reads back what earlier element blocks left there).
+    // (base / start / total are recomputed at the write-out rather than carried across the corner loop)
+    double2* K2 = reinterpret_cast<double2*>(A.K);
+    const int wbase = tid - lane;
+    unsigned char* owner = reinterpret_cast<unsigned char*>(acc + 2 * A.maxDeg * BLOCK + BLOCK) + 2 * A.maxDeg * wbase;
     double2& racc = acc[2 * A.maxDeg * BLOCK + tid];  // residual pair of the node: kept in shared memory, not in registers
-    if (WR) racc = make_double2(0.0, 0.0);
+    if (WK && !(KNOCK & 8)) {
+        const int start = 2 * (off - __shfl_sync(0xffffffffu, off, 0));  // my first position in the run
+        for (int m = 0; m < 2 * deg; ++m) owner[start + m] = (unsigned char)lane;
+    }
+    if (accumulate) {
+        if (WK) {
+            const int base = __shfl_sync(0xffffffffu, off, 0);
+            const int start = 2 * (off - base);
+            const int total = __shfl_sync(0xffffffffu, start + 2 * deg, 31);  // invalid tail lanes hold off = end, deg = 0
+            __syncwarp();
+            for (int f0 = 0; f0 < total; f0 += 32) {
+                const int f = f0 + lane;
+                const bool ok = f < total;
+                const int r = ok ? owner[f] : 0;
+                const int mm = f - __shfl_sync(0xffffffffu, start, r);
+                if (ok) acc[mm * BLOCK + ((wbase + r + mm) & (BLOCK - 1))] = K2[2ll * base + f];
+            }
+            __syncwarp();
+        }
+        if (WR) racc = valid ? reinterpret_cast<const double2*>(A.R)[i] : make_double2(0.0, 0.0);
+    } else {
+        if (WK && !(KNOCK & 1))
+            for (int m = 0; m < 2 * deg; ++m) slot(m) = make_double2(0.0, 0.0);
+        if (WR) racc = make_double2(0.0, 0.0);
+    }
 
-    const int c0 = valid ? __ldg(A.adjPtr + i) : 0, c1 = valid ? __ldg(A.adjPtr + i + 1) : 0;
+    const int c0 = valid ? __ldg(A.cBegin + i) : 0, c1 = valid ? __ldg(A.cEnd + i) : 0;
     for (int c = c0; c < c1; ++c) {
         int e, a, node[4 * CW];
         unsigned kw[CW];  // slot positions: 7-bit fields from bit 4 (NN <= 4) or bytes
@@ -124,7 +162,7 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
                 ux[b] = uy[b] = 0.0;
             }
         }
-        const double theta = (KNOCK & 2) ? 1.0 + 1e-9 * e : __ldg(A.thick + e);
+        const double theta = (KNOCK & 2) ? 1.0 + 1e-9 * e : __ldg(A.thick + elemOffset + e);
 
         // node-row strip of K_e: blocks (a, b), b = 0..NN-1, and the residual pair of node a
         double Kr[NN][4];
@@ -258,7 +296,7 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     // ---- BC rows, loads, residual ---------------------------------------------------------------------------
     // A warp waits for its slowest lane, so the (rare) constrained nodes take everything from per-constrained-node
     // arrays built by femb_plan_set_bcs: one level of loads behind bcInfo.
-    const unsigned info = (valid && A.bcInfo) ? (unsigned)__ldg(A.bcInfo + i) : 0u;
+    const unsigned info = (valid && A.bcInfo && finalise) ? (unsigned)__ldg(A.bcInfo + i) : 0u;
     const unsigned m = info & 3u;
     if (m && WK) {  // constrained rows: zeros, occurrence count on the diagonal (AssemblyUtils.py:55-60)
         const double2 cnt = __ldg(A.bcNodeCnt + (info >> 9) - 1);
@@ -272,7 +310,7 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     }
     if (WR && valid) {
         double rx = racc.x, ry = racc.y;
-        if (A.loads) {  // R = scatter(R_e) - loads (Problem.py:653)
+        if (A.loads && finalise) {  // R = scatter(R_e) - loads (Problem.py:653)
             const double2 f = __ldg(A.loads + i);
             rx -= f.x;
             ry -= f.y;
@@ -285,21 +323,12 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
         reinterpret_cast<double2*>(A.R)[i] = make_double2(rx, ry);
     }
 
-    // ---- write-out --------------------------------------------------------------------------------------------
-    // The rows of the warp's 32 consecutive nodes are one contiguous run of the CSR values (both DOF rows of a node
-    // are adjacent and rows are stored in node order), so the warp streams [2*off_first, 2*off_last + 2*deg_last) in
-    // 512-byte steps.  A byte table maps a position of the run to the lane that owns it.
+    // ---- write-out: stream the warp's run of CSR values (owner table built at the top) ------------------------------
     if (WK && !(KNOCK & 8)) {
-        unsigned char* owner = reinterpret_cast<unsigned char*>(acc + 2 * A.maxDeg * BLOCK + BLOCK);
-        double2* K2 = reinterpret_cast<double2*>(A.K);
         const int base = __shfl_sync(0xffffffffu, off, 0);
-        const int start = 2 * (off - base);  // my first position in the run
-        unsigned char* mine = owner + 2 * A.maxDeg * (tid - lane) + start;
-        for (int m = 0; m < 2 * deg; ++m) mine[m] = (unsigned char)lane;
-        const int total = __shfl_sync(0xffffffffu, start + 2 * deg, 31);  // invalid tail lanes hold off = deg = 0
+        const int start = 2 * (off - base);
+        const int total = __shfl_sync(0xffffffffu, start + 2 * deg, 31);  // invalid tail lanes hold off = end, deg = 0
         __syncwarp();
-        const int wbase = tid - lane;
-        owner += 2 * A.maxDeg * wbase;  // one table per warp
         for (int f0 = 0; f0 < total; f0 += 32) {
             const int f = f0 + lane;
             const bool ok = f < total;

@@ -65,6 +65,8 @@ struct BlockData {
     std::vector<double> N, dN, w;
     int* d_conn = nullptr;  // node-major int32: conn[a * E + e]
     int* d_slot = nullptr;  // [(a*nn + b) * E + e] -> position of (node_a, node_b) in the node-level CSR
+    int4* d_connE = nullptr;   // element-major connectivity, ceil(nn/4) words per element (row-owner kernel)
+    void* d_corners = nullptr; // corner records of this block, indexed by the global corner number: int2 (nn <= 4) or int4
     PatchProgram prog;
 };
 
@@ -102,8 +104,8 @@ struct femb_plan {
     long long* d_pipeStats = nullptr;  // measurement only
     int debugFlags = 0;                // measurement only
     int usePatch = 2;            // assembly path: 2 row-owner kernel, 1 write-once patch pipeline, 0 slot-map scatter with FP64 atomics
-    int4* d_connE = nullptr;     // element-major connectivity, ceil(nn/4) words per element (single-block plans; row-owner kernel)
-    void* d_corners = nullptr;   // per (node, adjacent element) corner record, int2 (nn <= 4) or int4 (plan.cu: k_corners)
+    int* d_blockAdj = nullptr;   // (numBlocks+1) x numNodes: start of each block's corners in a node's adjacency list (row-owner kernel)
+    bool rowsBuilt = false;      // corner records / element-major connectivity exist for every block
     int maxDeg = 0;              // largest node degree
     // boundary conditions, de-duplicated on the host with the reference's semantics
     std::vector<int64_t> bcRawDof;  // the lists as last given (identical lists are not processed again)

@@ -157,15 +157,16 @@ __global__ void k_conn_elem_major(const int* __restrict__ conn, long long E, int
 // node's local index a in the element and the position k_b of each element node in the node's sorted neighbour list.
 //   nn <= 4: int2 {e, a | k_0 << 4 | k_1 << 11 | k_2 << 18 | k_3 << 25}            (7-bit positions)
 //   nn <= 12: int4 {e | a << 28, k_0..k_3, k_4..k_7, k_8..k_11}                      (one byte per position)
+// (the records of a block are indexed by the global corner number; e is the element id within the block)
 __global__ void k_corners(long long N, const int* __restrict__ nrowptr, const int* __restrict__ ncols,
-                          const int* __restrict__ adjPtr, const int* __restrict__ adj, const int4* __restrict__ connE, int nn,
-                          void* __restrict__ corners) {
+                          const int* __restrict__ cBegin, const int* __restrict__ cEnd, const int* __restrict__ adj,
+                          const int4* __restrict__ connE, int nn, int elemOffset, void* __restrict__ corners) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int off = nrowptr[i], deg = nrowptr[i + 1] - off;
     const int cw = (nn + 3) / 4;
-    for (int c = adjPtr[i]; c < adjPtr[i + 1]; ++c) {
-        const int e = adj[c];
+    for (int c = cBegin[i]; c < cEnd[i]; ++c) {
+        const int e = adj[c] - elemOffset;
         unsigned a = 0, packed = 0, kb[3] = {0u, 0u, 0u};
         for (int b = 0; b < nn; ++b) {
             const int4 cn = connE[(long long)e * cw + (b >> 2)];
@@ -182,6 +183,19 @@ __global__ void k_corners(long long N, const int* __restrict__ nrowptr, const in
         if (nn <= 4) reinterpret_cast<int2*>(corners)[c] = make_int2(e, (int)(packed | a));
         else reinterpret_cast<int4*>(corners)[c] = make_int4((int)((unsigned)e | (a << 28)), (int)kb[0], (int)kb[1], (int)kb[2]);
     }
+}
+
+// first corner of node i whose (global) element id is >= firstElem: start of a block's corners in the node's sorted list
+__global__ void k_block_adj(long long N, const int* __restrict__ adjPtr, const int* __restrict__ adj, long long firstElem,
+                            int* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int lo = adjPtr[i], hi = adjPtr[i + 1];
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (adj[mid] < firstElem) lo = mid + 1; else hi = mid;
+    }
+    out[i] = lo;
 }
 
 __global__ void k_max_int(const int* __restrict__ v, long long n, int* __restrict__ out) {
@@ -363,14 +377,31 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
         k_max_int<<<grid_for(N, 256), 256, 0, st>>>(d_deg, N, p->d_flag);
         CUDA_TRY(cudaMemcpyAsync(&p->maxDeg, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         launches++;
-        if (p->blocks.size() == 1 && p->blocks[0].nn <= 12 && p->blocks[0].numElems < (1ll << 28)) {
-            auto& b = p->blocks[0];
-            const int cw = (b.nn + 3) / 4;
-            CUDA_TRY(cudaMalloc(&p->d_connE, b.numElems * cw * sizeof(int4)));
-            k_conn_elem_major<<<grid_for(b.numElems, 256), 256, 0, st>>>(b.d_conn, b.numElems, b.nn, p->d_connE);
-            CUDA_TRY(cudaMalloc(&p->d_corners, std::max<int64_t>(totalAdj, 1) * (b.nn <= 4 ? sizeof(int2) : sizeof(int4))));
-            k_corners<<<grid_for(N, 128), 128, 0, st>>>(N, p->d_nrowptr, p->d_ncols, d_adjPtr, d_adj, p->d_connE, b.nn, p->d_corners);
-            launches += 2;
+        bool rowsOk = true;
+        for (auto& b : p->blocks) rowsOk = rowsOk && b.nn <= 12 && b.numElems < (1ll << 28);
+        if (rowsOk) {
+            // row-owner kernel: per block element-major connectivity, corner records (indexed by the global corner
+            // number) and, per node, where the block's corners start in the node's adjacency list (the list is sorted
+            // by global element id and a block is a contiguous id range)
+            const size_t nb = p->blocks.size();
+            CUDA_TRY(cudaMalloc(&p->d_blockAdj, (nb + 1) * (size_t)N * sizeof(int)));
+            for (size_t k = 0; k <= nb; ++k) {
+                const long long firstElem = k < nb ? p->blocks[k].elemOffset : (long long)p->numElems;
+                k_block_adj<<<grid_for(N, 256), 256, 0, st>>>(N, d_adjPtr, d_adj, firstElem, p->d_blockAdj + k * (size_t)N);
+                launches++;
+            }
+            for (auto& b : p->blocks) {
+                const int cw = (b.nn + 3) / 4;
+                CUDA_TRY(cudaMalloc(&b.d_connE, b.numElems * cw * sizeof(int4)));
+                k_conn_elem_major<<<grid_for(b.numElems, 256), 256, 0, st>>>(b.d_conn, b.numElems, b.nn, b.d_connE);
+                CUDA_TRY(cudaMalloc(&b.d_corners, std::max<int64_t>(totalAdj, 1) * (b.nn <= 4 ? sizeof(int2) : sizeof(int4))));
+                const size_t k = &b - &p->blocks[0];
+                k_corners<<<grid_for(N, 128), 128, 0, st>>>(N, p->d_nrowptr, p->d_ncols, p->d_blockAdj + k * (size_t)N,
+                                                           p->d_blockAdj + (k + 1) * (size_t)N, d_adj, b.d_connE, b.nn,
+                                                           (int)b.elemOffset, b.d_corners);
+                launches += 2;
+            }
+            p->rowsBuilt = true;
         }
     }
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -407,8 +438,12 @@ extern "C" void femb_plan_destroy(femb_plan* p) {
     dfree(p->d_ncols);
     dfree(p->d_adjPtr);
     dfree(p->d_adj);
-    dfree(p->d_connE);
-    dfree(p->d_corners);
+    dfree(p->d_blockAdj);
+    for (auto& b : p->blocks) {
+        dfree(b.d_connE);
+        if (b.d_corners) cudaFree(b.d_corners);
+        b.d_corners = nullptr;
+    }
     dfree(p->d_hintCoords);
     dfree(p->d_bcMask);
     dfree(p->d_bcInfo);

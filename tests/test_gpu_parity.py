@@ -393,6 +393,40 @@ def test_row_owner_kernel_matches_oracle(elType, n, renumber):
     plan.close()
 
 
+@pytest.mark.parametrize("order", [("quad", "triangle"), ("triangle", "quad")])
+def test_mixed_mesh_row_owner_matches_oracle(order):
+    """several element blocks: one row-owner launch per block (later blocks add to the rows the earlier ones wrote,
+    the last one applies loads and BCs) -- still no atomics, 2 launches for 2 blocks"""
+    coords, cq = meshes.quad4_grid(31, 23)
+    coords = coords + 4e-3 * np.random.default_rng(2).random(coords.shape)
+    col = np.tile(np.arange(31), 23)
+    rest = cq["quad"][col >= 14]
+    conn = {"quad": cq["quad"][col < 14], "triangle": np.vstack((rest[:, [0, 1, 2]], rest[:, [0, 2, 3]]))}
+    conn = {k: conn[k] for k in order}
+    N = coords.shape[0]
+    numEl = sum(c.shape[0] for c in conn.values())
+    rng = np.random.default_rng(11)
+    states = 1e-3 * rng.random((N, 2))
+    thick = rng.random(numEl) * 1e-2 + 1e-3
+    loads = rng.random(2 * N)
+    left = np.arange(0, N, 32)  # first node of every grid row
+    bcDOF = np.concatenate((2 * left, 2 * left + 1, 2 * left[:2]))
+    bcVal = rng.random(bcDOF.size) * 1e-4
+    plan = AssemblyPlan(N)
+    plan.setLocalityHint(coords)
+    for elType, c in conn.items():
+        plan.addBlock(*ELEMENT_FOR[elType]().tables(), c)
+    plan.finalize()
+    assert plan.info("rows_path") == 1
+    case = (coords, conn, states, thick, loads, bcDOF, bcVal)
+    K1, R1 = _check_against_oracle(plan, None, case, launchesExpected=2)
+    plan.setOption("assembly_path", 0)  # scatter kernels: memset-free init + one launch per block + BC kernel
+    K0, R0 = plan.assemble(coords, states, thick, make_cm(0).material(), bcDOF, bcVal, True, loads)
+    assert plan.lastLaunches == 4
+    assert relerr(K1, K0) < 1e-13 and relerr(R1, R0) < 1e-13
+    plan.close()
+
+
 @pytest.mark.parametrize("path", ["rows", "patch"])
 def test_write_once_path_is_deterministic(path):
     """write-once assembly has a fixed summation order: two runs are bit-identical"""
