@@ -243,7 +243,6 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    plan.profile(True)
     torch.cuda.synchronize()
     sampler.start()
     for i in range(args.steps):
@@ -254,6 +253,13 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     times = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    # second pass with the in-library events around the assembly kernel (roofline leg): kept out of the timed steps
+    # above, where the two extra event records would sit inside the measured interval
+    plan.profile(True)
+    for i in range(min(args.steps, 50)):
+        flush_l2()
+        step()
+    torch.cuda.synchronize()
     kernel_ms_sum, kernel_calls = plan.profileRead()
     plan.profile(False)
     ms_per_step = float(times.mean())
@@ -373,7 +379,6 @@ def run_ours_multi(args, rank, world, local_rank, dev):
     sampler = ClockSampler(local_rank)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    asm.plan.profile(True)
     torch.cuda.synchronize()
     dist.barrier()
     sampler.start()
@@ -385,6 +390,11 @@ def run_ours_multi(args, rank, world, local_rank, dev):
     torch.cuda.synchronize()
     dist.barrier()
     clocks = sampler.stop()
+    asm.plan.profile(True)  # roofline leg: in-library events, outside the timed steps
+    for i in range(min(args.steps, 50)):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
     kernel_ms_sum, kernel_calls = asm.plan.profileRead()
     asm.plan.profile(False)
     total_ms = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, ends))], dtype=torch.float64, device=dev)
