@@ -427,6 +427,21 @@ def test_mixed_mesh_row_owner_matches_oracle(order):
     plan.close()
 
 
+def test_high_degree_node_falls_back_to_scatter_kernels():
+    """a node shared by 60 triangles has 61 neighbours: more than the row-owner kernel's shared-memory rows hold"""
+    m = 60
+    ang = 2 * np.pi * np.arange(m) / m
+    coords = np.vstack(([[0.0, 0.0]], np.stack((np.cos(ang), np.sin(ang)), axis=1) * (1.0 + 0.1 * np.cos(3 * ang))[:, None]))
+    conn = {"triangle": np.stack((np.zeros(m, dtype=np.int64), 1 + np.arange(m), 1 + (np.arange(m) + 1) % m), axis=1)}
+    N = coords.shape[0]
+    rng = np.random.default_rng(4)
+    case = (coords, conn, 1e-3 * rng.random((N, 2)), rng.random(m) + 0.5, rng.random(2 * N), np.array([2, 3, 5]), np.array([1e-4, 0.0, 2e-4]))
+    plan = _raw_plan("triangle", coords, conn)
+    assert plan.info("max_degree") == 61 and plan.info("rows_path") == 0
+    _check_against_oracle(plan, "triangle", case, launchesExpected=3)
+    plan.close()
+
+
 @pytest.mark.parametrize("path", ["rows", "patch"])
 def test_write_once_path_is_deterministic(path):
     """write-once assembly has a fixed summation order: two runs are bit-identical"""
