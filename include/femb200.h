@@ -74,18 +74,27 @@ int femb_plan_create(int64_t numNodes, int32_t numDim, int32_t numStates, int32_
 int femb_plan_add_block(femb_plan* plan, int32_t nodesPerElem, int32_t numQuad, const double* N, const double* dNdxi,
                         const double* w, int64_t numElems, const int64_t* conn);
 
-/* builds the node->element adjacency, the sorted structural CSR pattern and the element scatter map */
+/* builds the node->element adjacency, the sorted structural CSR pattern, the corner records of the row-owner
+ * kernel, the element scatter map of the fallback kernels and (assembly_path 1 only) the node-patch programs */
 int femb_plan_finalize(femb_plan* plan);
 void femb_plan_destroy(femb_plan* plan);
 
 /* optional, before finalize: node coordinates (numNodes, numDim) used ONLY to order nodes for locality when
- * the node patches of the write-once assembly are cut (Morton order); results do not depend on it */
+ * the node patches of the opt-in patch pipeline are cut (Morton order); results do not depend on it */
 int femb_plan_set_locality_hint(femb_plan* plan, const double* coords);
 
-/* tuning knobs: "patch_nodes" (owned nodes per patch, before finalize; 0 = default),
- * "use_patches" (0: scatter kernels with FP64 atomics, 1: write-once patch kernels where available) */
+/* options:
+ *   "assembly_path" (alias "use_patches"): 2 (default) row-owner kernel -- one thread per node row, one launch per
+ *       element block, no atomics, bit-reproducible; 3/4/6/9/10-node elements, node degree <= 48, else the scatter
+ *       kernels run; 1: patch pipeline (3/4-node elements, must be chosen before finalize); 0: slot-map scatter
+ *       kernels with FP64 atomics (every family);
+ *   "patch_nodes" (owned nodes per patch, before finalize; 0 = default), "team_warps" (1 or 2, before finalize):
+ *       patch pipeline only;
+ *   "debug_flags": measurement builds only */
 int femb_plan_set_option(femb_plan* plan, const char* name, int64_t value);
-/* "num_patches", "patch_nodes", "patch_elems_total", "patch_elems_max", "patch_sources_total", "patch_path" */
+/* "assembly_path", "rows_path" (1: the row-owner kernel will run), "max_degree", "patch_path", "num_patches",
+ * "patch_nodes", "team_warps", "patch_elems_total", "patch_elems_max", "patch_blob_bytes", "patch_colours_max";
+ * -1 for an unknown name */
 int64_t femb_plan_get_info(const femb_plan* plan, const char* name);
 
 /* external != 0: run the plan's kernels on the caller's CUDA stream (e.g.
