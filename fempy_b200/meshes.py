@@ -52,6 +52,17 @@ def tri3_grid(nx, ny, warped=True):
     return coords, {"triangle": np.vstack((lower, upper)).astype(np.int64)}
 
 
+def tri6_grid(nx, ny, warped=True):
+    """6-node triangles on the quad9 node grid: every cell split on its LL-UR diagonal, meshio triangle6 node
+    order (3 corners, then the mid-points of edges 0-1, 1-2, 2-0); lower triangles first, then upper."""
+    W = 2 * nx + 1
+    coords = _grid_nodes(W, 2 * ny + 1, warped)
+    ll = np.tile(2 * np.arange(nx), ny) + np.repeat(2 * W * np.arange(ny), nx)
+    lower = np.stack((ll, ll + 2, ll + 2 * W + 2, ll + 1, ll + W + 2, ll + W + 1), axis=1)
+    upper = np.stack((ll, ll + 2 * W + 2, ll + 2 * W, ll + W + 1, ll + 2 * W + 1, ll + W), axis=1)
+    return coords, {"triangle6": np.vstack((lower, upper)).astype(np.int64)}
+
+
 def edge_nodes(coords, x=None, y=None):
     """Indices of nodes lying exactly on x == value or y == value (as the reference scripts select
     boundary nodes, e.g. PlotQuadMeshScaling.py:65-66)."""
@@ -60,4 +71,4 @@ def edge_nodes(coords, x=None, y=None):
     return np.argwhere(coords[:, 1] == y).flatten()
 
 
-GENERATORS = {"quad": quad4_grid, "quad9": quad9_grid, "triangle": tri3_grid}
+GENERATORS = {"quad": quad4_grid, "quad9": quad9_grid, "triangle": tri3_grid, "triangle6": tri6_grid}

@@ -370,7 +370,7 @@ def _renumbered(case, seed=3):
     return coords[inv], conn2, states[inv], thick, loads2, bc2, bcVal
 
 
-@pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29)])
+@pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29), ("quad9", 11), ("triangle6", 12)])
 @pytest.mark.parametrize("renumber", [False, True])
 def test_row_owner_kernel_matches_oracle(elType, n, renumber):
     """default path: one thread per node row, every K value and R entry written exactly once = 1 launch"""
