@@ -152,13 +152,14 @@ static int launch_pipe(const femb_plan* p, const BlockData& b, const DMat& D, pi
     A.offRacc = S.offRacc;
     A.teamStride = S.teamStride;
     A.offTeams = S.offTeams;
-    static int configured = 0;
-    if (S.total > configured) {
+    static int configured[64] = {};  // per device ordinal
+    int& conf = configured[p->device & 63];
+    if (S.total > conf) {
         CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
-        configured = S.total;
+        conf = S.total;
     }
-    static int numSMs = 0;
-    if (!numSMs) CUDA_TRY(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, p->device));
+    int numSMs = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, p->device));
     const int64_t wanted = (p->numPatches + numTeams - 1) / numTeams;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(wanted, numSMs));
     if (A.stats && !NL && WK && WR) {  // measurement build of the headline variant only
@@ -225,10 +226,12 @@ static int launch_rows_mb(const femb_plan* p, const BlockData& b, const DMat& D,
     const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
     // accumulator rows + residual pairs + write-out owner table
     const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * (sizeof(double2) + 1) + rows::BLOCK * sizeof(double2);
-    static size_t configured = 0;
-    if (smem > configured) {
+    // per device (a process may hold plans on several GPUs): the opt-in above 48 KB is remembered per device ordinal
+    static size_t configured[64] = {};
+    size_t& conf = configured[p->device & 63];
+    if (smem > conf) {
         CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        conf = smem;
     }
     rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB><<<grid_for(p->numNodes, rows::BLOCK), rows::BLOCK, smem, st>>>(tb, D, A);
     return 0;

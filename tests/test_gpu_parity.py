@@ -427,6 +427,16 @@ def test_mixed_mesh_row_owner_matches_oracle(order):
     plan.close()
 
 
+@pytest.mark.parametrize("scale", [1e-6, 1e6])
+def test_coordinate_scale_invariance(scale):
+    """the division-free gradients (hardware reciprocal seed + Newton steps) keep 1e-12 far away from unit-sized cells"""
+    coords, conn, states, thick, loads, bcDOF, bcVal = _path_case("quad", 21)
+    case = (coords * scale, conn, states * scale, thick, loads, bcDOF, bcVal * scale)
+    plan = _raw_plan("quad", case[0], conn)
+    _check_against_oracle(plan, "quad", case, launchesExpected=1)
+    plan.close()
+
+
 def test_high_degree_node_falls_back_to_scatter_kernels():
     """a node shared by 60 triangles has 61 neighbours: more than the row-owner kernel's shared-memory rows hold"""
     m = 60
