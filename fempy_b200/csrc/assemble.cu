@@ -307,6 +307,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
     const bool patchPath = !rowsPath && patch_path_available(p, wk, wr);
     const bool multi = p->blocks.size() > 1;
     const bool bcs = applyBCs && p->nBC > 0;
+    if (!rowsPath && !patchPath) TRY(ensure_slot_maps(p));
     if (!rowsPath && (!patchPath || multi)) {  // scatter path, or several element types summing into the same rows
         if (wk) CUDA_TRY(cudaMemsetAsync(d_K, 0, nnz * sizeof(double), st));
         if (wr) {

@@ -160,6 +160,7 @@ static inline int need_final(const femb_plan* p, const char* who) {
 int exclusive_scan(const int* d_in, int* d_out, int64_t n, cudaStream_t st, int64_t& launches);
 
 bool rows_path_available(const femb_plan* p);
+int ensure_slot_maps(femb_plan* p);  // plan.cu: builds the scatter kernels' slot maps on first use
 // true when the write-once patch pipeline will run for this plan (assemble.cu)
 bool patch_path_available(const femb_plan* p, bool wk, bool wr);
 

@@ -366,12 +366,6 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
     CUDA_TRY(cudaMalloc(&p->d_ncols, std::max<int64_t>(nnzNode, 1) * sizeof(int)));
     k_compact_rows<<<grid_for(N, 128), 128, 0, st>>>(N, d_candPtr, d_cand, p->d_nrowptr, p->d_ncols);
     launches++;
-    for (auto& b : p->blocks) {
-        const int64_t cnt = b.numElems * (int64_t)b.nn * b.nn;
-        CUDA_TRY(cudaMalloc(&b.d_slot, cnt * sizeof(int)));
-        k_build_slots<<<grid_for(cnt, 256), 256, 0, st>>>(b.d_conn, b.numElems, b.nn, p->d_nrowptr, p->d_ncols, b.d_slot);
-        launches++;
-    }
     {  // largest node degree + element-major connectivity for the row-owner kernel
         CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
         k_max_int<<<grid_for(N, 256), 256, 0, st>>>(d_deg, N, p->d_flag);
@@ -587,6 +581,19 @@ extern "C" int femb_plan_pattern(femb_plan* p, int64_t* indptr, int64_t* indices
     cudaFree(d_ip);
     cudaFree(d_ix);
     return rc;
+}
+
+// The element -> CSR slot map of the scatter kernels (4*nn^2 bytes per element) is only built when those kernels are
+// going to run: the row-owner and patch paths never read it.
+int ensure_slot_maps(femb_plan* p) {
+    for (auto& b : p->blocks) {
+        if (b.d_slot) continue;
+        const int64_t cnt = b.numElems * (int64_t)b.nn * b.nn;
+        CUDA_TRY(cudaMalloc(&b.d_slot, cnt * sizeof(int)));
+        k_build_slots<<<grid_for(cnt, 256), 256, 0, p->stream>>>(b.d_conn, b.numElems, b.nn, p->d_nrowptr, p->d_ncols, b.d_slot);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 // =============================================================================================
