@@ -223,7 +223,8 @@ def test_medium_meshes_against_oracle(elType, n, model):
 
 
 # ---- full-size configurations through size-independent properties --------------------------------------------------
-FULL = [("quad", 512, "config 2: 526k DOF"), ("quad9", 250, "config 3 family: 502k DOF"), ("triangle", 700, "config 4 family: 983k DOF")]
+FULL = [("quad", 512, "config 2: 526k DOF"), ("quad9", 250, "config 3 family: 502k DOF"), ("triangle", 700, "config 4 family: 983k DOF"),
+        ("quad9", 500, "config 3: 2.0M DOF, nnz 64M"), ("triangle", 1580, "config 4: 5.0M DOF, nnz 70M")]
 
 
 @pytest.mark.parametrize("elType,n,label", FULL)
