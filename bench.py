@@ -103,74 +103,82 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_port_run(wl, rows):
-    """The CPU port (oracle/fem_oracle.py) on the first `rows` element rows of the workload mesh:
-    K (COO -> CSR) + R with BCs and loads, the reference's stages (FEMpy/Problem.py:565-661)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle import fem_oracle as fo
-    from util import oracle_blocks
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
-    elType, n = wl["elType"], wl["n"]
-    perRow = wl["numElems"] // n
-    numEl = perRow * rows if elType != "triangle" else None
-    conn = wl["conn"][elType]
-    if elType == "triangle":
-        half = conn.shape[0] // 2
-        sub = np.vstack((conn[: (half // n) * rows], conn[half : half + (half // n) * rows]))
-    else:
-        sub = conn[:numEl]
-    numNodes = int(sub.max()) + 1
-    coords, states = wl["coords"][:numNodes], wl["states"][:numNodes]
-    thick = np.full(sub.shape[0], MAT["t"])
-    keep = wl["bcDOF"] < 2 * numNodes
-    bcDOF, bcVal, loads = wl["bcDOF"][keep], wl["bcVal"][keep], wl["loads"][: 2 * numNodes]
-    blocks = oracle_blocks({elType: sub})
-    t0 = time.perf_counter()
-    K = fo.assemble_matrix(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], bcDOF)
-    R = fo.assemble_residual(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], loads, bcDOF, bcVal)
-    dt = time.perf_counter() - t0
-    assert K.nnz > 0 and R.size == 2 * numNodes
-    return sub.shape[0], dt
+
+class CpuPort:
+    """The CPU port (oracle/fem_oracle.py: the reference's stages, FEMpy/Problem.py:565-661) on all host cores:
+    one worker process per core (oracle/cpu_port.py), each assembling K (COO -> CSR) + R with BCs and loads of its
+    own strip of `rows` element rows of the workload mesh."""
+
+    def __init__(self, wl, procs=None):
+        from oracle import cpu_port
+
+        self.cp, self.wl = cpu_port, wl
+        self.procs = min(procs or host_cores(), 64)
+        self.pool = cpu_port.StripPool(self.procs)
+
+    def run(self, rows):
+        """One round: `procs` strips of `rows` rows each (wrapping around the mesh); returns (elements, seconds)."""
+        n = self.wl["n"]
+        rows = max(1, min(rows, n))
+        starts = [(k * rows) % max(1, n - rows + 1) for k in range(self.procs)]
+        strips = [self.cp.strip_inputs(self.wl, st, rows, MAT) for st in starts]
+        return self.pool.run(strips)
+
+    def close(self):
+        self.pool.close()
 
 
 def cpu_baseline(wl, budget_s=12.0):
+    port = CpuPort(wl)
     rows = max(1, wl["n"] // 16)
-    numEl, dt = cpu_port_run(wl, rows)  # calibration + warm numpy caches
-    rows = int(min(wl["n"], max(rows, rows * budget_s / max(dt, 1e-3))))
-    numEl, dt = cpu_port_run(wl, rows)
-    return {"value": numEl / dt, "unit": "elements/s", "cores": 1, "kind": "port",
-            "sample": f"oracle/fem_oracle.py (numpy port of the reference's stages) on the first {rows} of {wl['n']} element rows "
-                      f"of the workload ({numEl} elements, {dt:.2f} s)"}
+    port.run(max(1, rows // 4))  # start the workers, warm numpy
+    numEl, dt = port.run(rows)  # calibration
+    rows = int(min(wl["n"], max(1, rows * budget_s / max(dt, 1e-3))))
+    numEl, dt = port.run(rows)
+    port.close()
+    return {"value": numEl / dt, "unit": "elements/s", "cores": port.procs, "kind": "port",
+            "sample": f"oracle/fem_oracle.py (numpy port of the reference's stages), {port.procs} worker processes each assembling "
+                      f"its own strip of {rows} of the workload's {wl['n']} element rows ({numEl} elements in {dt:.2f} s wall)"}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU port of the reference's algorithm on the host cores (rank 0 only)."""
+    """--impl reference: the CPU port of the reference's algorithm on all host cores (rank 0 only)."""
     if rank != 0:
         return
     # same workload as the GPU arm at this N: config 2 at N = 1, its per-GPU share times N (a 512 x 512N strip) for N > 1,
     # or the fixed config-5 mesh with --config c5.  The metric is a rate and every step assembles a bounded sample
-    # (about 32k elements = the first rows of the mesh), so the N > 1 strip is sampled on its first 512-wide rows.
+    # (about 32k elements per worker process = strips of the mesh's first 512-wide rows).
     strong = args.gpus > 1 and args.config == "c5"
     wl = make_workload("c5" if strong else (args.config if args.gpus == 1 else "c2"), args.nx)
     if args.gpus > 1 and not strong:
         wl["desc"] = (f"config2 per GPU: structured Q4 {wl['n']}x{wl['n'] * args.gpus} = {args.gpus} x ({wl['n']}x{wl['n']}), "
                       "iso plane stress, element-partitioned (weak scaling)")
+    port = CpuPort(wl, args.cpu_procs)
     rows = max(1, 32768 // wl["n"])
-    for _ in range(args.warmup):
-        cpu_port_run(wl, max(1, rows // 4))
+    port.run(max(1, rows // 4))
+    for _ in range(max(0, args.warmup - 1)):
+        port.run(max(1, rows // 4))
     total_el, total_t = 0, 0.0
     for _ in range(args.steps):
-        numEl, dt = cpu_port_run(wl, rows)
+        numEl, dt = port.run(rows)
         total_el += numEl
         total_t += dt
+    port.close()
     value = total_el / total_t
+    sample = (f"{port.procs} worker processes, each assembling its own strip of {rows} of {wl['n']} element rows per step "
+              f"({total_el // args.steps} elements per step), numpy port of the reference's stages")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "sample_rows": rows},
-        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": 1, "kind": "port",
-                         "sample": f"first {rows} of {wl['n']} element rows per step, numpy port of the reference's stages"},
+        "config": {"workload": wl["desc"], "sample_rows_per_worker": rows, "workers": port.procs},
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": port.procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
@@ -471,6 +479,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--nx", type=int, default=None, help="override the mesh size (exploration only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--cpu-procs", type=int, default=None, help="worker processes of the CPU legs (default: all host cores)")
     ap.add_argument("--flush-write-only", action="store_true", help="L2 flush by the 512 MB write alone (leaves dirty lines for the timed kernel to evict)")
     ap.add_argument("--patch-nodes", type=int, default=0, help="owned nodes per patch (0 = library default)")
     ap.add_argument("--dist-mode", default="halo", choices=["halo", "exchange"], help="multi-GPU: redundant boundary elements (no exchange) or unique elements + NCCL interface exchange")

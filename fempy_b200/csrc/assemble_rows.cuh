@@ -85,6 +85,9 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     const int off = __ldg(A.nrowptr + (valid ? i : A.numNodes));  // tail lanes: end of the values, degree 0
     const int deg = valid ? __ldg(A.nrowptr + i + 1) - off : 0;
     auto slot = [&](int m) -> double2& { return acc[m * BLOCK + ((tid + m) & (BLOCK - 1))]; };
+    // loads the kernel waits on later are issued here: the corner range (start of the corner loop) and the BC word (epilogue)
+    const int c0 = valid ? __ldg(A.cBegin + i) : 0, c1 = valid ? __ldg(A.cEnd + i) : 0;
+    const unsigned info = (valid && A.bcInfo && finalise) ? (unsigned)__ldg(A.bcInfo + i) : 0u;
 
     // The rows of the warp's 32 consecutive nodes are one contiguous run of the CSR values (both DOF rows of a node
     // are adjacent and rows are stored in node order): [2*off_first, 2*off_last + 2*deg_last) in double2 units.  A byte
@@ -95,11 +98,19 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     const int wbase = tid - lane;
     unsigned char* owner = reinterpret_cast<unsigned char*>(acc + 2 * A.maxDeg * BLOCK + BLOCK) + 2 * A.maxDeg * wbase;
     double2& racc = acc[2 * A.maxDeg * BLOCK + tid];  // residual pair of the node: kept in shared memory, not in registers
-    if (WK && !(KNOCK & 8)) {
-        const int start = 2 * (off - __shfl_sync(0xffffffffu, off, 0));  // my first position in the run
-        for (int m = 0; m < 2 * deg; ++m) owner[start + m] = (unsigned char)lane;
-    }
+    const int ownStart = (WK && !(KNOCK & 8)) ? 2 * (off - __shfl_sync(0xffffffffu, off, 0)) : 0;  // my first position in the run
+    // owner table + zeroed accumulators: thread-private stores, so they run under the first corner's loads
+    auto fill = [&]() {
+        if (WK && !(KNOCK & 8))
+            for (int m = 0; m < 2 * deg; ++m) owner[ownStart + m] = (unsigned char)lane;
+        if (WK && !(KNOCK & 1))
+            for (int m = 0; m < 2 * deg; ++m) slot(m) = make_double2(0.0, 0.0);
+        if (WR) racc = make_double2(0.0, 0.0);
+    };
+    bool fillPending = !accumulate;
     if (accumulate) {
+        if (WK && !(KNOCK & 8))
+            for (int m = 0; m < 2 * deg; ++m) owner[ownStart + m] = (unsigned char)lane;
         if (WK) {
             const int base = __shfl_sync(0xffffffffu, off, 0);
             const int start = 2 * (off - base);
@@ -115,13 +126,8 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
             __syncwarp();
         }
         if (WR) racc = valid ? reinterpret_cast<const double2*>(A.R)[i] : make_double2(0.0, 0.0);
-    } else {
-        if (WK && !(KNOCK & 1))
-            for (int m = 0; m < 2 * deg; ++m) slot(m) = make_double2(0.0, 0.0);
-        if (WR) racc = make_double2(0.0, 0.0);
     }
 
-    const int c0 = valid ? __ldg(A.cBegin + i) : 0, c1 = valid ? __ldg(A.cEnd + i) : 0;
     for (int c = c0; c < c1; ++c) {
         int e, a, node[4 * CW];
         unsigned kw[CW];  // slot positions: 7-bit fields from bit 4 (NN <= 4) or bytes
@@ -163,6 +169,10 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
             }
         }
         const double theta = (KNOCK & 2) ? 1.0 + 1e-9 * e : __ldg(A.thick + elemOffset + e);
+        if (fillPending) {
+            fill();
+            fillPending = false;
+        }
 
         // node-row strip of K_e: blocks (a, b), b = 0..NN-1, and the residual pair of node a
         double Kr[NN][4];
@@ -293,10 +303,11 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
         }
     }
 
+    if (fillPending) fill();  // nodes without a corner in this element block
+
     // ---- BC rows, loads, residual ---------------------------------------------------------------------------
     // A warp waits for its slowest lane, so the (rare) constrained nodes take everything from per-constrained-node
     // arrays built by femb_plan_set_bcs: one level of loads behind bcInfo.
-    const unsigned info = (valid && A.bcInfo && finalise) ? (unsigned)__ldg(A.bcInfo + i) : 0u;
     const unsigned m = info & 3u;
     if (m && WK) {  // constrained rows: zeros, occurrence count on the diagonal (AssemblyUtils.py:55-60)
         const double2 cnt = __ldg(A.bcNodeCnt + (info >> 9) - 1);
@@ -308,19 +319,14 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
             }
         }
     }
+    // residual epilogue split around the write-out: its loads are issued here and consumed after the K stores
+    double2 fLoad = make_double2(0.0, 0.0), uBC = make_double2(0.0, 0.0), valBC = make_double2(0.0, 0.0);
     if (WR && valid) {
-        double rx = racc.x, ry = racc.y;
-        if (A.loads && finalise) {  // R = scatter(R_e) - loads (Problem.py:653)
-            const double2 f = __ldg(A.loads + i);
-            rx -= f.x;
-            ry -= f.y;
+        if (A.loads && finalise) fLoad = __ldg(A.loads + i);
+        if (m) {
+            uBC = __ldg(A.states + i);
+            valBC = __ldg(A.bcNodeVal + (info >> 9) - 1);
         }
-        if (m) {  // R[bc] = u - c (AssemblyUtils.py:93)
-            const double2 u = __ldg(A.states + i), val = __ldg(A.bcNodeVal + (info >> 9) - 1);
-            if (m & 1u) rx = u.x - val.x;
-            if (m & 2u) ry = u.y - val.y;
-        }
-        reinterpret_cast<double2*>(A.R)[i] = make_double2(rx, ry);
     }
 
     // ---- write-out: stream the warp's run of CSR values (owner table built at the top) ------------------------------
@@ -336,6 +342,12 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
             const int mm = f - __shfl_sync(0xffffffffu, start, r);
             if (ok) st_stream(K2 + 2ll * base + f, acc[mm * BLOCK + ((wbase + r + mm) & (BLOCK - 1))]);
         }
+    }
+    if (WR && valid) {
+        double rx = racc.x - fLoad.x, ry = racc.y - fLoad.y;  // R = scatter(R_e) - loads (Problem.py:653)
+        if (m & 1u) rx = uBC.x - valBC.x;                      // R[bc] = u - c (AssemblyUtils.py:93)
+        if (m & 2u) ry = uBC.y - valBC.y;
+        reinterpret_cast<double2*>(A.R)[i] = make_double2(rx, ry);
     }
 #if ROWS_TRACE
     if (A.stats && lane == 0) {  // [0] sum of warp lifetimes (cycles) [1] warps [2] longest [3] first start (ns) [4] last end (ns) [5] shortest
