@@ -128,6 +128,19 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
         if (WR) racc = valid ? reinterpret_cast<const double2*>(A.R)[i] : make_double2(0.0, 0.0);
     }
 
+#ifndef ROWS_VAR
+#define ROWS_VAR 1  // bit 1: wide families load the next corner's record and connectivity one iteration ahead
+#endif
+    // Wide families (6-10 nodes) run at 8-12 warps per SM with registers to spare: the next corner's record and
+    // connectivity words are fetched one iteration ahead, which takes two of the three dependent loads
+    // (record -> connectivity -> coordinates) off the critical path.
+    constexpr bool AHEAD = NN > 4 && (ROWS_VAR & 1);
+    int4 recAhead = make_int4(0, 0, 0, 0), connAhead[CW];
+    if (AHEAD && c0 < c1) {
+        recAhead = __ldg(reinterpret_cast<const int4*>(A.corners) + c0);
+#pragma unroll
+        for (int w = 0; w < CW; ++w) connAhead[w] = __ldg(A.connE + (long long)(recAhead.x & 0x0fffffff) * CW + w);
+    }
     for (int c = c0; c < c1; ++c) {
         int e, a, node[4 * CW];
         unsigned kw[CW];  // slot positions: 7-bit fields from bit 4 (NN <= 4) or bytes
@@ -138,7 +151,7 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
             kw[0] = (unsigned)rec.y;
             a = rec.y & 0xf;
         } else {
-            const int4 rec = __ldg(reinterpret_cast<const int4*>(A.corners) + c);
+            const int4 rec = AHEAD ? recAhead : __ldg(reinterpret_cast<const int4*>(A.corners) + c);
             e = rec.x & 0x0fffffff;
             a = (int)((unsigned)rec.x >> 28);
             kw[0] = (unsigned)rec.y;
@@ -147,11 +160,16 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
         }
 #pragma unroll
         for (int w = 0; w < CW; ++w) {
-            const int4 cn = (KNOCK & 4) ? make_int4((int)i, (int)i + 1, (int)i + 2, (int)i + 3) : __ldg(A.connE + (long long)e * CW + w);
+            const int4 cn = AHEAD ? connAhead[w] : (KNOCK & 4) ? make_int4((int)i, (int)i + 1, (int)i + 2, (int)i + 3) : __ldg(A.connE + (long long)e * CW + w);
             node[4 * w] = cn.x;
             node[4 * w + 1] = cn.y;
             node[4 * w + 2] = cn.z;
             node[4 * w + 3] = cn.w;
+        }
+        if (AHEAD && c + 1 < c1) {
+            recAhead = __ldg(reinterpret_cast<const int4*>(A.corners) + c + 1);
+#pragma unroll
+            for (int w = 0; w < CW; ++w) connAhead[w] = __ldg(A.connE + (long long)(recAhead.x & 0x0fffffff) * CW + w);
         }
         double x[NN], y[NN], ux[NN], uy[NN];
 #pragma unroll
