@@ -286,7 +286,8 @@ def run_ours(args, rank, world, local_rank):
     kernel_ms = kernel_ms_sum / max(kernel_calls, 1)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("k_assemble_rows") if (args.path == "rows" and args.config == "c2" and args.nx is None) else None,
+                "traffic": (ncu_traffic({"c2": "k_assemble_rows", "c3": "k_assemble_rows_config3"}.get(args.config, ""))
+                            if (args.path == "rows" and args.nx is None) else None),
                 "kernel": {"rows": "k_assemble_rows (one thread per node row, redundant element geometry, private swizzled smem row, coalesced warp write-out; BCs and loads fused)",
                            "patch": "k_assemble_pipe (persistent self-prefetching warp teams over node patches)",
                            "scatter": "k_assemble_sym (fused K_e/R_e evaluation + RED.F64 scatter)"}[args.path], "kernel_ms": kernel_ms,

@@ -58,6 +58,17 @@ __global__ void __launch_bounds__(128) k_function(const __grid_constant__ Tables
     }
     if (reduction == FEMB_REDUCE_NONE) return;
     if (reduction == FEMB_REDUCE_MEAN) r /= (double)NQ;
+    if (reduction == FEMB_REDUCE_KSMAX) {  // r holds the maximum; second pass re-evaluates the (bit-identical) point values
+        constexpr double rho = 100.0;      // KSAgg.py:26
+        double s = 0.0;
+#pragma unroll 1
+        for (int p = 0; p < NQ; ++p) {
+            double v, det;
+            point_function<NN, NQ, NL>(tb, D, func, p, x, y, ux, uy, v, det);
+            s += exp(rho * (v - r));
+        }
+        r += 1.0 / rho * log(1.0 / (double)NQ * s);
+    }
     F.out[e] = r;
 }
 
@@ -110,7 +121,7 @@ extern "C" int femb_function_dev(femb_plan* p, const double* d_coords, const dou
     TRY(need_final(p, "femb_function_dev"));
     if (!mat || !d_coords || !d_states || !d_out) return fail("femb_function_dev: NULL argument");
     if (func != FEMB_FUNC_MASS && func != FEMB_FUNC_VON_MISES) return fail("femb_function_dev: unknown function id %d", func);
-    if (reduction < FEMB_REDUCE_NONE || reduction > FEMB_REDUCE_MAX)
+    if (reduction < FEMB_REDUCE_NONE || reduction > FEMB_REDUCE_KSMAX)
         return fail("femb_function_dev: unknown reduction id %d", reduction);
     TRY(use_device(p));
     const DMat D = make_dmat(*mat);

@@ -88,8 +88,6 @@ class Element:
         if elementReductionType is not None:
             assert elementReductionType.lower() in ["sum", "mean", "integrate", "min", "max", "ksmax", "ksmin"], \
                 "elementReductionType not valid"
-            if elementReductionType.lower() in ["ksmax", "ksmin"]:
-                raise NotImplementedError("KS aggregation is outside the CUDA hot path (SURVEY.md section 2.1)")
         plan, X = self._flatPlan(nodeCoords, intOrder)
         q = np.ascontiguousarray(nodeStates, dtype=np.float64).reshape(-1, self.numStates)
         numElements = X.shape[0] // self.numNodes

@@ -11,7 +11,8 @@ from . import _lib
 from ._lib import as_f64, as_i64, check, dptr, iptr
 
 WANT_K, WANT_R = 1, 2
-REDUCTIONS = {None: 0, "none": 0, "sum": 1, "mean": 2, "integrate": 3, "min": 4, "max": 5}
+# "ksmin" is not a typo: the reference evaluates the KS *max* for both names (Element.py:261-265)
+REDUCTIONS = {None: 0, "none": 0, "sum": 1, "mean": 2, "integrate": 3, "min": 4, "max": 5, "ksmax": 6, "ksmin": 6}
 
 
 class AssemblyPlan:

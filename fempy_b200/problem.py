@@ -104,8 +104,6 @@ class B200AssemblyMixin:
         if elementReductionType is not None:
             assert elementReductionType.lower() in ["sum", "mean", "integrate", "min", "max", "ksmax", "ksmin"], \
                 "elementReductionType not valid"
-            if elementReductionType.lower() in ["ksmax", "ksmin"]:
-                raise NotImplementedError("KS aggregation is outside the CUDA hot path (SURVEY.md section 2.1)")
         del func
         plan, coords, q, _, mat = self._b200Inputs(self.states)
         vals = plan.function(coords, q, mat, funcId, elementReductionType)
@@ -123,7 +121,9 @@ class B200AssemblyMixin:
             assert globalReductionType.lower() in ["sum", "mean", "min", "max", "ksmax", "ksmin"], "globalReductionType not valid"
             red = globalReductionType.lower()
             if red in ("ksmax", "ksmin"):
-                raise NotImplementedError("KS aggregation is outside the CUDA hot path (SURVEY.md section 2.1)")
+                # Problem.py:335-347 calls its local ksMax() / ksMin() without arguments: the reference raises TypeError here
+                raise TypeError(f"globalReductionType '{globalReductionType}': the reference's ksMax()/ksMin() wrappers are called "
+                                "without their argument (FEMpy/Problem.py:340,347); no KS global reduction exists to mirror")
             reductionFunc = {"mean": np.average, "sum": np.sum, "min": np.min, "max": np.max}[red]
             globalValues = np.zeros(len(self.model.elements))
             for i, elType in enumerate(functionValues):

@@ -39,6 +39,8 @@ typedef struct femb_plan femb_plan;
 #define FEMB_REDUCE_INTEGRATE 3
 #define FEMB_REDUCE_MIN 4
 #define FEMB_REDUCE_MAX 5
+#define FEMB_REDUCE_KSMAX 6 /* KS aggregate, rho = 100 (FEMpy/Utils/KSAgg.py:25-58): max + log(mean(exp(rho (v - max)))) / rho.
+                               The reference reaches this for "ksmax" AND "ksmin" (Element.py:261-265) */
 
 /* what femb_assemble produces */
 #define FEMB_WANT_K 1

@@ -247,7 +247,8 @@ def element_residuals(dNdxi, w, X, q, theta, model, E, nu, nonlinear=False):
 
 
 MASS, VON_MISES = 0, 1
-REDUCTIONS = ("sum", "mean", "integrate", "min", "max")
+REDUCTIONS = ("sum", "mean", "integrate", "min", "max", "ksmax", "ksmin")
+KS_RHO = 100.0  # FEMpy/Utils/KSAgg.py:26
 
 
 def element_function(dNdxi, w, X, q, func, reduction, model, E, nu, rho, nonlinear=False):
@@ -283,6 +284,11 @@ def element_function(dNdxi, w, X, q, func, reduction, model, E, nu, rho, nonline
             out[lo:hi] = vals.min(axis=1)
         elif red == "max":
             out[lo:hi] = vals.max(axis=1)
+        elif red in ("ksmax", "ksmin"):
+            # Element.py:261-265: both names reach ksAgg(values, "max") (the "ksmin" branch below it is unreachable);
+            # KSAgg.py:52-53: max + log(mean(exp(rho (g - max)))) / rho
+            mx = vals.max(axis=1)
+            out[lo:hi] = mx + 1.0 / KS_RHO * np.log(1.0 / P * np.sum(np.exp(KS_RHO * (vals - mx[:, None])), axis=1))
         else:
             out[lo:hi] = np.einsum("ep,ep,p->e", vals, detJ, w)
     return out

@@ -9,6 +9,7 @@ Fixtures
   elements.npz    element-level K_e, R_e, von Mises point values for random elements of every family
                   x {plane stress, plane strain} x {linear, Green strain}  (the "finer seams" of SURVEY 8b)
   meshes.npz      assembled K (CSR), R, element functions on small quad / quad9 / triangle / mixed meshes
+  ks.npz          element-level KS reductions ("ksmax" / "ksmin", Element.py:261-265) of von Mises on the elements.npz inputs
   lbracket.npz    config 1: Examples/Meshes/LBracket.msh mesh arrays + assembled K, R, solution, functions
 """
 import os
@@ -72,6 +73,23 @@ def gen_elements(fp):
                 out[key + "_vmmean"] = el.computeFunction(X, q, dvs, cm.getFunction("Von-Mises-Stress"), "mean")
                 out[key + "_massint"] = el.computeFunction(X, q, dvs, cm.getFunction("Mass"), "integrate")
     np.savez_compressed(os.path.join(OUT, "elements.npz"), **out)
+
+
+def gen_ks(fp):
+    """KS element reductions (rho = 100, FEMpy/Utils/KSAgg.py:25-58) on the inputs of elements.npz.  Both names take
+    the reference's first branch (Element.py:261-265), i.e. the KS *max*; a soft material (E = 2) keeps the
+    exponentials away from 0/1 so the aggregate is not just max + log(1/P)/rho."""
+    g = np.load(os.path.join(OUT, "elements.npz"))
+    out = {}
+    for name, el in families(fp).items():
+        X, q, thick = g[f"{name}_X"], g[f"{name}_q"], g[f"{name}_t"]
+        for model in (0, 1):
+            for Emod in (MAT["E"], 2.0):
+                cm = rh.make_constitutive(fp, model, Emod, MAT["nu"], MAT["rho"], MAT["t"], True)
+                key = f"{name}_m{model}_E{'soft' if Emod == 2.0 else 'stiff'}"
+                for red in ("ksmax", "ksmin"):
+                    out[f"{key}_{red}"] = el.computeFunction(X, q, {"Thickness": thick}, cm.getFunction("Von-Mises-Stress"), red)
+    np.savez_compressed(os.path.join(OUT, "ks.npz"), **out)
 
 
 def mixed_grid(nx, ny):
@@ -188,9 +206,13 @@ def gen_lbracket(fp):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     fp = rh.import_reference()
+    if sys.argv[1:] == ["ks"]:  # later addition: leaves the other fixtures untouched
+        gen_ks(fp)
+        sys.exit(0)
     gen_tables(fp)
     gen_elements(fp)
     gen_meshes(fp)
     gen_lbracket(fp)
+    gen_ks(fp)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -78,6 +78,34 @@ def test_element_level_against_reference(family, model, linear):
     assert relerr(el.computeFunction(X, q, dvs, cm.getFunction("Mass"), "integrate"), g[key + "_massint"]) < TOL
 
 
+@pytest.mark.parametrize("family", sorted(FAMILY_ELEMENT))
+@pytest.mark.parametrize("model", [0, 1])
+def test_ks_element_reduction_against_reference(family, model):
+    """KS element reduction (Element.py:261-265, KSAgg.py:25-58) through femb_function: both names are the KS max"""
+    g, ks = golden("elements.npz"), golden("ks.npz")
+    el = ELEMENT_FOR[FAMILY_ELEMENT[family]]()
+    X, q, t = g[family + "_X"], g[family + "_q"], g[family + "_t"]
+    for tag, Emod in (("stiff", MAT["E"]), ("soft", 2.0)):
+        cm = make_cm(model, True, E=Emod)
+        for red in ("ksmax", "ksmin"):
+            v = el.computeFunction(X, q, {"Thickness": t}, cm.getFunction("Von-Mises-Stress"), red)
+            assert v.shape == (X.shape[0],) and relerr(v, ks[f"{family}_m{model}_E{tag}_{red}"]) < TOL, (tag, red)
+
+
+def test_ks_reduction_on_a_mesh_and_global_ks_error():
+    """Problem.computeFunction: element-level KS per element type == oracle; the global KS names raise TypeError as in
+    the reference (Problem.py:340,347 call ksMax()/ksMin() without their argument)"""
+    coords, conn = meshes.quad4_grid(24, 17)
+    m, p = build_problem(coords, conn, 0, E=3.0, states=1e-2 * np.random.default_rng(5).random(coords.shape))
+    got = p.computeFunction("Von-Mises-Stress", "ksmax")["quad"]
+    want = fo.compute_function(oracle_blocks(conn), coords, p.states, fo.VON_MISES, "ksmax", 0, 3.0, MAT["nu"], MAT["rho"])[0]
+    assert relerr(got, want) < TOL
+    hard = p.computeFunction("Von-Mises-Stress", "max")["quad"]
+    assert np.all(got <= hard + 1e-15) and np.all(got >= hard + np.log(1.0 / 4) / 100.0 - 1e-15)  # KS-mean bounds of the max
+    with pytest.raises(TypeError):
+        p.computeFunction("Von-Mises-Stress", "mean", "ksmax")
+
+
 def test_lbracket_config1():
     """BASELINE config 1 (Examples/LBracketExample.py): pattern, K, R, solve, von Mises, mass"""
     g = golden("lbracket.npz")

@@ -177,6 +177,20 @@ def test_element_level_against_reference(family, model, linear):
     assert relerr(mi, g[key + "_massint"]) < TOL
 
 
+@pytest.mark.parametrize("family", sorted(FAMILY_ELEMENT))
+@pytest.mark.parametrize("model", [0, 1])
+def test_ks_element_reduction_against_reference(family, model):
+    """Element.py:261-265 + Utils/KSAgg.py:25-58: "ksmax" and "ksmin" both give the KS max (rho = 100)"""
+    g, ks = golden("elements.npz"), golden("ks.npz")
+    N, dN, w = ELEMENT_FOR[FAMILY_ELEMENT[family]]().tables()
+    X, q = g[family + "_X"], g[family + "_q"]
+    for tag, Emod in (("stiff", MAT["E"]), ("soft", 2.0)):
+        for red in ("ksmax", "ksmin"):
+            v = fo.element_function(dN, w, X, q, fo.VON_MISES, red, model, Emod, MAT["nu"], MAT["rho"])
+            assert relerr(v, ks[f"{family}_m{model}_E{tag}_{red}"]) < TOL, (tag, red)
+    np.testing.assert_array_equal(ks[f"{family}_m{model}_Esoft_ksmax"], ks[f"{family}_m{model}_Esoft_ksmin"])
+
+
 @pytest.mark.parametrize("name", mesh_case_names(golden("meshes.npz")))
 def test_assembled_meshes_against_reference(name):
     g = golden("meshes.npz")
