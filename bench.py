@@ -217,6 +217,8 @@ def run_ours(args, rank, world, local_rank):
     plan.setLocalityHint(wl["coords"])
     plan.setOption("assembly_path", {"scatter": 0, "patch": 1, "rows": 2}[args.path])
     plan.setOption("team_warps", args.team_warps)
+    if args.balance_rows is not None:
+        plan.setOption("balance_rows", args.balance_rows)
     if args.debug_flags:
         plan.setOption("debug_flags", args.debug_flags)
     if args.patch_nodes:
@@ -326,7 +328,8 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step), "clocks": clocks,
         "plan_build": {"device_ms": plan.buildMs, "wall_ms": plan_wall_ms},
-        "path": {"assembly_path": args.path, "rows_path": plan.info("rows_path"), "max_degree": plan.info("max_degree"), "write_once_patches": plan.info("patch_path"), "patch_nodes": plan.info("patch_nodes"), "team_warps": plan.info("team_warps"), "num_patches": plan.info("num_patches"),
+        "path": {"assembly_path": args.path, "rows_path": plan.info("rows_path"), "max_degree": plan.info("max_degree"), "rows_balanced": plan.info("rows_balanced"),
+                 "row_iters": [plan.info("row_iters_node_order"), plan.info("row_iters_balanced")], "write_once_patches": plan.info("patch_path"), "patch_nodes": plan.info("patch_nodes"), "team_warps": plan.info("team_warps"), "num_patches": plan.info("num_patches"),
                  "patch_elems_total": plan.info("patch_elems_total"), "patch_elems_max": plan.info("patch_elems_max"),
                  "patch_colours_max": plan.info("patch_colours_max"), "patch_blob_bytes": plan.info("patch_blob_bytes")},
     }  # fmt: skip
@@ -480,6 +483,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--nx", type=int, default=None, help="override the mesh size (exploration only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--balance-rows", type=int, default=None, help="row schedule of the row-owner kernel: 0 node order, 1 balanced when it pays (default), 2 always")
     ap.add_argument("--cpu-procs", type=int, default=None, help="worker processes of the CPU legs (default: all host cores)")
     ap.add_argument("--flush-write-only", action="store_true", help="L2 flush by the 512 MB write alone (leaves dirty lines for the timed kernel to evict)")
     ap.add_argument("--patch-nodes", type=int, default=0, help="owned nodes per patch (0 = library default)")

@@ -221,7 +221,7 @@ bool rows_path_available(const femb_plan* p) {
     return smem <= 200 * 1024;
 }
 
-template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB>
+template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB, bool PERM>
 static int launch_rows_mb(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
     const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
     // accumulator rows + residual pairs + write-out owner table
@@ -230,17 +230,22 @@ static int launch_rows_mb(const femb_plan* p, const BlockData& b, const DMat& D,
     static size_t configured[64] = {};
     size_t& conf = configured[p->device & 63];
     if (smem > conf) {
-        CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB, PERM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conf = smem;
     }
-    rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB><<<grid_for(p->numNodes, rows::BLOCK), rows::BLOCK, smem, st>>>(tb, D, A);
+    const long long slots = PERM ? p->rowSlots : p->numNodes;
+    rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB, PERM><<<grid_for(slots, rows::BLOCK), rows::BLOCK, smem, st>>>(tb, D, A);
     return 0;
 }
 
 template <int NN, int NQ, bool NL, bool WK, bool WR>
 static int launch_rows(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
-    if (p->blocks.size() > 1) return launch_rows_mb<NN, NQ, NL, WK, WR, true>(p, b, D, A, st);
-    return launch_rows_mb<NN, NQ, NL, WK, WR, false>(p, b, D, A, st);
+    if (p->rowsBalanced) {
+        if (p->blocks.size() > 1) return launch_rows_mb<NN, NQ, NL, WK, WR, true, true>(p, b, D, A, st);
+        return launch_rows_mb<NN, NQ, NL, WK, WR, false, true>(p, b, D, A, st);
+    }
+    if (p->blocks.size() > 1) return launch_rows_mb<NN, NQ, NL, WK, WR, true, false>(p, b, D, A, st);
+    return launch_rows_mb<NN, NQ, NL, WK, WR, false, false>(p, b, D, A, st);
 }
 
 template <int NN, int NQ>
@@ -330,6 +335,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
         if (rowsPath) {
             rows::Args A;
             A.numNodes = p->numNodes;
+            A.slotRec = p->d_slotRec;
             A.nrowptr = p->d_nrowptr;
             A.ncols = p->d_ncols;
             const size_t k = &b - &p->blocks[0];

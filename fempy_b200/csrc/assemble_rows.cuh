@@ -30,6 +30,7 @@ static constexpr int MAXD = 48;  // largest node degree (neighbours incl. itself
 
 struct Args {
     long long numNodes;
+    const int4* slotRec;     // balanced schedule (PERM kernels): {node or -1, first value of the row, degree | corners << 8, first corner}
     const int* nrowptr;
     const int* ncols;
     const int* cBegin;       // per node: first / one-past-last corner of this element block (global corner numbers)
@@ -66,7 +67,9 @@ __host__ __device__ constexpr int resident_threads() {
 
 // MB: the plan has several element blocks (one launch per block: later blocks add to what earlier ones left in K and R,
 // the last one applies loads and boundary conditions); single-block plans compile those switches away
-template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB>
+// PERM: the thread's node comes from the plan's balanced row schedule (nodes of a window ordered by corner count) instead
+// of the thread index; the warp's rows are then 32 separate runs of the CSR values instead of one
+template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB, bool PERM>
 __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const __grid_constant__ femb::DMat D,
                                                         const Args A) {
     using namespace femb;
@@ -80,13 +83,18 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gStart));
 #endif
     const int tid = threadIdx.x, lane = tid & 31;
-    const long long i = (long long)blockIdx.x * BLOCK + tid;
-    const bool valid = i < A.numNodes;
-    const int off = __ldg(A.nrowptr + (valid ? i : A.numNodes));  // tail lanes: end of the values, degree 0
-    const int deg = valid ? __ldg(A.nrowptr + i + 1) - off : 0;
+    const long long slot0 = (long long)blockIdx.x * BLOCK + tid;
+    int4 srec = make_int4(0, 0, 0, 0);
+    if (PERM) srec = __ldg(A.slotRec + slot0);
+    const long long i = PERM ? (long long)srec.x : slot0;
+    const bool valid = PERM ? i >= 0 : i < A.numNodes;
+    const int off = PERM ? srec.y : __ldg(A.nrowptr + (valid ? i : A.numNodes));  // tail lanes: end of the values, degree 0
+    const int deg = PERM ? (srec.z & 0xff) : valid ? __ldg(A.nrowptr + i + 1) - off : 0;
     auto slot = [&](int m) -> double2& { return acc[m * BLOCK + ((tid + m) & (BLOCK - 1))]; };
     // loads the kernel waits on later are issued here: the corner range (start of the corner loop) and the BC word (epilogue)
-    const int c0 = valid ? __ldg(A.cBegin + i) : 0, c1 = valid ? __ldg(A.cEnd + i) : 0;
+    // (balanced single-block plans carry the range in the slot record)
+    const int c0 = (PERM && !MB) ? srec.w : valid ? __ldg(A.cBegin + i) : 0;
+    const int c1 = (PERM && !MB) ? srec.w + (int)((unsigned)srec.z >> 8) : valid ? __ldg(A.cEnd + i) : 0;
     const unsigned info = (valid && A.bcInfo && finalise) ? (unsigned)__ldg(A.bcInfo + i) : 0u;
 
     // The rows of the warp's 32 consecutive nodes are one contiguous run of the CSR values (both DOF rows of a node
@@ -98,7 +106,22 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     const int wbase = tid - lane;
     unsigned char* owner = reinterpret_cast<unsigned char*>(acc + 2 * A.maxDeg * BLOCK + BLOCK) + 2 * A.maxDeg * wbase;
     double2& racc = acc[2 * A.maxDeg * BLOCK + tid];  // residual pair of the node: kept in shared memory, not in registers
-    const int ownStart = (WK && !(KNOCK & 8)) ? 2 * (off - __shfl_sync(0xffffffffu, off, 0)) : 0;  // my first position in the run
+    // my first position in the warp's run of values (PERM: in the concatenation of the 32 separate runs)
+    int ownStart = 0;
+    if (WK && !(KNOCK & 8)) {
+        if (PERM) {
+            int incl = 2 * deg;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
+            }
+            ownStart = incl - 2 * deg;
+        } else {
+            ownStart = 2 * (off - __shfl_sync(0xffffffffu, off, 0));
+        }
+    }
+    const int ownGlobal = 2 * off - ownStart;  // PERM: value position (double2 units) = ownGlobal of the owning lane + run position
     // owner table + zeroed accumulators: thread-private stores, so they run under the first corner's loads
     auto fill = [&]() {
         if (WK && !(KNOCK & 8))
@@ -113,7 +136,7 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
             for (int m = 0; m < 2 * deg; ++m) owner[ownStart + m] = (unsigned char)lane;
         if (WK) {
             const int base = __shfl_sync(0xffffffffu, off, 0);
-            const int start = 2 * (off - base);
+            const int start = ownStart;
             const int total = __shfl_sync(0xffffffffu, start + 2 * deg, 31);  // invalid tail lanes hold off = end, deg = 0
             __syncwarp();
             for (int f0 = 0; f0 < total; f0 += 32) {
@@ -121,7 +144,8 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
                 const bool ok = f < total;
                 const int r = ok ? owner[f] : 0;
                 const int mm = f - __shfl_sync(0xffffffffu, start, r);
-                if (ok) acc[mm * BLOCK + ((wbase + r + mm) & (BLOCK - 1))] = K2[2ll * base + f];
+                const long long g = PERM ? (long long)__shfl_sync(0xffffffffu, ownGlobal, r) + f : 2ll * base + f;
+                if (ok) acc[mm * BLOCK + ((wbase + r + mm) & (BLOCK - 1))] = K2[g];
             }
             __syncwarp();
         }
@@ -350,7 +374,7 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     // ---- write-out: stream the warp's run of CSR values (owner table built at the top) ------------------------------
     if (WK && !(KNOCK & 8)) {
         const int base = __shfl_sync(0xffffffffu, off, 0);
-        const int start = 2 * (off - base);
+        const int start = PERM ? ownStart : 2 * (off - base);  // (node order: recomputed rather than carried across the corner loop)
         const int total = __shfl_sync(0xffffffffu, start + 2 * deg, 31);  // invalid tail lanes hold off = end, deg = 0
         __syncwarp();
         for (int f0 = 0; f0 < total; f0 += 32) {
@@ -358,7 +382,8 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
             const bool ok = f < total;
             const int r = ok ? owner[f] : 0;
             const int mm = f - __shfl_sync(0xffffffffu, start, r);
-            if (ok) st_stream(K2 + 2ll * base + f, acc[mm * BLOCK + ((wbase + r + mm) & (BLOCK - 1))]);
+            const long long g = PERM ? (long long)__shfl_sync(0xffffffffu, ownGlobal, r) + f : 2ll * base + f;
+            if (ok) st_stream(K2 + g, acc[mm * BLOCK + ((wbase + r + mm) & (BLOCK - 1))]);
         }
     }
     if (WR && valid) {

@@ -105,6 +105,12 @@ struct femb_plan {
     int debugFlags = 0;                // measurement only
     int usePatch = 2;            // assembly path: 2 row-owner kernel, 1 write-once patch pipeline, 0 slot-map scatter with FP64 atomics
     int* d_blockAdj = nullptr;   // (numBlocks+1) x numNodes: start of each block's corners in a node's adjacency list (row-owner kernel)
+    int* d_rowOrder = nullptr;   // plan-time temporary: balanced row order (plan.cu: k_row_order), node of every thread slot, -1 = padding
+    int4* d_slotRec = nullptr;   // balanced row schedule: one record per thread slot (plan.cu: k_slot_records); NULL = node order
+    long long rowSlots = 0;      // thread slots of the balanced schedule (multiple of the sort window)
+    long long rowIters[2] = {0, 0};  // sum over warps of the longest corner walk: node order / balanced order
+    bool rowsBalanced = false;
+    int balanceRows = 1;         // option "balance_rows": 0 never, 1 when it saves > 8 % of the corner iterations, 2 always
     bool rowsBuilt = false;      // corner records / element-major connectivity exist for every block
     int maxDeg = 0;              // largest node degree
     // boundary conditions, de-duplicated on the host with the reference's semantics

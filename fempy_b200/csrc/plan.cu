@@ -203,6 +203,47 @@ __global__ void k_max_int(const int* __restrict__ v, long long n, int* __restric
     if (i < n) atomicMax(out, v[i]);
 }
 
+// Row schedule of the row-owner kernel: inside every window of ROW_WINDOW consecutive nodes the nodes are ordered by
+// falling corner count (stable), so that the 32 nodes a warp owns walk the same number of corners (a 9-node quad mesh
+// alternates nodes with 4 / 2 / 1 adjacent elements: in node order a warp idles on a quarter of its corner iterations).
+// iters[0] / iters[1]: sum over warps of the longest corner walk in node order / in the balanced order.
+constexpr int ROW_WINDOW = 256;
+__global__ void __launch_bounds__(ROW_WINDOW) k_row_order(long long N, const int* __restrict__ cFirst, const int* __restrict__ cLast,
+                                                         int* __restrict__ order, unsigned long long* __restrict__ iters) {
+    __shared__ int cnt[ROW_WINDOW];
+    __shared__ int sorted[ROW_WINDOW];
+    const int t = threadIdx.x;
+    const long long i = (long long)blockIdx.x * ROW_WINDOW + t;
+    const int mine = i < N ? cLast[i] - cFirst[i] : -1;  // padding slots sort to the end
+    cnt[t] = mine;
+    __syncthreads();
+    int rank = 0;
+    for (int u = 0; u < ROW_WINDOW; ++u) rank += (cnt[u] > mine) || (cnt[u] == mine && u < t);
+    order[(long long)blockIdx.x * ROW_WINDOW + rank] = i < N ? (int)i : -1;
+    sorted[rank] = mine;
+    __syncthreads();
+    const int a = __reduce_max_sync(0xffffffffu, max(mine, 0)), b = __reduce_max_sync(0xffffffffu, max(sorted[t], 0));
+    if ((t & 31) == 0) {
+        atomicAdd(iters, (unsigned long long)a);
+        atomicAdd(iters + 1, (unsigned long long)b);
+    }
+}
+
+// slot records of the balanced schedule: everything a thread needs before its corner loop in one coalesced 16-byte load
+// {node (-1: padding), first value of the node row, degree | corners of the first block << 8, first corner of the first block}
+__global__ void k_slot_records(long long slots, const int* __restrict__ order, const int* __restrict__ nrowptr,
+                               const int* __restrict__ cFirst, const int* __restrict__ cLast, int4* __restrict__ rec) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    const int i = order[s];
+    if (i < 0) {
+        rec[s] = make_int4(-1, 0, 0, 0);
+        return;
+    }
+    const int off = nrowptr[i], c0 = cFirst[i];
+    rec[s] = make_int4(i, off, (nrowptr[i + 1] - off) | ((cLast[i] - c0) << 8), c0);
+}
+
 __global__ void k_permute_mask(const int* __restrict__ order, const unsigned char* __restrict__ mask, long long N,
                                unsigned char* __restrict__ maskPerm) {
     const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -396,6 +437,32 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
                 launches += 2;
             }
             p->rowsBuilt = true;
+            {  // balanced row schedule: kept only when it saves more than 8 % of the warps' corner iterations
+                const long long windows = (N + ROW_WINDOW - 1) / ROW_WINDOW;
+                unsigned long long* d_iters = nullptr;
+                unsigned long long iters[2] = {0, 0};
+                CUDA_TRY(cudaMalloc(&p->d_rowOrder, windows * ROW_WINDOW * sizeof(int)));
+                CUDA_TRY(cudaMalloc(&d_iters, sizeof(iters)));
+                CUDA_TRY(cudaMemsetAsync(d_iters, 0, sizeof(iters), st));
+                k_row_order<<<(unsigned)windows, ROW_WINDOW, 0, st>>>(N, p->d_blockAdj, p->d_blockAdj + nb * (size_t)N, p->d_rowOrder, d_iters);
+                launches++;
+                CUDA_TRY(cudaMemcpyAsync(iters, d_iters, sizeof(iters), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                cudaFree(d_iters);
+                p->rowSlots = windows * ROW_WINDOW;
+                p->rowIters[0] = (long long)iters[0];
+                p->rowIters[1] = (long long)iters[1];
+                p->rowsBalanced = p->balanceRows != 0 && (p->balanceRows == 2 || (double)iters[1] < 0.92 * (double)iters[0]);
+                if (p->rowsBalanced) {
+                    CUDA_TRY(cudaMalloc(&p->d_slotRec, p->rowSlots * sizeof(int4)));
+                    k_slot_records<<<grid_for(p->rowSlots, 256), 256, 0, st>>>(p->rowSlots, p->d_rowOrder, p->d_nrowptr, p->d_blockAdj,
+                                                                             p->d_blockAdj + (size_t)N, p->d_slotRec);
+                    launches++;
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                }
+                cudaFree(p->d_rowOrder);
+                p->d_rowOrder = nullptr;
+            }
         }
     }
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -433,6 +500,9 @@ extern "C" void femb_plan_destroy(femb_plan* p) {
     dfree(p->d_adjPtr);
     dfree(p->d_adj);
     dfree(p->d_blockAdj);
+    dfree(p->d_rowOrder);
+    if (p->d_slotRec) cudaFree(p->d_slotRec);
+    p->d_slotRec = nullptr;
     for (auto& b : p->blocks) {
         dfree(b.d_connE);
         if (b.d_corners) cudaFree(b.d_corners);
@@ -498,6 +568,10 @@ extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t valu
         if (value < 0 || value > 2) return fail("femb_plan_set_option: assembly_path must be 0 (scatter), 1 (patch pipeline) or 2 (row owner)");
         if (value == 1 && p->finalized && !p->patchesBuilt) return fail("femb_plan_set_option: the patch pipeline must be selected before finalize");
         p->usePatch = (int)value;
+    } else if (!strcmp(name, "balance_rows")) {
+        if (p->finalized) return fail("femb_plan_set_option: balance_rows must be set before finalize");
+        if (value < 0 || value > 2) return fail("femb_plan_set_option: balance_rows must be 0 (never), 1 (when it pays) or 2 (always)");
+        p->balanceRows = (int)value;
     } else if (!strcmp(name, "debug_flags")) {
         p->debugFlags = (int)value;
 
@@ -535,6 +609,9 @@ extern "C" int64_t femb_plan_get_info(const femb_plan* p, const char* name) {
     if (!strcmp(name, "assembly_path")) return p->usePatch;
     if (!strcmp(name, "rows_path")) return rows_path_available(p) ? 1 : 0;
     if (!strcmp(name, "max_degree")) return p->maxDeg;
+    if (!strcmp(name, "rows_balanced")) return p->rowsBalanced ? 1 : 0;
+    if (!strcmp(name, "row_iters_node_order")) return p->rowIters[0];
+    if (!strcmp(name, "row_iters_balanced")) return p->rowIters[1];
     if (!strcmp(name, "patch_path")) return patch_path_available(p, true, true) ? 1 : 0;
     return -1;
 }

@@ -300,7 +300,7 @@ def test_full_size_properties(elType, n, label):
 PATHS = {"scatter": 0, "patch": 1, "rows": 2}
 
 
-def _raw_plan(elType, coords, conn, hint=True, patchNodes=None, path="rows", teamWarps=None):
+def _raw_plan(elType, coords, conn, hint=True, patchNodes=None, path="rows", teamWarps=None, balance=None):
     el = ELEMENT_FOR[elType]()
     plan = AssemblyPlan(coords.shape[0])
     if hint:
@@ -310,6 +310,8 @@ def _raw_plan(elType, coords, conn, hint=True, patchNodes=None, path="rows", tea
         plan.setOption("patch_nodes", patchNodes)
     if teamWarps is not None:
         plan.setOption("team_warps", teamWarps)
+    if balance is not None:
+        plan.setOption("balance_rows", balance)
     N_, dN, w = el.tables()
     plan.addBlock(N_, dN, w, conn[elType])
     plan.finalize()
@@ -401,13 +403,17 @@ def _renumbered(case, seed=3):
 
 @pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29), ("quad9", 11), ("triangle6", 12)])
 @pytest.mark.parametrize("renumber", [False, True])
-def test_row_owner_kernel_matches_oracle(elType, n, renumber):
-    """default path: one thread per node row, every K value and R entry written exactly once = 1 launch"""
+@pytest.mark.parametrize("balance", [0, 2])
+def test_row_owner_kernel_matches_oracle(elType, n, renumber, balance):
+    """default path: one thread per node row, every K value and R entry written exactly once = 1 launch;
+    in node order (balance 0) and with the balanced row schedule forced (2: windows of nodes ordered by corner count)"""
     case = _path_case(elType, n)
     if renumber:
         case = _renumbered(case)
-    plan = _raw_plan(elType, case[0], case[1], path="rows")
+    plan = _raw_plan(elType, case[0], case[1], path="rows", balance=balance)
     assert plan.info("rows_path") == 1 and plan.info("num_patches") == 0  # no patch programs are built for this path
+    assert plan.info("rows_balanced") == (1 if balance == 2 else 0)
+    assert 0 < plan.info("row_iters_balanced") <= plan.info("row_iters_node_order")
     _check_against_oracle(plan, elType, case, launchesExpected=1)
     # Green-strain model through the same kernel family
     coords, conn, states, thick, loads, bcDOF, bcVal = case
@@ -423,7 +429,8 @@ def test_row_owner_kernel_matches_oracle(elType, n, renumber):
 
 
 @pytest.mark.parametrize("order", [("quad", "triangle"), ("triangle", "quad")])
-def test_mixed_mesh_row_owner_matches_oracle(order):
+@pytest.mark.parametrize("balance", [0, 2])
+def test_mixed_mesh_row_owner_matches_oracle(order, balance):
     """several element blocks: one row-owner launch per block (later blocks add to the rows the earlier ones wrote,
     the last one applies loads and BCs) -- still no atomics, 2 launches for 2 blocks"""
     coords, cq = meshes.quad4_grid(31, 23)
@@ -443,10 +450,11 @@ def test_mixed_mesh_row_owner_matches_oracle(order):
     bcVal = rng.random(bcDOF.size) * 1e-4
     plan = AssemblyPlan(N)
     plan.setLocalityHint(coords)
+    plan.setOption("balance_rows", balance)
     for elType, c in conn.items():
         plan.addBlock(*ELEMENT_FOR[elType]().tables(), c)
     plan.finalize()
-    assert plan.info("rows_path") == 1
+    assert plan.info("rows_path") == 1 and plan.info("rows_balanced") == (1 if balance == 2 else 0)
     case = (coords, conn, states, thick, loads, bcDOF, bcVal)
     K1, R1 = _check_against_oracle(plan, None, case, launchesExpected=2)
     plan.setOption("assembly_path", 0)  # scatter kernels: memset-free init + one launch per block + BC kernel
