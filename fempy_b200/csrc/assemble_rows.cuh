@@ -158,19 +158,29 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     // Wide families (6-10 nodes) run at 8-12 warps per SM with registers to spare: the next corner's record and
     // connectivity words are fetched one iteration ahead, which takes two of the three dependent loads
     // (record -> connectivity -> coordinates) off the critical path.
-    constexpr bool AHEAD = NN > 4 && (ROWS_VAR & 1);
+    constexpr bool AHEAD = (NN > 4 && (ROWS_VAR & 1)) || (NN == 3 && (ROWS_VAR & 2));
+    auto load_rec = [&](int c) -> int4 {
+        if constexpr (NN <= 4) {
+            const int2 r = __ldg(reinterpret_cast<const int2*>(A.corners) + c);
+            return make_int4(r.x, r.y, 0, 0);
+        } else {
+            return __ldg(reinterpret_cast<const int4*>(A.corners) + c);
+        }
+    };
+    constexpr int EMASK = NN <= 4 ? 0x7fffffff : 0x0fffffff;
     int4 recAhead = make_int4(0, 0, 0, 0), connAhead[CW];
     if (AHEAD && c0 < c1) {
-        recAhead = __ldg(reinterpret_cast<const int4*>(A.corners) + c0);
+        recAhead = load_rec(c0);
 #pragma unroll
-        for (int w = 0; w < CW; ++w) connAhead[w] = __ldg(A.connE + (long long)(recAhead.x & 0x0fffffff) * CW + w);
+        for (int w = 0; w < CW; ++w) connAhead[w] = __ldg(A.connE + (long long)(recAhead.x & EMASK) * CW + w);
     }
     for (int c = c0; c < c1; ++c) {
         int e, a, node[4 * CW];
         unsigned kw[CW];  // slot positions: 7-bit fields from bit 4 (NN <= 4) or bytes
         if constexpr (NN <= 4) {
-            const int2 rec = (KNOCK & 4) ? make_int2(c & 0xffff, ((c - c0) & 3) | (1 << 11) | (2 << 18) | (3 << 25))
-                                         : __ldg(reinterpret_cast<const int2*>(A.corners) + c);
+            const int2 rec = AHEAD ? make_int2(recAhead.x, recAhead.y)
+                             : (KNOCK & 4) ? make_int2(c & 0xffff, ((c - c0) & 3) | (1 << 11) | (2 << 18) | (3 << 25))
+                                           : __ldg(reinterpret_cast<const int2*>(A.corners) + c);
             e = rec.x;
             kw[0] = (unsigned)rec.y;
             a = rec.y & 0xf;
@@ -191,9 +201,9 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
             node[4 * w + 3] = cn.w;
         }
         if (AHEAD && c + 1 < c1) {
-            recAhead = __ldg(reinterpret_cast<const int4*>(A.corners) + c + 1);
+            recAhead = load_rec(c + 1);
 #pragma unroll
-            for (int w = 0; w < CW; ++w) connAhead[w] = __ldg(A.connE + (long long)(recAhead.x & 0x0fffffff) * CW + w);
+            for (int w = 0; w < CW; ++w) connAhead[w] = __ldg(A.connE + (long long)(recAhead.x & EMASK) * CW + w);
         }
         double x[NN], y[NN], ux[NN], uy[NN];
 #pragma unroll

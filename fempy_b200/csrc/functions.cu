@@ -28,7 +28,8 @@ static int stage(double** buf, const double* host, size_t n, cudaStream_t st) {
 // =============================================================================================
 // element function kernel
 // =============================================================================================
-template <int NN, int NQ, bool NL>
+// KS: separate instantiation for the KS aggregate (second pass + exp/log) so the plain reductions keep their registers
+template <int NN, int NQ, bool NL, bool KS>
 __global__ void __launch_bounds__(128) k_function(const __grid_constant__ Tables<NN, NQ> tb, const DMat D,
                                                   const FuncArgs F, const int func, const int reduction) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(128) k_function(const __grid_constant__ Tables
     }
     if (reduction == FEMB_REDUCE_NONE) return;
     if (reduction == FEMB_REDUCE_MEAN) r /= (double)NQ;
-    if (reduction == FEMB_REDUCE_KSMAX) {  // r holds the maximum; second pass re-evaluates the (bit-identical) point values
+    if (KS) {  // r holds the maximum; second pass re-evaluates the (bit-identical) point values
         constexpr double rho = 100.0;      // KSAgg.py:26
         double s = 0.0;
 #pragma unroll 1
@@ -112,8 +113,11 @@ template <int NN, int NQ>
 static void launch_function(const BlockData& b, const DMat& D, const FuncArgs& F, bool nl, int func, int reduction,
                             cudaStream_t st) {
     const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
-    if (nl) k_function<NN, NQ, true><<<grid_for(F.E, 128), 128, 0, st>>>(tb, D, F, func, reduction);
-    else k_function<NN, NQ, false><<<grid_for(F.E, 128), 128, 0, st>>>(tb, D, F, func, reduction);
+    const bool ks = reduction == FEMB_REDUCE_KSMAX;
+    if (nl && ks) k_function<NN, NQ, true, true><<<grid_for(F.E, 128), 128, 0, st>>>(tb, D, F, func, reduction);
+    else if (nl) k_function<NN, NQ, true, false><<<grid_for(F.E, 128), 128, 0, st>>>(tb, D, F, func, reduction);
+    else if (ks) k_function<NN, NQ, false, true><<<grid_for(F.E, 128), 128, 0, st>>>(tb, D, F, func, reduction);
+    else k_function<NN, NQ, false, false><<<grid_for(F.E, 128), 128, 0, st>>>(tb, D, F, func, reduction);
 }
 
 extern "C" int femb_function_dev(femb_plan* p, const double* d_coords, const double* d_states, const femb_material* mat,

@@ -92,9 +92,13 @@ int femb_plan_set_locality_hint(femb_plan* plan, const double* coords);
  *       kernels with FP64 atomics (every family);
  *   "patch_nodes" (owned nodes per patch, before finalize; 0 = default), "team_warps" (1 or 2, before finalize):
  *       patch pipeline only;
+ *   "balance_rows" (before finalize): row schedule of the row-owner kernel -- 0 threads take nodes in node order,
+ *       1 (default) nodes of every 256-node window are ordered by their number of adjacent elements when that saves
+ *       more than 8 % of the warps' element iterations (9-node quads, mixed meshes), 2 always; results do not depend on it;
  *   "debug_flags": measurement builds only */
 int femb_plan_set_option(femb_plan* plan, const char* name, int64_t value);
-/* "assembly_path", "rows_path" (1: the row-owner kernel will run), "max_degree", "patch_path", "num_patches",
+/* "assembly_path", "rows_path" (1: the row-owner kernel will run), "max_degree", "rows_balanced", "row_iters_node_order",
+ * "row_iters_balanced" (sum over warps of the longest element walk in either schedule), "patch_path", "num_patches",
  * "patch_nodes", "team_warps", "patch_elems_total", "patch_elems_max", "patch_blob_bytes", "patch_colours_max";
  * -1 for an unknown name */
 int64_t femb_plan_get_info(const femb_plan* plan, const char* name);
