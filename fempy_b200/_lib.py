@@ -54,6 +54,12 @@ _SIGNATURES = {
     "femb_plan_pipe_stats": (C.c_int, [C.c_void_p, C.c_int32, c_int64_p, C.c_int64]),
     "femb_function": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.POINTER(Material), C.c_int32, C.c_int32, c_double_p]),
     "femb_function_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Material), C.c_int32, C.c_int32, C.c_void_p]),
+    "femb_solve_pcg": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int32, C.POINTER(C.c_int32), c_double_p]),
+    "femb_solve_pcg_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.POINTER(C.c_int32),
+                                     c_double_p]),
+    "femb_assemble_solve": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.POINTER(Material), c_int64_p, c_double_p,
+                                      C.c_int64, c_double_p, C.c_double, C.c_int32, c_double_p, c_double_p, C.POINTER(C.c_int32),
+                                      c_double_p]),
     "femb_element_blocks": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.POINTER(Material), c_double_p, c_double_p]),
     "femb_local_matrices_to_coo": (C.c_int, [c_double_p, c_int64_p, C.c_int64, C.c_int32, C.c_int32, c_int64_p, c_int64_p,
                                              c_double_p, c_int64_p]),

@@ -130,6 +130,7 @@ struct femb_plan {
     double *s_coords = nullptr, *s_states = nullptr, *s_thick = nullptr, *s_loads = nullptr, *s_K = nullptr,
            *s_R = nullptr, *s_out = nullptr;
     size_t s_outCap = 0;
+    void* s_solve = nullptr;  // work vectors + scalars of femb_solve_pcg_dev (solve.cu)
     int* d_flag = nullptr;
     // optional CUDA-event timing of the dominant assembly kernel(s) (bench.py roofline leg)
     bool profile = false;

@@ -501,6 +501,8 @@ extern "C" void femb_plan_destroy(femb_plan* p) {
     dfree(p->d_adj);
     dfree(p->d_blockAdj);
     dfree(p->d_rowOrder);
+    if (p->s_solve) cudaFree(p->s_solve);
+    p->s_solve = nullptr;
     if (p->d_slotRec) cudaFree(p->d_slotRec);
     p->d_slotRec = nullptr;
     for (auto& b : p->blocks) {

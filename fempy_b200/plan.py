@@ -192,6 +192,34 @@ class AssemblyPlan:
     def functionDev(self, d_coords, d_states, material, funcId, reduction, d_out):
         check(self._lib.femb_function_dev(self._h, _p(d_coords), _p(d_states), C.byref(material), int(funcId), int(reduction), _p(d_out)))
 
+    def solvePCG(self, K, rhs, relTol=1e-10, maxIter=20000):
+        """K x = rhs on the GPU (femb_solve_pcg): K = the CSR values assembled with applyBCs and the plan's current BCs.
+        Returns (x, iterations, relative residual)."""
+        Kv, b = as_f64(K), as_f64(rhs)
+        x = np.empty(self.numDOF)
+        it, res = C.c_int32(0), C.c_double(0.0)
+        check(self._lib.femb_solve_pcg(self._h, dptr(Kv), dptr(b), dptr(x), float(relTol), int(maxIter), C.byref(it), C.byref(res)))
+        return x, it.value, res.value
+
+    def assembleSolve(self, coords, states, thickness, material, bcDOF, bcValues, loads=None, relTol=1e-10, maxIter=20000):
+        """One fused assembly (BCs applied) + update = K^-1 (-R) on the GPU (femb_assemble_solve); the CSR values stay on
+        the device.  Returns (update, R, iterations, relative residual)."""
+        c, q, t = as_f64(coords), as_f64(states), as_f64(thickness)
+        bcd, bcv = as_i64(bcDOF if bcDOF is not None else []), as_f64(bcValues if bcValues is not None else [])
+        ld = as_f64(loads) if loads is not None else None
+        update, R = np.empty(self.numDOF), np.empty(self.numDOF)
+        it, res = C.c_int32(0), C.c_double(0.0)
+        check(self._lib.femb_assemble_solve(
+            self._h, dptr(c), dptr(q), dptr(t), C.byref(material), iptr(bcd) if bcd.size else None, dptr(bcv) if bcd.size else None,
+            bcd.size, dptr(ld) if ld is not None else None, float(relTol), int(maxIter), dptr(update), dptr(R), C.byref(it), C.byref(res)))  # fmt: skip
+        return update, R, it.value, res.value
+
+    def solvePCGDev(self, d_K, d_rhs, d_x, relTol=1e-10, maxIter=20000):
+        """Device pointers; synchronises the plan's stream every 25 iterations.  Returns (iterations, relative residual)."""
+        it, res = C.c_int32(0), C.c_double(0.0)
+        check(self._lib.femb_solve_pcg_dev(self._h, _p(d_K), _p(d_rhs), _p(d_x), float(relTol), int(maxIter), C.byref(it), C.byref(res)))
+        return it.value, res.value
+
     def profile(self, enable=True):
         check(self._lib.femb_plan_profile(self._h, int(bool(enable))))
 

@@ -97,6 +97,20 @@ class B200AssemblyMixin:
         indptr, indices = plan.pattern()
         return csr_array((K, indices, indptr), shape=(self.numDOF, self.numDOF)), R
 
+    def solveOnDevice(self, relTol=1e-10, maxIter=50000):
+        """`solve` (Problem.py:137-169) with the linear solve on the GPU as well: one fused K + R assembly, then
+        update = K^-1 (-R) by preconditioned CG on the device-resident CSR values (femb_assemble_solve) -- the matrix never
+        crosses PCIe and no csr_array / factorisation is built.  Not in the reference API; the answer agrees with the
+        direct solve to about relTol x condition number.  Returns {"iterations", "relativeResidual"}."""
+        plan, coords, q, thickness, mat = self._b200Inputs(self.states)
+        bcDOF, bcVal = AssemblyUtils.convertBCDictToLists(self.getBCs())
+        loads = AssemblyUtils.convertLoadsDictToVector(self.loads, self.numDOF) if self.loads else None
+        update, R, iters, res = plan.assembleSolve(coords, q, thickness, mat, bcDOF, bcVal, loads, relTol, maxIter)
+        self.Res = R
+        self.incrementState(update)
+        self.solveCounter += 1
+        return {"iterations": iters, "relativeResidual": res}
+
     def computeFunction(self, name, elementReductionType, globalReductionType=None):
         """Element function over the whole model (Problem.py:282-355)."""
         func = self.model.constitutiveModel.getFunction(name)  # raises ValueError for unknown names

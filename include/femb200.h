@@ -155,6 +155,26 @@ int femb_function(femb_plan* plan, const double* coords, const double* states, c
 int femb_function_dev(femb_plan* plan, const double* d_coords, const double* d_states, const femb_material* mat,
                       int32_t func, int32_t reduction, double* d_out);
 
+/* ---- device-resident linear solve: the hand-off after assembly.
+ * Replaces, on request, the host factorisation of FEMpyProblem.solveJacLinear (FEMpy/Problem.py:171-198).  K: the
+ * plan's CSR values as femb_assemble[_dev] left them with applyBCs = 1 and the plan's current BC set (constrained rows =
+ * zeros + occurrence count on the diagonal, AssemblyUtils.py:26-62); b, x: numDOF.  Solves K x = b by Jacobi-
+ * preconditioned conjugate gradients on the free DOFs (x_c = b_c / count substituted; symmetric positive definite for
+ * the elasticity models) until ||r|| <= relTol ||r_0|| or maxIter; iters / relRes may be NULL.  Three launches per
+ * iteration on the plan's stream, host check every 25 iterations.  Not a bit-for-bit replacement of a direct solve:
+ * the answer agrees with it to about relTol x condition number. */
+int femb_solve_pcg(femb_plan* plan, const double* K, const double* b, double* x, double relTol, int32_t maxIter,
+                   int32_t* iters, double* relRes);
+int femb_solve_pcg_dev(femb_plan* plan, const double* d_K, const double* d_b, double* d_x, double relTol, int32_t maxIter,
+                       int32_t* iters, double* relRes);
+/* One step of FEMpyProblem.solve (Problem.py:137-169) without the CSR values crossing PCIe: H2D of the nodal inputs,
+ * one fused K + R assembly with the BCs applied, update = K^-1 (-R) by femb_solve_pcg_dev on the device values, D2H of
+ * update (numDOF) and, when R != NULL, of the residual.  The caller adds update to its states. */
+int femb_assemble_solve(femb_plan* plan, const double* coords, const double* states, const double* thickness,
+                        const femb_material* mat, const int64_t* bcDof, const double* bcVal, int64_t nBC,
+                        const double* loads /* may be NULL */, double relTol, int32_t maxIter, double* update,
+                        double* R /* may be NULL */, int32_t* iters, double* relRes);
+
 /* ---- per-element blocks: Element.computeResidualJacobians / computeResiduals
  * (FEMpy/Elements/Element.py:370-486).  Ke: (E_b, n*s, n*s) per block, Re: (E_b, n, s) per block,
  * blocks concatenated.  Either output may be NULL. */

@@ -134,6 +134,82 @@ def test_lbracket_config1():
     assert relerr(prob._assembleResidual(prob.states), g["R_solved"]) < 1e-6 or np.abs(g["R_solved"]).max() < 1e-3
 
 
+# ---- device-resident linear solve: the hand-off after assembly ------------------------------------
+def test_lbracket_solve_on_device():
+    """config 1 solved without the CSR values leaving the GPU (femb_assemble_solve): the state equals the reference's
+    direct solve to the conditioning of the problem, and the converged state has no residual"""
+    g = golden("lbracket.npz")
+    E, nu, rho, t = g["material"]
+    from fempy_b200 import Constitutive
+
+    model = FEMpyModel(Constitutive.IsoPlaneStress(E, nu, rho, t), nodeCoords=g["coords"], connectivity={"quad": g["conn"].astype(np.int64)})
+    model.addFixedBCToNodes(name="Fixed", nodeInds=[int(i) for i in g["top"]], dof=[0, 1], value=0.0)
+    prob = model.addProblem("Vertical-Load")
+    prob.addLoadToNodes(name="RightEdgeLoad", nodeInds=[int(i) for i in g["right"]], dof=1, value=-1e5, totalLoad=True)
+    info = prob.solveOnDevice(relTol=1e-11)
+    assert 0 < info["iterations"] < 50000 and info["relativeResidual"] <= 1e-11
+    assert relerr(prob.Res, g["R"]) < TOL  # the residual the step started from
+    assert relerr(prob.states, g["u"]) < 1e-5
+    np.testing.assert_allclose(np.abs(prob.states).max(), 3.285941388626e-02, rtol=1e-5)
+    R1 = prob._assembleResidual(prob.states)
+    assert np.abs(R1).max() < 1e-6 * np.abs(g["R"]).max()
+
+
+@pytest.mark.parametrize("elType,n", [("quad", 40), ("triangle", 31), ("quad9", 12)])
+def test_pcg_matches_direct_solve(elType, n):
+    """femb_solve_pcg on the assembled values (BC rows kept, prescribed values != 0, duplicate BCs) against scipy's direct
+    solve.  The reference hands the row-only-BC matrix to the factorisation as it is; with prescribed values != 0 that
+    system is badly scaled (BC rows ~ 1, stiffness rows ~ 1e10) and SuperLU returns the constrained DOFs to ~1e-3 only
+    (tools/dbg_pcg.py), so the yardstick here is the direct solve of the equivalent reduced system
+    K_ff x_f = b_f - K_fc x_c with x_c = b_c / count."""
+    from scipy.sparse.linalg import spsolve
+
+    coords, conn, states, thick, loads, bcDOF, bcVal = _path_case(elType, n)
+    thick = thick * 100.0
+    plan = _raw_plan(elType, coords, conn)
+    K, R = plan.assemble(coords, states, thick, make_cm(0).material(), bcDOF, bcVal, True, 1e6 * loads)
+    indptr, indices = plan.pattern()
+    A = csr_array((K, indices, indptr), shape=(R.size, R.size))
+    free = np.setdiff1d(np.arange(R.size), bcDOF)
+    con = np.unique(bcDOF)
+    want = np.zeros(R.size)
+    want[con] = (-R / np.maximum(np.bincount(bcDOF, minlength=R.size), 1))[con]
+    want[free] = spsolve(A[free][:, free].tocsc(), (-R - A @ want)[free])
+    asIs = spsolve(A.tocsc(), -R)  # what the reference's host solve returns
+    assert relerr(asIs[free], want[free]) < 1e-3
+    x, iters, res = plan.solvePCG(K, -R, relTol=1e-12, maxIter=20000)
+    assert 0 < iters < 20000 and res <= 1e-12
+    trueRes = np.abs((A @ x + R)[free]).max() / np.abs(R).max()
+    assert trueRes <= 1e-9, trueRes
+    assert relerr(x, want) < 1e-7, (relerr(x, want), trueRes, iters)
+    # constrained DOFs: x_c = b_c / count exactly as the row equation count * x_c = b_c says
+    cnt = np.bincount(bcDOF, minlength=R.size)
+    np.testing.assert_allclose(x[np.unique(bcDOF)], (-R / np.maximum(cnt, 1))[np.unique(bcDOF)], rtol=1e-15)
+    plan.close()
+
+
+def test_pcg_without_bcs_and_bad_arguments():
+    """no BC set: plain PCG on K + shift (SPD); argument checks"""
+    coords, conn = meshes.quad4_grid(9, 7)
+    plan = _raw_plan("quad", coords, conn)
+    N = coords.shape[0]
+    K, _ = plan.assemble(coords, np.zeros((N, 2)), np.ones(conn["quad"].shape[0]), make_cm(0).material(), None, None, False, None)
+    indptr, indices = plan.pattern()
+    A = csr_array((K, indices, indptr), shape=(2 * N, 2 * N))
+    diagPos = np.flatnonzero(indices == np.repeat(np.arange(2 * N), np.diff(indptr)))
+    Ks = K.copy()
+    Ks[diagPos] += 1e9  # rigid-body modes out of the null space
+    b = np.random.default_rng(0).random(2 * N)
+    x, iters, res = plan.solvePCG(Ks, b, relTol=1e-12)
+    As = csr_array((Ks, indices, indptr), shape=A.shape)
+    assert relerr(As @ x, b) < 1e-10
+    from fempy_b200._lib import FembError
+
+    with pytest.raises(FembError):
+        plan.solvePCG(Ks, b, relTol=0.0)
+    plan.close()
+
+
 # ---- the reference's own known-answer vectors, through the CUDA path ------------------------------------------------
 def test_local_matrices_to_coo_reference_vector():
     """reference tests/testAssembleutils.py:55-81"""
