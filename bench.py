@@ -350,7 +350,19 @@ def run_ours_multi(args, rank, world, local_rank, dev):
     from fempy_b200 import Constitutive, Elements, meshes
     from fempy_b200.dist import DistributedAssembly, GpuLocalAssembler, Partition
 
-    dist.init_process_group("nccl", device_id=dev)
+    # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed on stdout at communicator
+    # creation when NCCL_DEBUG=VERSION) is sent to stderr by pointing fd 1 at fd 2 until the first collective is through
+    sys.stdout.flush()
+    savedStdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(savedStdout, 1)
+        os.close(savedStdout)
     strong = args.config == "c5"
     if strong:
         nx = ny = args.nx or 5000
