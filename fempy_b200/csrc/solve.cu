@@ -12,7 +12,7 @@
 //
 // Per iteration three launches, no host synchronisation (alpha, beta live in device scalars, double-buffered by iteration
 // parity); the host reads the residual norm every `CHECK` iterations.
-//   k_spmv   q = K p (8 lanes per node row: the two DOF rows of a node are one contiguous run),  pq = p.q
+//   k_spmv   q = K p (4 lanes per node row: the two DOF rows of a node are one contiguous run),  pq = p.q
 //   k_update alpha = rz/pq;  x += alpha p;  r -= alpha q;  z = r / diag;  rz' = r.z;  rr = r.r
 //   k_direct beta = rz'/rz;  p = z + beta p
 // HBM traffic per iteration: K values once (8 B/nnz) + node columns (1 B/nnz) + 9 vector passes.
@@ -22,7 +22,10 @@ using namespace femb;
 
 namespace {
 
-constexpr int LANES = 8;   // lanes that share a node row in the product
+#ifndef SPMV_LANES
+#define SPMV_LANES 4  // A/B at config 2 (deg 9): 1 lane 44.1, 2 lanes 39.7, 4 lanes 40.5, 8 lanes 48.5, 16 lanes 67.1 us per iteration
+#endif
+constexpr int LANES = SPMV_LANES;  // lanes that share a node row in the product
 constexpr int CHECK = 25;  // iterations between convergence checks
 
 struct Scal {  // device scalars, [parity]
