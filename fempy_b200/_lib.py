@@ -46,6 +46,7 @@ _SIGNATURES = {
     "femb_plan_pattern_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "femb_assemble": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.POINTER(Material), c_int64_p, c_double_p,
                                 C.c_int64, C.c_int32, c_double_p, C.c_int32, c_double_p, c_double_p]),
+    "femb_plan_set_geometry": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "femb_plan_set_bcs": (C.c_int, [C.c_void_p, c_int64_p, c_double_p, C.c_int64]),
     "femb_assemble_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Material), C.c_int32,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -460,19 +460,40 @@ static int stage(double** buf, const double* host, size_t n, cudaStream_t st) {
     return 0;
 }
 
+// Device-side model: node coordinates and per-element thickness are constants of a Newton or
+// optimisation loop (FEMpyModel.setCoordinates / setDesignVariables change them, Model.py:240-276); uploaded once here,
+// the host-pointer entries then take NULL for them and move only the states (and loads) per call.
+extern "C" int femb_plan_set_geometry(femb_plan* p, const double* coords, const double* thickness) {
+    TRY(need_final(p, "femb_plan_set_geometry"));
+    TRY(use_device(p));
+    if (coords) {
+        TRY(stage_geometry(p, coords, nullptr, false, "femb_plan_set_geometry"));
+        p->coordsResident = true;
+    } else {
+        p->coordsResident = false;
+    }
+    if (thickness) {
+        TRY(stage(&p->s_thick, thickness, (size_t)p->numElems, p->stream));
+        p->thickResident = true;
+    } else {
+        p->thickResident = false;
+    }
+    CUDA_TRY(cudaStreamSynchronize(p->stream));  // the caller's arrays may change after the call
+    return 0;
+}
+
 extern "C" int femb_assemble(femb_plan* p, const double* coords, const double* states, const double* thickness,
                              const femb_material* mat, const int64_t* bcDof, const double* bcVal, int64_t nBC,
                              int32_t applyBCs, const double* loads, int32_t want, double* Kdata, double* R) {
     TRY(need_final(p, "femb_assemble"));
-    if (!coords || !states || !thickness) return fail("femb_assemble: NULL input");
+    if (!states) return fail("femb_assemble: NULL input");
     const bool wk = (want & FEMB_WANT_K) != 0, wr = (want & FEMB_WANT_R) != 0;
     if ((wk && !Kdata) || (wr && !R)) return fail("femb_assemble: NULL output");
     TRY(use_device(p));
     const int64_t numDOF = femb_plan_num_dof(p), nnz = femb_plan_nnz(p);
     if (applyBCs) TRY(femb_plan_set_bcs(p, bcDof, bcVal, nBC));
-    TRY(stage(&p->s_coords, coords, (size_t)p->numNodes * 2, p->stream));
+    TRY(stage_geometry(p, coords, thickness, true, "femb_assemble"));
     TRY(stage(&p->s_states, states, (size_t)numDOF, p->stream));
-    TRY(stage(&p->s_thick, thickness, (size_t)p->numElems, p->stream));
     if (loads && wr) TRY(stage(&p->s_loads, loads, (size_t)numDOF, p->stream));
     if (wk) TRY(dalloc(&p->s_K, (size_t)nnz));
     if (wr) TRY(dalloc(&p->s_R, (size_t)numDOF));

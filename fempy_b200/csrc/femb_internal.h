@@ -130,6 +130,7 @@ struct femb_plan {
     double *s_coords = nullptr, *s_states = nullptr, *s_thick = nullptr, *s_loads = nullptr, *s_K = nullptr,
            *s_R = nullptr, *s_out = nullptr;
     size_t s_outCap = 0;
+    bool coordsResident = false, thickResident = false;  // femb_plan_set_geometry: s_coords / s_thick hold the model's arrays
     void* s_solve = nullptr;  // work vectors + scalars of femb_solve_pcg_dev (solve.cu)
     int* d_flag = nullptr;
     // optional CUDA-event timing of the dominant assembly kernel(s) (bench.py roofline leg)
@@ -154,6 +155,27 @@ static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + b
 
 static inline int use_device(const femb_plan* p) {
     CUDA_TRY(cudaSetDevice(p->device));
+    return 0;
+}
+
+// host-pointer entries: upload coords / thickness, or -- pointer NULL -- use the copy femb_plan_set_geometry left on the
+// device.  An explicit pointer overwrites the scratch, so the resident promise ends there.
+static inline int stage_geometry(femb_plan* p, const double* coords, const double* thickness, bool needThickness, const char* who) {
+    if (coords) {
+        if (!p->s_coords) CUDA_TRY(cudaMalloc((void**)&p->s_coords, std::max<size_t>((size_t)p->numNodes * 2, 1) * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(p->s_coords, coords, (size_t)p->numNodes * 2 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        p->coordsResident = false;
+    } else if (!p->coordsResident) {
+        return fail("%s: coords is NULL and no resident copy exists (femb_plan_set_geometry)", who);
+    }
+    if (!needThickness) return 0;
+    if (thickness) {
+        if (!p->s_thick) CUDA_TRY(cudaMalloc((void**)&p->s_thick, std::max<size_t>((size_t)p->numElems, 1) * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(p->s_thick, thickness, (size_t)p->numElems * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        p->thickResident = false;
+    } else if (!p->thickResident) {
+        return fail("%s: thickness is NULL and no resident copy exists (femb_plan_set_geometry)", who);
+    }
     return 0;
 }
 

@@ -148,11 +148,11 @@ extern "C" int femb_function_dev(femb_plan* p, const double* d_coords, const dou
 extern "C" int femb_function(femb_plan* p, const double* coords, const double* states, const femb_material* mat,
                              int32_t func, int32_t reduction, double* out) {
     TRY(need_final(p, "femb_function"));
-    if (!coords || !states || !out) return fail("femb_function: NULL argument");
+    if (!states || !out) return fail("femb_function: NULL argument");
     TRY(use_device(p));
     const int64_t numDOF = femb_plan_num_dof(p);
     const size_t nout = (size_t)(reduction == FEMB_REDUCE_NONE ? p->numPoints : p->numElems);
-    TRY(stage(&p->s_coords, coords, (size_t)p->numNodes * 2, p->stream));
+    TRY(stage_geometry(p, coords, nullptr, false, "femb_function"));
     TRY(stage(&p->s_states, states, (size_t)numDOF, p->stream));
     if (p->s_outCap < nout) {
         dfree(p->s_out);

@@ -265,13 +265,12 @@ extern "C" int femb_assemble_solve(femb_plan* p, const double* coords, const dou
                                    const double* loads, double relTol, int32_t maxIter, double* update, double* R,
                                    int32_t* itersOut, double* relResOut) {
     TRY(need_final(p, "femb_assemble_solve"));
-    if (!coords || !states || !thickness || !mat || !update) return fail("femb_assemble_solve: NULL argument");
+    if (!states || !mat || !update) return fail("femb_assemble_solve: NULL argument");
     TRY(use_device(p));
     const size_t numDOF = (size_t)femb_plan_num_dof(p), nnz = (size_t)femb_plan_nnz(p);
     TRY(femb_plan_set_bcs(p, bcDof, bcVal, nBC));
-    TRY(stage_in(&p->s_coords, coords, (size_t)p->numNodes * 2, p->stream));
+    TRY(stage_geometry(p, coords, thickness, true, "femb_assemble_solve"));
     TRY(stage_in(&p->s_states, states, numDOF, p->stream));
-    TRY(stage_in(&p->s_thick, thickness, (size_t)p->numElems, p->stream));
     if (loads) TRY(stage_in(&p->s_loads, loads, numDOF, p->stream));
     else TRY(dalloc(&p->s_loads, numDOF));
     TRY(dalloc(&p->s_K, nnz));

@@ -20,6 +20,7 @@ class FEMpyModel:
                 raise KeyError(f"Option {key} is not a valid FEMpyModel option")
             self.options[key] = value
         self.constitutiveModel = constitutiveModel
+        self._b200_geomVersion = 0  # counts setCoordinates / setDesignVariables calls: the device copy follows it
         if meshFileName is not None:
             raise NotImplementedError("mesh file input needs meshio, which is outside the B200 hot path; pass nodeCoords and connectivity")
         if nodeCoords is None or connectivity is None:
@@ -99,6 +100,7 @@ class FEMpyModel:
             raise ValueError(
                 f"Invalid number of coordinate dimensions, problem is {self.numDim}D but {size}D coordinates were supplied"
             )
+        self._b200_geomVersion += 1  # the device copy of the coordinates is stale (problem.py: _b200Inputs)
         for prob in self.problems:
             prob.markResOutOfDate()
             prob.markJacOutOfDate()
@@ -111,6 +113,7 @@ class FEMpyModel:
                 raise ValueError(
                     f"Invalid shape for design variable '{dvName}', expected {self.dvs[dvName].shape} but got {dvs[dvName].shape}"
                 )
+        self._b200_geomVersion += 1
         for prob in self.problems:
             prob.markResOutOfDate()
             prob.markJacOutOfDate()

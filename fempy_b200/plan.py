@@ -117,12 +117,26 @@ class AssemblyPlan:
             self._pattern = (indptr, indices)
         return self._pattern
 
+    # -- device-side model -------------------------------------------------------------------------
+    def setGeometry(self, coords, thickness):
+        """Keep node coordinates / per-element thickness on the device (femb_plan_set_geometry): the host-pointer calls
+        below then take None for them and upload only the states (and loads).  None drops the resident copy."""
+        c = as_f64(coords) if coords is not None else None
+        t = as_f64(thickness) if thickness is not None else None
+        if (c is not None and c.shape != (self.numNodes, self.numDim)) or (t is not None and t.shape != (self.numElements,)):
+            raise ValueError("coords/thickness have the wrong shape for this plan")
+        check(self._lib.femb_plan_set_geometry(self._h, dptr(c) if c is not None else None, dptr(t) if t is not None else None))
+
     # -- host-pointer compute calls -----------------------------------------------------------------
     def assemble(self, coords, states, thickness, material, bcDOF=None, bcValues=None, applyBCs=True, loads=None,
                  wantK=True, wantR=True, Kout=None, Rout=None):
-        """Kout / Rout: optional preallocated float64 outputs (e.g. pinned host memory)."""
-        coords, states, thickness = as_f64(coords), as_f64(states), as_f64(thickness)
-        if coords.shape != (self.numNodes, self.numDim) or states.size != self.numDOF or thickness.shape != (self.numElements,):
+        """Kout / Rout: optional preallocated float64 outputs (e.g. pinned host memory).  coords / thickness None: use
+        the resident copies (setGeometry)."""
+        coords = as_f64(coords) if coords is not None else None
+        thickness = as_f64(thickness) if thickness is not None else None
+        states = as_f64(states)
+        if ((coords is not None and coords.shape != (self.numNodes, self.numDim)) or states.size != self.numDOF
+                or (thickness is not None and thickness.shape != (self.numElements,))):
             raise ValueError("coords/states/thickness have the wrong shape for this plan")
         nBC = 0
         bcd = bcv = None
@@ -144,7 +158,8 @@ class AssemblyPlan:
         want = (WANT_K if wantK else 0) | (WANT_R if wantR else 0)
         check(
             self._lib.femb_assemble(
-                self._h, dptr(coords), dptr(states), dptr(thickness), C.byref(material),
+                self._h, dptr(coords) if coords is not None else None, dptr(states),
+                dptr(thickness) if thickness is not None else None, C.byref(material),
                 iptr(bcd) if nBC else None, dptr(bcv) if nBC else None, nBC, int(bool(applyBCs)),
                 dptr(lv) if lv is not None else None, want,
                 dptr(K) if wantK else None, dptr(R) if wantR else None,
@@ -157,9 +172,10 @@ class AssemblyPlan:
             key = reduction.lower() if isinstance(reduction, str) else None
             assert key in REDUCTIONS, "elementReductionType not valid"
             reduction = REDUCTIONS[key]
-        coords, states = as_f64(coords), as_f64(states)
+        coords, states = (as_f64(coords) if coords is not None else None), as_f64(states)
         out = np.empty(self.numPoints if reduction == 0 else self.numElements)
-        check(self._lib.femb_function(self._h, dptr(coords), dptr(states), C.byref(material), int(funcId), int(reduction), dptr(out)))
+        check(self._lib.femb_function(self._h, dptr(coords) if coords is not None else None, dptr(states), C.byref(material),
+                                      int(funcId), int(reduction), dptr(out)))
         return out
 
     def elementBlocks(self, coords, states, thickness, material, wantK=True, wantR=True):
@@ -204,13 +220,14 @@ class AssemblyPlan:
     def assembleSolve(self, coords, states, thickness, material, bcDOF, bcValues, loads=None, relTol=1e-10, maxIter=20000):
         """One fused assembly (BCs applied) + update = K^-1 (-R) on the GPU (femb_assemble_solve); the CSR values stay on
         the device.  Returns (update, R, iterations, relative residual)."""
-        c, q, t = as_f64(coords), as_f64(states), as_f64(thickness)
+        c, q, t = (as_f64(coords) if coords is not None else None), as_f64(states), (as_f64(thickness) if thickness is not None else None)
         bcd, bcv = as_i64(bcDOF if bcDOF is not None else []), as_f64(bcValues if bcValues is not None else [])
         ld = as_f64(loads) if loads is not None else None
         update, R = np.empty(self.numDOF), np.empty(self.numDOF)
         it, res = C.c_int32(0), C.c_double(0.0)
         check(self._lib.femb_assemble_solve(
-            self._h, dptr(c), dptr(q), dptr(t), C.byref(material), iptr(bcd) if bcd.size else None, dptr(bcv) if bcd.size else None,
+            self._h, dptr(c) if c is not None else None, dptr(q), dptr(t) if t is not None else None, C.byref(material),
+            iptr(bcd) if bcd.size else None, dptr(bcv) if bcd.size else None,
             bcd.size, dptr(ld) if ld is not None else None, float(relTol), int(maxIter), dptr(update), dptr(R), C.byref(it), C.byref(res)))  # fmt: skip
         return update, R, it.value, res.value
 

@@ -60,9 +60,19 @@ class B200AssemblyMixin:
     """The CUDA assembly path behind FEMpyProblem's private assembly drivers."""
 
     def _b200Inputs(self, states):
+        """Plan + inputs of one call.  A model that counts its geometry changes (`_b200_geomVersion`, bumped by this
+        package's FEMpyModel.setCoordinates / setDesignVariables) keeps node coordinates and thickness on the device:
+        they are uploaded when the count moves and the calls pass None (device-side model, femb_plan_set_geometry).
+        The reference's own FEMpyModel has no such counter: its arrays are uploaded on every call."""
         plan = planFor(self.model)
         coords = np.ascontiguousarray(self.model.nodeCoords, dtype=np.float64)
         thickness = np.ascontiguousarray(self.model.dvs["Thickness"], dtype=np.float64)
+        version = getattr(self.model, "_b200_geomVersion", None)
+        if version is not None:
+            if getattr(plan, "_geomVersion", None) != version:
+                plan.setGeometry(coords, thickness)
+                plan._geomVersion = version
+            coords = thickness = None
         return plan, coords, np.ascontiguousarray(states, dtype=np.float64), thickness, materialFor(self.constitutiveModel)
 
     def _assembleMatrix(self, states, applyBCs=True):

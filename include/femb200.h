@@ -120,6 +120,14 @@ int64_t femb_plan_last_launches(const femb_plan* plan); /* kernels launched by t
 int femb_plan_pattern(femb_plan* plan, int64_t* indptr, int64_t* indices);
 int femb_plan_pattern_dev(femb_plan* plan, int64_t* d_indptr, int64_t* d_indices);
 
+/* ---- device-side model.  Node coordinates and per-element thickness are constants of a Newton or
+ * optimisation loop (the reference changes them through FEMpyModel.setCoordinates / setDesignVariables, Model.py:240-276
+ * and gathers them again per element on every assembly, Model.py:288-329).  After this call femb_assemble,
+ * femb_function and femb_assemble_solve accept NULL for coords / thickness and use the resident copies: only states
+ * (and loads) cross PCIe per call.  Passing NULL here, or an explicit pointer to one of those entries later, ends the
+ * residency of that array.  The arrays are copied before the call returns. */
+int femb_plan_set_geometry(femb_plan* plan, const double* coords /* N*2 or NULL */, const double* thickness /* E or NULL */);
+
 /* ---- K + R assembly: FEMpyProblem._assembleMatrix + _assembleResidual (FEMpy/Problem.py:565-661)
  * coords (numNodes, numDim), states (numNodes, numStates), thickness (numElems) ["Thickness" DV],
  * bcDof/bcVal (nBC) = AssemblyUtils.convertBCDictToLists output (duplicates allowed, reference

@@ -134,6 +134,52 @@ def test_lbracket_config1():
     assert relerr(prob._assembleResidual(prob.states), g["R_solved"]) < 1e-6 or np.abs(g["R_solved"]).max() < 1e-3
 
 
+# ---- device-side model: coordinates / thickness resident between calls ---------------------------------
+def test_resident_geometry_matches_explicit_inputs():
+    """femb_plan_set_geometry: NULL coords / thickness use the resident copies, bit-identical to explicit inputs; an explicit
+    pointer ends the residency; NULL without a resident copy is an error"""
+    from fempy_b200._lib import FembError
+
+    coords, conn, states, thick, loads, bcDOF, bcVal = _path_case("quad", 33)
+    plan = _raw_plan("quad", coords, conn)
+    mat = make_cm(0).material()
+    K0, R0 = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
+    with pytest.raises(FembError, match="resident"):
+        plan.assemble(None, states, None, mat, bcDOF, bcVal, True, loads)
+    plan.setGeometry(coords, thick)
+    K1, R1 = plan.assemble(None, states, None, mat, bcDOF, bcVal, True, loads)
+    np.testing.assert_array_equal(K1, K0)
+    np.testing.assert_array_equal(R1, R0)
+    vm0 = plan.function(coords, states, mat, 1, "mean")  # explicit coords: that array is no longer resident
+    with pytest.raises(FembError, match="resident"):
+        plan.function(None, states, mat, 1, "mean")
+    plan.setGeometry(coords, None)
+    np.testing.assert_array_equal(plan.function(None, states, mat, 1, "mean"), vm0)
+    with pytest.raises(FembError, match="resident"):
+        plan.assemble(None, states, None, mat, bcDOF, bcVal, True, loads)  # thickness was dropped
+    plan.close()
+
+
+def test_model_geometry_changes_reach_the_device():
+    """FEMpyModel.setCoordinates / setDesignVariables invalidate the resident copies (version counter)"""
+    coords, conn = meshes.quad4_grid(14, 9)
+    m, p = build_problem(coords, conn, 0, states=1e-3 * np.random.default_rng(1).random(coords.shape))
+    blocks = oracle_blocks(conn)
+
+    def oracle_K():
+        Ko = fo.assemble_matrix(blocks, m.nodeCoords, p.states, m.dvs["Thickness"], 0, MAT["E"], MAT["nu"], None, dropZeros=False)
+        Ko.sort_indices()
+        return Ko.data
+
+    assert relerr(p._assembleMatrix(p.states, applyBCs=False).data, oracle_K()) < TOL
+    m.setCoordinates(m.nodeCoords * np.array([1.5, 0.75]))
+    assert relerr(p._assembleMatrix(p.states, applyBCs=False).data, oracle_K()) < TOL
+    m.setDesignVariables({"Thickness": np.random.default_rng(2).random(m.dvs["Thickness"].shape) + 0.5})
+    assert relerr(p._assembleMatrix(p.states, applyBCs=False).data, oracle_K()) < TOL
+    assert relerr(p.computeFunction("Von-Mises-Stress", "mean")["quad"],
+                  fo.compute_function(blocks, m.nodeCoords, p.states, fo.VON_MISES, "mean", 0, MAT["E"], MAT["nu"], MAT["rho"])[0]) < TOL
+
+
 # ---- device-resident linear solve (SURVEY 8f row 1): the hand-off after assembly ------------------------------------
 def test_lbracket_solve_on_device():
     """config 1 solved without the CSR values leaving the GPU (femb_assemble_solve): the state equals the reference's
