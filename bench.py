@@ -161,9 +161,13 @@ def run_reference(args, rank, world):
                       "iso plane stress, element-partitioned (weak scaling)")
     port = CpuPort(wl, args.cpu_procs)
     rows = max(1, 32768 // wl["n"])
-    port.run(max(1, rows // 4))
-    for _ in range(max(0, args.warmup - 1)):
+    port.run(max(1, rows // 4))  # starts the workers, warms numpy
+    for _ in range(max(0, min(args.warmup, 3) - 1)):
         port.run(max(1, rows // 4))
+    # bounded run: the timed steps together take about two minutes at most (the strips shrink for large --steps)
+    _, dt = port.run(rows)
+    if dt * args.steps > 120.0:
+        rows = max(2, int(rows * 120.0 / (dt * args.steps)))
     total_el, total_t = 0, 0.0
     for _ in range(args.steps):
         numEl, dt = port.run(rows)
