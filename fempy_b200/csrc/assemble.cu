@@ -345,6 +345,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.accumulate = k > 0;
             A.finalise = k + 1 == p->blocks.size();
             A.corners = b.d_corners;
+            A.cornerElem = b.d_cornerElem;
             A.zero = 0;
             A.stats = p->d_pipeStats;
             A.connE = b.d_connE;

@@ -38,7 +38,8 @@ struct Args {
     int elemOffset;          // first global element id of the block (thickness is indexed by global element id)
     int accumulate;          // 1: K and R already hold the contributions of earlier element blocks
     int finalise;            // 1: last block -- apply loads and boundary conditions
-    const void* corners;     // corner records (plan.cu: k_corners): int2 for NN <= 4, int4 for NN <= 12
+    const void* corners;     // corner records (plan.cu: k_corners)
+    const int* cornerElem;   // rotated 4-node records: element id of each corner
     const int4* connE;       // element-major connectivity, ceil(NN/4) words per element
     const double2* coords;
     const double2* states;
@@ -62,7 +63,10 @@ __device__ __forceinline__ void st_stream(double2* p, const double2 v) {  // K i
 // 12 for 6 nodes, 8 for 9/10 nodes (the node-row strip alone is 4*NN doubles)
 template <int NN, bool NL>
 __host__ __device__ constexpr int resident_threads() {
-    return NN <= 4 ? (NL ? 512 : 640) : (NN <= 6 ? 384 : 256);
+#ifndef ROWS_T3_THREADS
+#define ROWS_T3_THREADS 640
+#endif
+    return NN == 3 && !NL ? ROWS_T3_THREADS : NN <= 4 ? (NL ? 512 : 640) : (NN <= 6 ? 384 : 256);
 }
 
 // MB: the plan has several element blocks (one launch per block: later blocks add to what earlier ones left in K and R,
@@ -158,7 +162,18 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     // Wide families (6-10 nodes) run at 8-12 warps per SM with registers to spare: the next corner's record and
     // connectivity words are fetched one iteration ahead, which takes two of the three dependent loads
     // (record -> connectivity -> coordinates) off the critical path.
-    constexpr bool AHEAD = (NN > 4 && (ROWS_VAR & 1)) || (NN == 3 && (ROWS_VAR & 2));
+    constexpr bool AHEAD = NN > 4 && (ROWS_VAR & 1);
+    // 3-node triangles: the corner record holds the element rotated so that the owner is local node 0 and names the other
+    // two nodes (plan.cu: k_corners) -- no connectivity load, the owner's coordinates / state are read once per thread
+    constexpr bool ROT = NN == 3;
+    // 4-node quads, same idea ({slots, the three other nodes} + element id aside); the owner's coordinates / state are
+    // re-read per corner (one coalesced request per warp) because the 96-register budget has no room to keep them
+    constexpr bool ROT4 = NN == 4 && FEMB_ROT4;
+    double2 ownX = make_double2(0.0, 0.0), ownU = make_double2(0.0, 0.0);
+    if (ROT && valid) {
+        ownX = __ldg(A.coords + i);
+        ownU = __ldg(A.states + i);
+    }
     auto load_rec = [&](int c) -> int4 {
         if constexpr (NN <= 4) {
             const int2 r = __ldg(reinterpret_cast<const int2*>(A.corners) + c);
@@ -177,7 +192,25 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     for (int c = c0; c < c1; ++c) {
         int e, a, node[4 * CW];
         unsigned kw[CW];  // slot positions: 7-bit fields from bit 4 (NN <= 4) or bytes
-        if constexpr (NN <= 4) {
+        if constexpr (ROT) {
+            const int4 rec = __ldg(reinterpret_cast<const int4*>(A.corners) + c);
+            e = rec.x;
+            kw[0] = (unsigned)rec.y;
+            a = 0;
+            node[0] = (int)i;
+            node[1] = rec.z;
+            node[2] = rec.w;
+            node[3] = -1;
+        } else if constexpr (ROT4) {
+            const int4 rec = __ldg(reinterpret_cast<const int4*>(A.corners) + c);
+            e = __ldg(A.cornerElem + c);
+            kw[0] = (unsigned)rec.x << 4;  // same field positions as the unrotated record (a = 0 in the low bits)
+            a = 0;
+            node[0] = (int)i;
+            node[1] = rec.y;
+            node[2] = rec.z;
+            node[3] = rec.w;
+        } else if constexpr (NN <= 4) {
             const int2 rec = AHEAD ? make_int2(recAhead.x, recAhead.y)
                              : (KNOCK & 4) ? make_int2(c & 0xffff, ((c - c0) & 3) | (1 << 11) | (2 << 18) | (3 << 25))
                                            : __ldg(reinterpret_cast<const int2*>(A.corners) + c);
@@ -193,7 +226,7 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
             if (CW > 2) kw[CW - 1] = (unsigned)rec.w;
         }
 #pragma unroll
-        for (int w = 0; w < CW; ++w) {
+        for (int w = 0; w < ((ROT || ROT4) ? 0 : CW); ++w) {
             const int4 cn = AHEAD ? connAhead[w] : (KNOCK & 4) ? make_int4((int)i, (int)i + 1, (int)i + 2, (int)i + 3) : __ldg(A.connE + (long long)e * CW + w);
             node[4 * w] = cn.x;
             node[4 * w + 1] = cn.y;
@@ -208,12 +241,13 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
         double x[NN], y[NN], ux[NN], uy[NN];
 #pragma unroll
         for (int b = 0; b < NN; ++b) {
-            const double2 X = (KNOCK & 2) ? make_double2(0.01 * (node[b] & 511) + ((b == 1 || b == 2) ? 0.01 : 0.0), 1e-5 * node[b] + (b >= 2 ? 0.01 : 0.0))
-                                          : __ldg(A.coords + node[b]);
+            const double2 X = (ROT && b == 0) ? ownX
+                              : (KNOCK & 2) ? make_double2(0.01 * (node[b] & 511) + ((b == 1 || b == 2) ? 0.01 : 0.0), 1e-5 * node[b] + (b >= 2 ? 0.01 : 0.0))
+                                            : __ldg(A.coords + node[b]);
             x[b] = X.x;
             y[b] = X.y;
             if (NL) {
-                const double2 U = __ldg(A.states + node[b]);
+                const double2 U = (ROT && b == 0) ? ownU : __ldg(A.states + node[b]);
                 ux[b] = U.x;
                 uy[b] = U.y;
             } else {  // linear model: the states are fetched after the strip (short live range)
@@ -329,7 +363,7 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
                 Kr[b][2] = fma(d01, s10, d22 * s01);
                 Kr[b][3] = fma(d11, s11, d22 * s00);
                 if (WR) {  // R_a = sum_b K_ab q_b
-                    const double2 q = (KNOCK & 2) ? make_double2(1e-3, 1e-4 * node[b]) : __ldg(A.states + node[b]);
+                    const double2 q = (ROT && b == 0) ? ownU : (KNOCK & 2) ? make_double2(1e-3, 1e-4 * node[b]) : __ldg(A.states + node[b]);
                     ra0 = fma(Kr[b][0], q.x, fma(Kr[b][1], q.y, ra0));
                     ra1 = fma(Kr[b][2], q.x, fma(Kr[b][3], q.y, ra1));
                 }

@@ -18,6 +18,9 @@
 // ---------------------------------------------------------------------------------------------
 // error handling
 // ---------------------------------------------------------------------------------------------
+#ifndef FEMB_ROT4
+#define FEMB_ROT4 1  // 4-node quads: corner records hold the element rotated to the owner (plan.cu: k_corners); 0: {e, a | slots} + connectivity load
+#endif
 int femb_fail(const char* fmt, ...);
 #define fail femb_fail
 
@@ -66,7 +69,8 @@ struct BlockData {
     int* d_conn = nullptr;  // node-major int32: conn[a * E + e]
     int* d_slot = nullptr;  // [(a*nn + b) * E + e] -> position of (node_a, node_b) in the node-level CSR
     int4* d_connE = nullptr;   // element-major connectivity, ceil(nn/4) words per element (row-owner kernel)
-    void* d_corners = nullptr; // corner records of this block, indexed by the global corner number: int2 (nn <= 4) or int4
+    void* d_corners = nullptr; // corner records of this block, indexed by the global corner number (plan.cu: k_corners)
+    int* d_cornerElem = nullptr;  // rotated 4-node records: element id of each corner
     PatchProgram prog;
 };
 
