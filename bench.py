@@ -292,7 +292,7 @@ def run_ours(args, rank, world, local_rank):
     kernel_ms = kernel_ms_sum / max(kernel_calls, 1)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (ncu_traffic({"c2": "k_assemble_rows", "c3": "k_assemble_rows_config3"}.get(args.config, ""))
+                "traffic": (ncu_traffic({"c2": "k_assemble_rows", "c3": "k_assemble_rows_config3", "c4": "k_assemble_rows_config4"}.get(args.config, ""))
                             if (args.path == "rows" and args.nx is None) else None),
                 "kernel": {"rows": "k_assemble_rows (one thread per node row, redundant element geometry, private swizzled smem row, coalesced warp write-out; BCs and loads fused)",
                            "patch": "k_assemble_pipe (persistent self-prefetching warp teams over node patches)",
