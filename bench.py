@@ -30,12 +30,14 @@ WORKLOADS = {  # name -> (element type, nx = ny, description)
 METRIC = "elements/s assembled (CSR K + residual)"
 
 
-def make_workload(name, nx=None):
+def make_workload(name, nx=None, ny=None):
     from fempy_b200 import meshes
 
     elType, n, desc = WORKLOADS[name]
     n = nx or n
-    coords, conn = meshes.GENERATORS[elType](n, n)
+    coords, conn = meshes.GENERATORS[elType](n, ny or n)
+    if nx or ny:
+        desc += f" [mesh overridden: {n} x {ny or n} cells]"
     N = coords.shape[0]
     numEl = conn[elType].shape[0]
     rng = np.random.default_rng(0)
@@ -134,7 +136,34 @@ class CpuPort:
         self.pool.close()
 
 
-def cpu_baseline(wl, budget_s=12.0):
+def reference_installed():
+    """oracle/_ref holds the pip-installed, unmodified reference (oracle/make_ref.sh)."""
+    return os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "FEMpy", "Problem.py")) or os.path.isdir("/root/reference/FEMpy")
+
+
+# element rows of the workload mesh the reference assembles per timed pass: config 2 runs whole; the larger configs
+# are sampled by a strip of full-width element rows so that a pass stays at a few seconds of CPU work (the reference's
+# Python gathers and (EP, n, 2, n, 2) temporaries grow with E: config 3 whole needs 5.8 GB and 40 s, config 5 51 GB)
+REF_SAMPLE_ROWS = {"c2": None, "c3": 80, "c4": 130, "c5": 52}
+
+
+def run_ref_timing(config, reps, nx=None, ny=None, threads=None, breakdown=False, vm=False, timeout=900):
+    """oracle/ref_timing.py in its own process (its Numba thread pool and caches stay out of this one)."""
+    import subprocess
+
+    cmd = [sys.executable, "-m", "oracle.ref_timing", "--config", config, "--reps", str(reps)]
+    for flag, val in (("--nx", nx), ("--ny", ny), ("--threads", threads)):
+        if val:
+            cmd += [flag, str(val)]
+    cmd += (["--breakdown"] if breakdown else []) + (["--vm"] if vm else [])
+    res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    if res.returncode != 0:
+        raise RuntimeError("oracle.ref_timing failed:\n" + res.stderr[-2000:])
+    return json.loads(res.stdout.strip().splitlines()[-1])
+
+
+def port_baseline(wl, budget_s=6.0):
+    """The numpy port of the reference's stages on all host cores (a second, stronger CPU number)."""
     port = CpuPort(wl)
     rows = max(1, wl["n"] // 16)
     port.run(max(1, rows // 4))  # start the workers, warm numpy
@@ -147,15 +176,89 @@ def cpu_baseline(wl, budget_s=12.0):
                       f"its own strip of {rows} of the workload's {wl['n']} element rows ({numEl} elements in {dt:.2f} s wall)"}
 
 
+def cpu_baseline(wl, config, nx=None):
+    """The reference's own Numba path (FEMpyProblem._assembleMatrix + _assembleResidual, FEMpy/Problem.py:565-661) on
+    the host cores: protocol of Examples/Benchmarks/benchmarkQuadMeshScaling.py:56-102 (one pass to compile, then the
+    best of 3), all Numba threads, plus one single-thread pass and the stage breakdown; the numpy port beside it."""
+    port = port_baseline(wl)
+    if not reference_installed():
+        port["note"] = "oracle/_ref absent (oracle/make_ref.sh needs /root/reference): numpy port only"
+        return port
+    ny = None if nx else REF_SAMPLE_ROWS.get(config)
+    full = run_ref_timing(config, 3, nx=nx, ny=ny, breakdown=True)
+    one = run_ref_timing(config, 1, nx=nx, ny=ny, threads=1)
+    what = "whole workload mesh" if ny is None else f"strip of {ny} of the workload's {wl['n']} element rows"
+    return {"value": full["elements"] / full["min_s"], "unit": "elements/s", "cores": full["numba_threads"], "kind": "reference",
+            "sample": f"unmodified FEMpy 1.0.1 from oracle/_ref: _assembleMatrix + _assembleResidual (applyBCs) on the {what} "
+                      f"({full['elements']} elements), one compile pass then best of 3 ({full['min_s']:.2f} s), numba "
+                      f"{full['numba_threads']} threads ({full['threading_layer']}) on {full['cores']} host cores",
+            "times_s": full["times_s"], "threading_layer": full["threading_layer"], "host_cores": full["cores"],
+            "stage_breakdown_s": full.get("breakdown_s"), "first_pass_with_jit_s": full["first_pass_s"],
+            "one_thread": {"value": one["elements"] / one["min_s"], "seconds": one["min_s"]},
+            "residual_checksum": full["residual_checksum"], "K_abs_checksum": full["K_checksum"], "sampled_rows": ny,
+            "port": port}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU port of the reference's algorithm on all host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only): the
+    unmodified FEMpy from oracle/_ref, every step one _assembleMatrix + _assembleResidual pass (FEMpy/Problem.py:565-661)
+    with all Numba threads.  Config 2 is assembled whole every step; the larger workloads (and the N-GPU weak-scaling
+    mesh, whose per-GPU share is config 2) by a bounded strip of full-width element rows, the metric being a rate.
+    Without oracle/_ref the numpy port runs instead (kind "port")."""
     if rank != 0:
         return
-    # same workload as the GPU arm at this N: config 2 at N = 1, its per-GPU share times N (a 512 x 512N strip) for N > 1,
-    # or the fixed config-5 mesh with --config c5.  The metric is a rate and every step assembles a bounded sample
-    # (about 32k elements per worker process = strips of the mesh's first 512-wide rows).
     strong = args.gpus > 1 and args.config == "c5"
-    wl = make_workload("c5" if strong else (args.config if args.gpus == 1 else "c2"), args.nx)
+    config = "c5" if strong else (args.config if args.gpus == 1 else "c2")
+    if not reference_installed():
+        return run_reference_port(args, config)
+    import contextlib
+    import io
+
+    sys.path.insert(0, ROOT)
+    os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(ROOT, "oracle", "_ref", ".numba_cache"))
+    from oracle import ref_timing
+
+    ny = None if args.nx else REF_SAMPLE_ROWS.get(config)
+    wl = make_workload(config, args.nx, ny)
+    desc = WORKLOADS[config][2] + (f" [mesh overridden: {args.nx} x {args.nx} cells]" if args.nx else "")
+    if args.gpus > 1 and not strong:
+        desc = (f"config2 per GPU: structured Q4 {wl['n']}x{wl['n'] * args.gpus} = {args.gpus} x ({wl['n']}x{wl['n']}), "
+                "iso plane stress, element-partitioned (weak scaling)")
+    with contextlib.redirect_stdout(io.StringIO()):
+        fp, model, prob = ref_timing.build_reference_problem(wl, MAT)
+        ref_timing.one_pass(prob)  # every Numba kernel is compiled here
+        for _ in range(max(0, min(args.warmup, 3) - 1)):
+            ref_timing.one_pass(prob)
+    import numba
+
+    times = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            K, R, _ = ref_timing.one_pass(prob)
+            times.append(time.perf_counter() - t0)
+    numEl = wl["numElems"]
+    value = numEl * len(times) / sum(times)
+    sample = (f"unmodified FEMpy 1.0.1 (oracle/_ref): _assembleMatrix + _assembleResidual, applyBCs, "
+              + ("whole workload mesh" if ny is None else f"strip of {ny} full-width element rows of the workload mesh")
+              + f" = {numEl} elements per step, numba {numba.get_num_threads()} threads ({numba.threading_layer()})")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "elements_per_step": int(numEl), "sampled_rows": ny, "nnz_per_step": int(K.nnz)},
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": int(numba.get_num_threads()), "kind": "reference", "sample": sample,
+                         "threading_layer": numba.threading_layer(), "host_cores": host_cores(), "best_step_s": min(times)},
+        "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "residual_checksum": float(R.sum()),
+    }  # fmt: skip
+    print(json.dumps(line))
+
+
+def run_reference_port(args, config):
+    """Fallback of --impl reference when oracle/_ref is absent: the numpy port on all host cores."""
+    strong = args.gpus > 1 and args.config == "c5"
+    wl = make_workload(config, args.nx)
     if args.gpus > 1 and not strong:
         wl["desc"] = (f"config2 per GPU: structured Q4 {wl['n']}x{wl['n'] * args.gpus} = {args.gpus} x ({wl['n']}x{wl['n']}), "
                       "iso plane stress, element-partitioned (weak scaling)")
@@ -218,15 +321,11 @@ def run_ours(args, rank, world, local_rank):
     plan = AssemblyPlan(wl["numNodes"], 2, 2, device=local_rank)
     N_, dN, w = el.tables()
     t0 = time.perf_counter()
-    plan.setLocalityHint(wl["coords"])
-    plan.setOption("assembly_path", {"scatter": 0, "patch": 1, "rows": 2}[args.path])
-    plan.setOption("team_warps", args.team_warps)
+    plan.setOption("assembly_path", {"scatter": 0, "rows": 2}[args.path])
     if args.balance_rows is not None:
         plan.setOption("balance_rows", args.balance_rows)
-    if args.debug_flags:
-        plan.setOption("debug_flags", args.debug_flags)
-    if args.patch_nodes:
-        plan.setOption("patch_nodes", args.patch_nodes)
+    if args.no_fan:
+        plan.setOption("fan_rows", 0)
     plan.addBlock(N_, dN, w, wl["conn"][elType])
     plan.finalize()
     plan_wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -295,7 +394,6 @@ def run_ours(args, rank, world, local_rank):
                 "traffic": (ncu_traffic({"c2": "k_assemble_rows", "c3": "k_assemble_rows_config3", "c4": "k_assemble_rows_config4"}.get(args.config, ""))
                             if (args.path == "rows" and args.nx is None) else None),
                 "kernel": {"rows": "k_assemble_rows (one thread per node row, redundant element geometry, private swizzled smem row, coalesced warp write-out; BCs and loads fused)",
-                           "patch": "k_assemble_pipe (persistent self-prefetching warp teams over node patches)",
                            "scatter": "k_assemble_sym (fused K_e/R_e evaluation + RED.F64 scatter)"}[args.path], "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_element": alg_bytes / numEl,
                 "peak_source": peak_src, "step_frac_of_roofline": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
@@ -345,12 +443,10 @@ def run_ours(args, rank, world, local_rank):
         "launches_per_step": int(launches_per_step), "clocks": clocks,
         "plan_build": {"device_ms": plan.buildMs, "wall_ms": plan_wall_ms},
         "path": {"assembly_path": args.path, "rows_path": plan.info("rows_path"), "max_degree": plan.info("max_degree"), "rows_balanced": plan.info("rows_balanced"),
-                 "row_iters": [plan.info("row_iters_node_order"), plan.info("row_iters_balanced")], "write_once_patches": plan.info("patch_path"), "patch_nodes": plan.info("patch_nodes"), "team_warps": plan.info("team_warps"), "num_patches": plan.info("num_patches"),
-                 "patch_elems_total": plan.info("patch_elems_total"), "patch_elems_max": plan.info("patch_elems_max"),
-                 "patch_colours_max": plan.info("patch_colours_max"), "patch_blob_bytes": plan.info("patch_blob_bytes")},
+                 "row_iters": [plan.info("row_iters_node_order"), plan.info("row_iters_balanced")], "closed_form_q4": plan.info("closed_form_q4"), "fan_path": plan.info("fan_path")},
     }  # fmt: skip
     if not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(wl)
+        line["cpu_baseline"] = cpu_baseline(wl, args.config, args.nx)
     print(json.dumps(line))
 
 
@@ -514,13 +610,11 @@ def main():
     ap.add_argument("--balance-rows", type=int, default=None, help="row schedule of the row-owner kernel: 0 node order, 1 balanced when it pays (default), 2 always")
     ap.add_argument("--cpu-procs", type=int, default=None, help="worker processes of the CPU legs (default: all host cores)")
     ap.add_argument("--flush-write-only", action="store_true", help="L2 flush by the 512 MB write alone (leaves dirty lines for the timed kernel to evict)")
-    ap.add_argument("--patch-nodes", type=int, default=0, help="owned nodes per patch (0 = library default)")
     ap.add_argument("--dist-mode", default="halo", choices=["halo", "exchange"], help="multi-GPU: redundant boundary elements (no exchange) or unique elements + NCCL interface exchange")
+    ap.add_argument("--no-fan", action="store_true", help="accumulating row-owner kernel instead of the write-once fan kernel (exploration only)")
     ap.add_argument("--no-bcs", action="store_true", help="device-timed steps without boundary conditions (exploration only)")
-    ap.add_argument("--debug-flags", type=int, default=0, help="kernel experiment switches (exploration only)")
-    ap.add_argument("--team-warps", type=int, default=2, help="warps sharing a patch in the patch-pipeline kernel (1 or 2)")
-    ap.add_argument("--path", default="rows", choices=["rows", "patch", "scatter"],
-                    help="assembly path: row-owner kernel (default), write-once patch pipeline, or slot-map scatter with FP64 atomics")
+    ap.add_argument("--path", default="rows", choices=["rows", "scatter"],
+                    help="assembly path: row-owner kernel (default) or slot-map scatter with FP64 atomics")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

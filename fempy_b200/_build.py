@@ -6,8 +6,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libfemb200.so")
-SOURCES = ["common.cu", "plan.cu", "plan_patch.cu", "assemble.cu", "functions.cu", "solve.cu"]
-HEADERS = ["elem_math.cuh", "femb_internal.h", "patch_blob.h", "assemble_pipe.cuh", "assemble_rows.cuh", os.path.join("..", "..", "include", "femb200.h")]
+SOURCES = ["common.cu", "plan.cu", "assemble.cu", "functions.cu", "solve.cu"]
+HEADERS = ["elem_math.cuh", "femb_internal.h", "assemble_rows.cuh", "assemble_fan.cuh", os.path.join("..", "..", "include", "femb200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

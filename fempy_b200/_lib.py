@@ -33,7 +33,6 @@ _SIGNATURES = {
     "femb_plan_finalize": (C.c_int, [C.c_void_p]),
     "femb_plan_destroy": (None, [C.c_void_p]),
     "femb_plan_set_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
-    "femb_plan_set_locality_hint": (C.c_int, [C.c_void_p, c_double_p]),
     "femb_plan_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "femb_plan_get_info": (C.c_int64, [C.c_void_p, C.c_char_p]),
     "femb_plan_sync": (C.c_int, [C.c_void_p]),
@@ -52,7 +51,7 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "femb_plan_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "femb_plan_profile_read": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),
-    "femb_plan_pipe_stats": (C.c_int, [C.c_void_p, C.c_int32, c_int64_p, C.c_int64]),
+    "femb_plan_row_stats": (C.c_int, [C.c_void_p, C.c_int32, c_int64_p, C.c_int64]),
     "femb_function": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.POINTER(Material), C.c_int32, C.c_int32, c_double_p]),
     "femb_function_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Material), C.c_int32, C.c_int32, C.c_void_p]),
     "femb_solve_pcg": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int32, C.POINTER(C.c_int32), c_double_p]),
@@ -78,12 +77,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("FEMB200_LIB", LIB_PATH)  # measurement builds of the same library (tools/build_variant.sh)
+    if not os.path.exists(path):
         raise FembError(
-            f"{LIB_PATH} not found: build it with `python -m fempy_b200._build` (or __graft_entry__.build()). "
+            f"{path} not found: build it with `python -m fempy_b200._build` (or __graft_entry__.build()). "
             "fempy_b200 has no CPU fallback."
         )
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (restype, argtypes) in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = restype

@@ -1,5 +1,5 @@
 // Fused K + R assembly kernels and their C ABI.
-#include "assemble_pipe.cuh"
+#include "assemble_fan.cuh"
 #include "assemble_rows.cuh"
 #include "femb_internal.h"
 
@@ -133,96 +133,54 @@ __global__ void k_apply_bcs(long long nBC, const int* __restrict__ bcDof, const 
 
 
 // =============================================================================================
-// write-once assembly over node patches: persistent warp-specialised pipeline (assemble_pipe.cuh)
-// =============================================================================================
-static constexpr int PIPE_SMEM_LIMIT = 227 * 1024;
-
-template <int NN, int NQ, bool NL, bool WK, bool WR, int TEAM>
-static int launch_pipe(const femb_plan* p, const BlockData& b, const DMat& D, pipe::Args A, cudaStream_t st) {
-    const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
-    constexpr int numTeams = pipe::Cfg<TEAM>::NUM_TEAMS;
-    const pipe::SmemPlan S = pipe::smem_plan(numTeams, b.prog.maxBlobBytes, b.prog.maxLocal, b.prog.maxElems, b.prog.maxNodeBlocks, p->patchNodes, WK);
-    A.inStride = S.inStride;
-    A.offX = S.offX;
-    A.offU = S.offU;
-    A.offL = S.offL;
-    A.offTH = S.offTH;
-    A.offMask = S.offMask;
-    A.accStride = S.accStride;
-    A.offRacc = S.offRacc;
-    A.teamStride = S.teamStride;
-    A.offTeams = S.offTeams;
-    static int configured[64] = {};  // per device ordinal
-    int& conf = configured[p->device & 63];
-    if (S.total > conf) {
-        CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
-        conf = S.total;
-    }
-    int numSMs = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, p->device));
-    const int64_t wanted = (p->numPatches + numTeams - 1) / numTeams;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(wanted, numSMs));
-    if (A.stats && !NL && WK && WR) {  // measurement build of the headline variant only
-        CUDA_TRY(cudaFuncSetAttribute(pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
-        pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, true><<<grid, pipe::Cfg<TEAM>::THREADS, S.total, st>>>(tb, D, A);
-        return 0;
-    }
-    pipe::k_assemble_pipe<NN, NQ, NL, WK, WR, TEAM, false><<<grid, pipe::Cfg<TEAM>::THREADS, S.total, st>>>(tb, D, A);
-    return 0;
-}
-
-template <int NN, int NQ, int TEAM>
-static int launch_pipe_variant(const femb_plan* p, const BlockData& b, const DMat& D, const pipe::Args& A, bool nl, bool wk,
-                               bool wr, cudaStream_t st) {
-    if constexpr (NN <= 4) {
-        if (!nl) {
-            if (wk && wr) return launch_pipe<NN, NQ, false, true, true, TEAM>(p, b, D, A, st);
-            if (wk) return launch_pipe<NN, NQ, false, true, false, TEAM>(p, b, D, A, st);
-            return launch_pipe<NN, NQ, false, false, true, TEAM>(p, b, D, A, st);
-        }
-        if (wk && wr) return launch_pipe<NN, NQ, true, true, true, TEAM>(p, b, D, A, st);
-        if (wk) return launch_pipe<NN, NQ, true, true, false, TEAM>(p, b, D, A, st);
-        return launch_pipe<NN, NQ, true, false, true, TEAM>(p, b, D, A, st);
-    } else {
-        return fail("no patch kernel for %d-node elements", NN);
-    }
-}
-
-template <int NN, int NQ>
-static int launch_pipe_team(const femb_plan* p, const BlockData& b, const DMat& D, const pipe::Args& A, bool nl, bool wk, bool wr,
-                            cudaStream_t st) {
-    if (p->teamWarps == 1) return launch_pipe_variant<NN, NQ, 1>(p, b, D, A, nl, wk, wr, st);
-    return launch_pipe_variant<NN, NQ, 2>(p, b, D, A, nl, wk, wr, st);
-}
-
-bool patch_path_available(const femb_plan* p, bool wk, bool /*wr*/) {
-    if (p->usePatch != 1 || !p->patchesBuilt) return false;
-    const int numTeams = 10 / p->teamWarps;
-    const int elemCap = 32 * p->teamWarps;  // one thread per element
-    for (auto& b : p->blocks) {
-        if (!b.prog.built) return false;
-        if (b.nn > 4 || b.prog.maxElems > elemCap) return false;
-        const int total = pipe::smem_plan(numTeams, b.prog.maxBlobBytes, b.prog.maxLocal, b.prog.maxElems, b.prog.maxNodeBlocks, p->patchNodes, wk).total;
-        if (total > PIPE_SMEM_LIMIT) return false;
-    }
-    return true;
-}
-
-
-
-// =============================================================================================
 // row-owner path (assemble_rows.cuh): one thread per node row, redundant geometry, no atomics / barriers
 // =============================================================================================
 bool rows_path_available(const femb_plan* p) {
     // every block needs corner records (<= 12 nodes per element: 16-node quads stay on the scatter kernels, their strip
     // alone is 64 doubles per thread)
-    if (p->usePatch != 2 || !p->rowsBuilt || p->maxDeg > rows::MAXD) return false;
+    if (p->assemblyPath != 2 || !p->rowsBuilt || p->maxDeg > rows::MAXD) return false;
+    for (auto& b : p->blocks)
+        if (b.nn <= 4 && !b.cyclic) return false;  // rotated corner records need tables invariant under cyclic renumbering
     const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * (sizeof(double2) + 1) + rows::BLOCK * sizeof(double2);
     return smem <= 200 * 1024;
 }
 
-template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB, bool PERM>
-static int launch_rows_mb(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
+// =============================================================================================
+// write-once fan kernel (assemble_fan.cuh): single block of 3- / 4-node elements with the standard tables, small strain
+// =============================================================================================
+bool fan_path_available(const femb_plan* p) {
+    return rows_path_available(p) && p->useFan && p->blocks.size() == 1 && p->blocks[0].fanOK && p->blocks[0].closedForm;
+}
+
+template <int NN, bool WK, bool WR, bool CMP>
+static int launch_fan(const femb_plan* p, const DMat& D, const fan::Args& A, cudaStream_t st) {
+    const size_t smem = (size_t)2 * p->maxDeg * fan::BLOCK * sizeof(double2);  // row staging
+    static size_t configured[64] = {};
+    size_t& conf = configured[p->device & 63];
+    if (smem > conf) {
+        CUDA_TRY(cudaFuncSetAttribute(fan::k_assemble_fan<NN, WK, WR, CMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conf = smem;
+    }
+    fan::k_assemble_fan<NN, WK, WR, CMP><<<grid_for(p->numNodes, fan::BLOCK), fan::BLOCK, smem, st>>>(D, A);
+    return 0;
+}
+
+template <int NN>
+static int launch_fan_variant(const femb_plan* p, const DMat& D, const fan::Args& A, bool wk, bool wr, cudaStream_t st) {
+    if constexpr (NN == 4) {
+        if (p->blocks[0].fanCompact) {
+            if (wk && wr) return launch_fan<NN, true, true, true>(p, D, A, st);
+            if (wk) return launch_fan<NN, true, false, true>(p, D, A, st);
+            return launch_fan<NN, false, true, true>(p, D, A, st);
+        }
+    }
+    if (wk && wr) return launch_fan<NN, true, true, false>(p, D, A, st);
+    if (wk) return launch_fan<NN, true, false, false>(p, D, A, st);
+    return launch_fan<NN, false, true, false>(p, D, A, st);
+}
+
+template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB, bool PERM, bool CF>
+static int launch_rows_cf(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
     const Tables<NN, NQ> tb = make_tables<NN, NQ>(b);
     // accumulator rows + residual pairs + write-out owner table
     const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * (sizeof(double2) + 1) + rows::BLOCK * sizeof(double2);
@@ -230,12 +188,22 @@ static int launch_rows_mb(const femb_plan* p, const BlockData& b, const DMat& D,
     static size_t configured[64] = {};
     size_t& conf = configured[p->device & 63];
     if (smem > conf) {
-        CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB, PERM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB, PERM, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conf = smem;
     }
     const long long slots = PERM ? p->rowSlots : p->numNodes;
-    rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB, PERM><<<grid_for(slots, rows::BLOCK), rows::BLOCK, smem, st>>>(tb, D, A);
+    rows::k_assemble_rows<NN, NQ, NL, WK, WR, MB, PERM, CF><<<grid_for(slots, rows::BLOCK), rows::BLOCK, smem, st>>>(tb, D, A);
     return 0;
+}
+
+// 4-node blocks whose tables are the standard bilinear quad with the 2x2 Gauss rule (plan.cu: standard_q4) take the
+// closed-form kernel for the small-strain model
+template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB, bool PERM>
+static int launch_rows_mb(const femb_plan* p, const BlockData& b, const DMat& D, const rows::Args& A, cudaStream_t st) {
+    if constexpr (NN == 4 && NQ == 4 && !NL && FEMB_ROT4) {
+        if (b.closedForm) return launch_rows_cf<NN, NQ, NL, WK, WR, MB, PERM, true>(p, b, D, A, st);
+    }
+    return launch_rows_cf<NN, NQ, NL, WK, WR, MB, PERM, false>(p, b, D, A, st);
 }
 
 template <int NN, int NQ, bool NL, bool WK, bool WR>
@@ -309,11 +277,9 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
     const int64_t numDOF = femb_plan_num_dof(p), nnz = femb_plan_nnz(p);
     int64_t launches = 0;
     const bool rowsPath = rows_path_available(p);
-    const bool patchPath = !rowsPath && patch_path_available(p, wk, wr);
-    const bool multi = p->blocks.size() > 1;
     const bool bcs = applyBCs && p->nBC > 0;
-    if (!rowsPath && !patchPath) TRY(ensure_slot_maps(p));
-    if (!rowsPath && (!patchPath || multi)) {  // scatter path, or several element types summing into the same rows
+    if (!rowsPath) TRY(ensure_slot_maps(p));
+    if (!rowsPath) {  // scatter path: the element blocks are added into zeroed K / -loads
         if (wk) CUDA_TRY(cudaMemsetAsync(d_K, 0, nnz * sizeof(double), st));
         if (wr) {
             k_init_residual<<<grid_for(numDOF, 256), 256, 0, st>>>(d_R, d_loads, numDOF);
@@ -331,8 +297,29 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
         ev = &p->profEvents[p->profUsed++];
         CUDA_TRY(cudaEventRecord(ev->first, st));
     }
+    const bool fanPath = rowsPath && !mat->nonlinear && fan_path_available(p);
     for (auto& b : p->blocks) {
-        if (rowsPath) {
+        if (fanPath) {
+            fan::Args A;
+            A.numNodes = p->numNodes;
+            A.nrowptr = p->d_nrowptr;
+            A.cPtr = p->d_adjPtr;
+            A.rec = b.d_fanRec;
+            A.elem = b.d_fanElem;
+            A.coords = (const double2*)d_coords;
+            A.states = (const double2*)d_states;
+            A.thick = d_thick;
+            A.loads = (const double2*)d_loads;
+            A.bcInfo = bcs ? p->d_bcInfo : nullptr;
+            A.bcNodeCnt = (const double2*)p->d_bcNodeCnt;
+            A.bcNodeVal = (const double2*)p->d_bcNodeVal;
+            A.maxDeg = p->maxDeg;
+            A.zero = 0;
+            A.K = d_K;
+            A.R = d_R;
+            if (b.nn == 3) TRY((launch_fan_variant<3>(p, D, A, wk, wr, st)));
+            else TRY((launch_fan_variant<4>(p, D, A, wk, wr, st)));
+        } else if (rowsPath) {
             rows::Args A;
             A.numNodes = p->numNodes;
             A.slotRec = p->d_slotRec;
@@ -347,7 +334,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.corners = b.d_corners;
             A.cornerElem = b.d_cornerElem;
             A.zero = 0;
-            A.stats = p->d_pipeStats;
+            A.stats = p->d_rowStats;
             A.connE = b.d_connE;
             A.coords = (const double2*)d_coords;
             A.states = (const double2*)d_states;
@@ -360,27 +347,6 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.K = d_K;
             A.R = d_R;
             FEMB_DISPATCH_FAMILY(b.nn, b.nq, TRY((launch_rows_variant<NN, NQ>(p, b, D, A, mat->nonlinear != 0, wk, wr, st))));
-        } else if (patchPath) {
-            pipe::Args A;
-            A.numPatches = p->numPatches;
-            A.PN = p->patchNodes;
-            A.blobPtr = b.prog.d_blobPtr;
-            A.blob = b.prog.d_blob;
-            A.maskPerm = (bcs && !multi) ? p->d_bcMaskPerm : nullptr;
-            A.bcDof = p->d_bcDof;
-            A.bcVal = p->d_bcVal;
-            A.bcCount = p->d_bcCount;
-            A.nBC = (int)p->nBC;
-            A.coords = (const double2*)d_coords;
-            A.states = (const double2*)d_states;
-            A.loads = multi ? nullptr : (const double2*)d_loads;
-            A.thick = d_thick;
-            A.K = d_K;
-            A.R = d_R;
-            A.accumulate = multi ? 1 : 0;
-            A.stats = p->d_pipeStats;
-            A.debug = p->debugFlags;
-            FEMB_DISPATCH_FAMILY(b.nn, b.nq, TRY((launch_pipe_team<NN, NQ>(p, b, D, A, mat->nonlinear != 0, wk, wr, st))));
         } else {
             AsmArgs A;
             A.E = b.numElems;
@@ -398,7 +364,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
         launches++;
     }
     if (ev) CUDA_TRY(cudaEventRecord(ev->second, st));
-    if (bcs && !rowsPath && (!patchPath || multi)) {
+    if (bcs && !rowsPath) {
         k_apply_bcs<<<grid_for(p->nBC * 32, 128), 128, 0, st>>>(p->nBC, p->d_bcDof, p->d_bcVal, p->d_bcCount, p->d_nrowptr,
                                                                p->d_ncols, d_states, wk ? d_K : nullptr,
                                                                wr ? d_R : nullptr);
@@ -409,25 +375,25 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
     return 0;
 }
 
-// measurement only: per-CTA cycle counters of the pipeline roles (16 int64 per CTA, 256 CTAs max)
-extern "C" int femb_plan_pipe_stats(femb_plan* p, int32_t enable, int64_t* out, int64_t capacity) {
-    if (!p) return fail("femb_plan_pipe_stats: plan is NULL");
+// measurement builds only (ROWS_TRACE, tools/rows_trace.py): warp lifetime statistics of the row-owner kernel
+extern "C" int femb_plan_row_stats(femb_plan* p, int32_t enable, int64_t* out, int64_t capacity) {
+    if (!p) return fail("femb_plan_row_stats: plan is NULL");
     TRY(use_device(p));
     const size_t n = 16 * 256;
     if (out) {
-        if (!p->d_pipeStats) return fail("femb_plan_pipe_stats: not enabled");
+        if (!p->d_rowStats) return fail("femb_plan_row_stats: not enabled");
         CUDA_TRY(cudaStreamSynchronize(p->stream));
-        CUDA_TRY(cudaMemcpy(out, p->d_pipeStats, std::min<size_t>(n, (size_t)capacity) * sizeof(long long), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(out, p->d_rowStats, std::min<size_t>(n, (size_t)capacity) * sizeof(long long), cudaMemcpyDeviceToHost));
         return 0;
     }
     if (enable) {
-        TRY(dalloc(&p->d_pipeStats, n));
-        CUDA_TRY(cudaMemset(p->d_pipeStats, 0, n * sizeof(long long)));
-        const long long big = 0x7fffffffffffffffll;  // slots 3 and 5 hold minima (row-owner trace builds)
-        CUDA_TRY(cudaMemcpy(p->d_pipeStats + 3, &big, sizeof(big), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(p->d_pipeStats + 5, &big, sizeof(big), cudaMemcpyHostToDevice));
+        TRY(dalloc(&p->d_rowStats, n));
+        CUDA_TRY(cudaMemset(p->d_rowStats, 0, n * sizeof(long long)));
+        const long long big = 0x7fffffffffffffffll;  // slots 3 and 5 hold minima
+        CUDA_TRY(cudaMemcpy(p->d_rowStats + 3, &big, sizeof(big), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(p->d_rowStats + 5, &big, sizeof(big), cudaMemcpyHostToDevice));
     } else {
-        dfree(p->d_pipeStats);
+        dfree(p->d_rowStats);
     }
     return 0;
 }

@@ -1,0 +1,253 @@
+// Write-once row assembly over fan-ordered corners (sm_100a): 3- and 4-node elements, small strain, single element block.
+//
+// Like the row-owner kernel (assemble_rows.cuh) one thread owns the two DOF rows of one node, evaluates for every adjacent
+// element only the node-row strip of K_e, and the warp streams its 32 finished rows out as one contiguous run of the CSR
+// values.  What differs is how a row comes together.  The plan orders the corners of a node as a fan (plan.cu:
+// k_fan_corners): the last node of one corner is the first node of the next.  Walking the fan the thread finishes every
+// 2x2 block of its row in registers --
+//     own node        sum over all corners                  (kept in registers, stored after the walk)
+//     edge neighbour  last block of corner k + first block of corner k+1   (carried in registers from k to k+1)
+//     diagonal node   one corner                            (4-node elements)
+// -- and stores it ONCE into the row staging area in shared memory: no zero-fill, no read-modify-write.  The accumulating
+// kernel spends 44 % of the L1TEX data pipe on shared-memory wavefronts (ncu, round 2), two thirds of them the per-corner
+// read-modify-writes this kernel does not have.
+//
+// Element math (closed forms of the reference's point-by-point evaluation, FEMpy/Elements/Element.py:942-1168 with the
+// tables of QuadElement2D / TriElement2D order 1; the plan checks the block's tables, plan.cu: standard_q4 / standard_t3):
+//   4 nodes  with 8 det J dN_b/dx = C0_b + xi X0_b + eta E0_b, 8 det J dN_b/dy = C1_b + xi X1_b + eta E1_b (every
+//            coefficient one difference of two node coordinates), 8 det J = d0 + xi dx + eta de and the 2x2 Gauss rule,
+//            the geometric sums are S[d][D]_0b = P_d C_Db + Q_d X_Db + R_d E_Db with P, Q, R built from four moments of
+//            theta / (8 det J) over the Gauss points;
+//   3 nodes  constant gradients: S[d][D]_0b = theta / (2 det J) * Gh_d0 Gh_Db, Gh = adj(J) dN.
+// D is applied per block: K = [[D00 S00 + D22 S11, D01 S01 + D22 S10], [D01 S10 + D22 S01, D11 S11 + D22 S00]].
+#pragma once
+#include "assemble_rows.cuh"
+
+namespace fan {
+
+static constexpr int BLOCK = 32;
+
+struct Args {
+    long long numNodes;
+    const int* nrowptr;
+    const int* cPtr;          // node -> first corner (numNodes + 1 entries: the node -> element adjacency pointers)
+    const int4* rec;          // fan-ordered corner records
+    const int* elem;          // 4 nodes: element id per corner (3 nodes: in the record)
+    const double2* coords;
+    const double2* states;
+    const double* thick;
+    const double2* loads;     // may be NULL
+    const int* bcInfo;        // NULL: no BCs (see rows::Args)
+    const double2* bcNodeCnt;
+    const double2* bcNodeVal;
+    int maxDeg;
+    int zero;                 // always 0 (runtime-uniform index: keeps D out of the constant-bank operand slot)
+    double* K;
+    double* R;
+};
+
+template <int NN>
+__host__ __device__ constexpr int resident_warps() {
+#ifndef FAN_WARPS4
+#define FAN_WARPS4 16
+#endif
+#ifndef FAN_WARPS3
+#define FAN_WARPS3 24
+#endif
+    return NN == 4 ? FAN_WARPS4 : FAN_WARPS3;
+}
+
+// streaming inputs (corner records, element ids): read once, kept out of L1 so that the node data the corners share stays there
+__device__ __forceinline__ int4 ld_stream(const int4* p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// CMP: 4-node records with node / element ids as 24-bit differences to the owner (plan.cu: k_fan_compact)
+template <int NN, bool WK, bool WR, bool CMP>
+__global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(const __grid_constant__ femb::DMat D, const Args A) {
+    using femb::fast_rcp;
+    static_assert(NN == 3 || NN == 4, "fan kernel: 3- and 4-node elements");
+    // Row staging in the layout of the output: the warp's 32 rows are one contiguous run of the CSR values (both DOF rows
+    // of a node are adjacent, rows in node order), position p of the run sits at acc[swz(p)].  The swizzle (bit 3 of p
+    // flips bit 0) spreads the lanes' block stores -- 2*deg positions apart -- over all 16-byte bank groups and leaves the
+    // consecutive positions the write-out reads conflict-free.
+    extern __shared__ double2 acc[];  // [<= 2*maxDeg*BLOCK]
+    const int tid = threadIdx.x, lane = tid;
+    const long long i = (long long)blockIdx.x * BLOCK + tid;
+    const bool valid = i < A.numNodes;
+    const int off = __ldg(A.nrowptr + (valid ? i : A.numNodes));
+    const int deg = valid ? __ldg(A.nrowptr + i + 1) - off : 0;
+    const int c0 = valid ? __ldg(A.cPtr + i) : 0;
+    const int c1 = valid ? __ldg(A.cPtr + i + 1) : 0;
+    const unsigned info = (valid && A.bcInfo) ? (unsigned)__ldg(A.bcInfo + i) : 0u;
+    double2 ownX = make_double2(0.0, 0.0), ownU = make_double2(0.0, 0.0);
+    if (valid) {
+        ownX = __ldg(A.coords + i);
+        ownU = __ldg(A.states + i);
+    }
+    // first corner's record (and element id) are requested before anything waits
+    int4 rec = make_int4(0, 0, 0, 0);
+    int el = 0;
+    if (c0 < c1) {
+        rec = ld_stream(A.rec + c0);
+        if (NN == 4 && !CMP) el = ld_stream(A.elem + c0);
+    }
+    const int base = __shfl_sync(0xffffffffu, off, 0);
+    const int ownStart = 2 * (off - base);  // my first position in the warp's run of values
+    auto swz = [](int p) { return p ^ ((p >> 3) & 1); };
+    auto slot = [&](int m) -> double2& { return acc[swz(ownStart + m)]; };
+
+    // D through registers (an FP64 instruction with a constant-bank operand issues at half rate on sm_100)
+    const double* Dv = &D.d00 + A.zero;
+    const double d00 = Dv[0], d01 = Dv[1], d11 = Dv[2], d22 = Dv[3];
+
+    double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;  // own block, summed over the fan
+    double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0;  // block carried from the previous corner into this one's first neighbour
+    double ra0 = 0.0, ra1 = 0.0;                     // residual pair R_a = sum over corners of K_ab q_b
+    int firstSlot = 0;                               // row position of the first corner's first neighbour (closed fans wrap into it)
+    unsigned lastFlags = 0u;
+
+    // one 2x2 block: geometric sums -> D -> residual; returns the block
+    auto finish = [&](double s00, double s01, double s10, double s11, const double2 q, double& b0, double& b1, double& b2, double& b3) {
+        b0 = fma(d00, s00, d22 * s11);
+        b1 = fma(d01, s01, d22 * s10);
+        b2 = fma(d01, s10, d22 * s01);
+        b3 = fma(d11, s11, d22 * s00);
+        if (WR) {
+            ra0 = fma(b0, q.x, fma(b1, q.y, ra0));
+            ra1 = fma(b2, q.x, fma(b3, q.y, ra1));
+        }
+    };
+    auto store = [&](int k, double b0, double b1, double b2, double b3) {
+        if (WK) {
+            slot(k) = make_double2(b0, b1);
+            slot(deg + k) = make_double2(b2, b3);
+        }
+    };
+
+    for (int c = c0; c < c1; ++c) {
+        const unsigned kw = (unsigned)rec.x;
+        int n1 = rec.y, n2 = rec.z, n3 = rec.w;  // 3 nodes: n3 is the element id
+        int e = NN == 4 ? el : n3;
+        if constexpr (CMP) {  // four signed 24-bit differences to my node id
+            const int me = (int)i;
+            e = me + (rec.w >> 8);
+            n3 = me + ((int)(__funnelshift_r((unsigned)rec.z, (unsigned)rec.w, 16) << 8) >> 8);
+            n2 = me + ((int)(__funnelshift_r((unsigned)rec.y, (unsigned)rec.z, 24) << 8) >> 8);
+            n1 = me + ((rec.y << 8) >> 8);
+        }
+        const double2 X1 = __ldg(A.coords + n1), X2 = __ldg(A.coords + n2);
+        double2 X3 = make_double2(0.0, 0.0);
+        if (NN == 4) X3 = __ldg(A.coords + n3);
+        const double theta = __ldg(A.thick + e);
+        double2 q1 = make_double2(0.0, 0.0), q2 = q1, q3 = q1;
+        if (WR) {
+            q1 = __ldg(A.states + n1);
+            q2 = __ldg(A.states + n2);
+            if (NN == 4) q3 = __ldg(A.states + n3);
+        }
+        if (c + 1 < c1) {  // next corner's record: one iteration ahead of its use
+            rec = ld_stream(A.rec + c + 1);
+            if (NN == 4 && !CMP) el = ld_stream(A.elem + c + 1);
+        }
+        if (c == c0) firstSlot = (kw >> 7) & 0x7f;
+        lastFlags = kw;
+        double b0, b1, b2, b3;
+        if constexpr (NN == 4) {
+            const double ya = X1.y - X3.y, yb = X2.y - ownX.y, yc = X3.y - X2.y, yd = ownX.y - X1.y, ye = X2.y - X1.y, yf = ownX.y - X3.y;
+            const double xa = X3.x - X1.x, xb = ownX.x - X2.x, xc = X2.x - X3.x, xd = X1.x - ownX.x, xe = X1.x - X2.x, xf = X3.x - ownX.x;
+            constexpr double G = 0.57735026918962576451, THIRD = 1.0 / 3.0;
+            const double dd0 = xb * ya - xa * yb;
+            const double gx = G * (xc * yd - xd * yc), ge = G * (xe * yf - xf * ye);
+            const double tp = dd0 + gx, tm = dd0 - gx, th8 = 0.125 * theta;
+            const double spp = th8 * fast_rcp(tp + ge), spm = th8 * fast_rcp(tp - ge);
+            const double smp = th8 * fast_rcp(tm + ge), smm = th8 * fast_rcp(tm - ge);
+            const double up = spp + spm, um = smp + smm, vp = spp - spm, vm = smp - smm;
+            const double m0 = up + um, mx = G * (up - um), me = G * (vp + vm), mxe = THIRD * (vp - vm), m3 = THIRD * m0;
+            const double P0 = fma(m0, ya, fma(mx, yc, me * ye)), Q0 = fma(mx, ya, fma(m3, yc, mxe * ye)), R0 = fma(me, ya, fma(mxe, yc, m3 * ye));
+            const double P1 = fma(m0, xa, fma(mx, xc, me * xe)), Q1 = fma(mx, xa, fma(m3, xc, mxe * xe)), R1 = fma(me, xa, fma(mxe, xc, m3 * xe));
+            // b:        0            1            2            3
+            // C_Db:  ya | xa      yb | xb     -ya | -xa    -yb | -xb
+            // X_Db:  yc | xc     -yc | -xc     yd | xd     -yd | -xd
+            // E_Db:  ye | xe      yf | xf     -yf | -xf    -ye | -xe
+            finish(fma(P0, ya, fma(Q0, yc, R0 * ye)), fma(P0, xa, fma(Q0, xc, R0 * xe)), fma(P1, ya, fma(Q1, yc, R1 * ye)),
+                   fma(P1, xa, fma(Q1, xc, R1 * xe)), ownU, b0, b1, b2, b3);
+            o0 += b0, o1 += b1, o2 += b2, o3 += b3;
+            finish(fma(P0, yb, fma(R0, yf, -(Q0 * yc))), fma(P0, xb, fma(R0, xf, -(Q0 * xc))), fma(P1, yb, fma(R1, yf, -(Q1 * yc))),
+                   fma(P1, xb, fma(R1, xf, -(Q1 * xc))), q1, b0, b1, b2, b3);
+            store((kw >> 7) & 0x7f, b0 + k0, b1 + k1, b2 + k2, b3 + k3);
+            finish(fma(Q0, yd, -fma(P0, ya, R0 * yf)), fma(Q0, xd, -fma(P0, xa, R0 * xf)), fma(Q1, yd, -fma(P1, ya, R1 * yf)),
+                   fma(Q1, xd, -fma(P1, xa, R1 * xf)), q2, b0, b1, b2, b3);
+            store((kw >> 14) & 0x7f, b0, b1, b2, b3);
+            finish(-fma(P0, yb, fma(Q0, yd, R0 * ye)), -fma(P0, xb, fma(Q0, xd, R0 * xe)), -fma(P1, yb, fma(Q1, yd, R1 * ye)),
+                   -fma(P1, xb, fma(Q1, xd, R1 * xe)), q3, k0, k1, k2, k3);
+        } else {
+            // Gh_0 = (y1 - y2, y2 - y0, y0 - y1), Gh_1 = (x2 - x1, x0 - x2, x1 - x0), 2 * area = det
+            const double g00 = X1.y - X2.y, g01 = X2.y - ownX.y, g02 = ownX.y - X1.y;
+            const double g10 = X2.x - X1.x, g11 = ownX.x - X2.x, g12 = X1.x - ownX.x;
+            const double det = g12 * g01 - g11 * g02;  // (x1 - x0)(y2 - y0) - (x2 - x0)(y1 - y0)
+            const double sc = 0.5 * theta * fast_rcp(det);
+            const double A0 = sc * g00, A1 = sc * g10;
+            finish(A0 * g00, A0 * g10, A1 * g00, A1 * g10, ownU, b0, b1, b2, b3);
+            o0 += b0, o1 += b1, o2 += b2, o3 += b3;
+            finish(A0 * g01, A0 * g11, A1 * g01, A1 * g11, q1, b0, b1, b2, b3);
+            store((kw >> 7) & 0x7f, b0 + k0, b1 + k1, b2 + k2, b3 + k3);
+            finish(A0 * g02, A0 * g12, A1 * g02, A1 * g12, q2, k0, k1, k2, k3);
+        }
+        if (!(kw & (1u << 28)) && !(kw & (1u << 29))) {  // the fan ends here (open end or chain break): the carried block is final
+            store((kw >> (7 * (NN - 1))) & 0x7f, k0, k1, k2, k3);
+            k0 = k1 = k2 = k3 = 0.0;
+        }
+    }
+    if (WK && c0 < c1) {
+        if (lastFlags & (1u << 29)) {  // closed fan: the last corner continues into the first one's first neighbour
+            double2& s0 = slot(firstSlot);
+            double2& s1 = slot(deg + firstSlot);
+            const double2 p0 = s0, p1 = s1;
+            s0 = make_double2(p0.x + k0, p0.y + k1);
+            s1 = make_double2(p1.x + k2, p1.y + k3);
+        }
+        store((int)(lastFlags & 0x7f), o0, o1, o2, o3);  // own block
+    }
+
+    // ---- BC rows, loads, residual: as in the row-owner kernel ------------------------------------------------------
+    const unsigned m = info & 3u;
+    if (m && WK) {  // constrained rows: zeros, occurrence count on the diagonal (AssemblyUtils.py:55-60)
+        const double2 cnt = __ldg(A.bcNodeCnt + (info >> 9) - 1);
+        const int diagK = (info >> 2) & 0x7f;
+        for (int r = 0; r < 2; ++r) {
+            if (m & (1u << r)) {
+                for (int k = 0; k < deg; ++k) slot(r * deg + k) = make_double2(0.0, 0.0);
+                slot(r * deg + diagK) = r ? make_double2(0.0, cnt.y) : make_double2(cnt.x, 0.0);
+            }
+        }
+    }
+    double2 fLoad = make_double2(0.0, 0.0), valBC = make_double2(0.0, 0.0);
+    if (WR && valid) {
+        if (A.loads) fLoad = __ldg(A.loads + i);
+        if (m) valBC = __ldg(A.bcNodeVal + (info >> 9) - 1);
+    }
+    // ---- write-out: stream the warp's run of CSR values (both DOF rows of a node are adjacent, rows in node order) ---
+    if (WK) {
+        double2* K2 = reinterpret_cast<double2*>(A.K) + 2ll * base;
+        const int total = __shfl_sync(0xffffffffu, ownStart + 2 * deg, 31);  // invalid tail lanes hold off = end, deg = 0
+        __syncwarp();
+#pragma unroll 4
+        for (int f = lane; f < total; f += 32) rows::st_stream(K2 + f, acc[swz(f)]);
+    }
+    if (WR && valid) {
+        double rx = ra0 - fLoad.x, ry = ra1 - fLoad.y;  // R = scatter(R_e) - loads (Problem.py:653)
+        if (m & 1u) rx = ownU.x - valBC.x;             // R[bc] = u - c (AssemblyUtils.py:93)
+        if (m & 2u) ry = ownU.y - valBC.y;
+        reinterpret_cast<double2*>(A.R)[i] = make_double2(rx, ry);
+    }
+}
+
+}  // namespace fan

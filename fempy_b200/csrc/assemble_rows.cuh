@@ -73,11 +73,14 @@ __host__ __device__ constexpr int resident_threads() {
 // the last one applies loads and boundary conditions); single-block plans compile those switches away
 // PERM: the thread's node comes from the plan's balanced row schedule (nodes of a window ordered by corner count) instead
 // of the thread index; the warp's rows are then 32 separate runs of the CSR values instead of one
-template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB, bool PERM>
+// CF: closed-form bilinear quad (4 nodes, 2x2 Gauss rule, small strain; plan.cu checks the block's tables): the geometry of
+// a corner is 12 coordinate differences and four reciprocals, the Gauss-point sum is carried by four moments of w*theta/det
+template <int NN, int NQ, bool NL, bool WK, bool WR, bool MB, bool PERM, bool CF>
 __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_assemble_rows(const __grid_constant__ femb::Tables<NN, NQ> tb, const __grid_constant__ femb::DMat D,
                                                         const Args A) {
     using namespace femb;
     static_assert(NN <= 12, "corner records hold at most 12 slot positions");
+    static_assert(!CF || (NN == 4 && NQ == 4 && !NL && FEMB_ROT4), "closed form: rotated bilinear quads, small strain");
     constexpr int CW = (NN + 3) / 4;  // connectivity words per element
     extern __shared__ double2 acc[];  // [2*maxDeg][BLOCK], swizzled
     const bool accumulate = MB && A.accumulate, finalise = !MB || A.finalise;
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
     // re-read per corner (one coalesced request per warp) because the 96-register budget has no room to keep them
     constexpr bool ROT4 = NN == 4 && FEMB_ROT4;
     double2 ownX = make_double2(0.0, 0.0), ownU = make_double2(0.0, 0.0);
-    if (ROT && valid) {
+    if ((ROT || CF) && valid) {
         ownX = __ldg(A.coords + i);
         ownU = __ldg(A.states + i);
     }
@@ -238,116 +241,166 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
 #pragma unroll
             for (int w = 0; w < CW; ++w) connAhead[w] = __ldg(A.connE + (long long)(recAhead.x & EMASK) * CW + w);
         }
-        double x[NN], y[NN], ux[NN], uy[NN];
-#pragma unroll
-        for (int b = 0; b < NN; ++b) {
-            const double2 X = (ROT && b == 0) ? ownX
-                              : (KNOCK & 2) ? make_double2(0.01 * (node[b] & 511) + ((b == 1 || b == 2) ? 0.01 : 0.0), 1e-5 * node[b] + (b >= 2 ? 0.01 : 0.0))
-                                            : __ldg(A.coords + node[b]);
-            x[b] = X.x;
-            y[b] = X.y;
-            if (NL) {
-                const double2 U = (ROT && b == 0) ? ownU : __ldg(A.states + node[b]);
-                ux[b] = U.x;
-                uy[b] = U.y;
-            } else {  // linear model: the states are fetched after the strip (short live range)
-                ux[b] = uy[b] = 0.0;
-            }
-        }
-        const double theta = (KNOCK & 2) ? 1.0 + 1e-9 * e : __ldg(A.thick + elemOffset + e);
-        if (fillPending) {
-            fill();
-            fillPending = false;
-        }
-
-        // node-row strip of K_e: blocks (a, b), b = 0..NN-1, and the residual pair of node a
-        double Kr[NN][4];
+        double Kr[NN][4];  // node-row strip of K_e: blocks (a, b), b = 0..NN-1 -- geometric sums S[d][D] until D is applied
         double ra0 = 0.0, ra1 = 0.0;
-#pragma unroll
-        for (int b = 0; b < NN; ++b) Kr[b][0] = Kr[b][1] = Kr[b][2] = Kr[b][3] = 0.0;
-#pragma unroll POINT_UNROLL
-        for (int p = 0; p < ((KNOCK & 16) ? 1 : NQ); ++p) {
-            if (!NL) {
-                // Linear model, division-free gradients: with adj = det * J^-1 and Gh = adj * dN (so G = Gh / det),
-                //   sc * G_a G_b = (w * theta / det) * Gh_a Gh_b,
-                // so only the scalar w*theta/det carries the reciprocal.  The gradient of "my" shape function comes
-                // from the table with a per-thread index (constant-bank load) instead of register selects, and the
-                // tables are read through uniform registers (rolled loop): FP64 instructions with a constant-bank
-                // operand issue at half rate on sm_100 (tools/micro/fp64_micro2.cu).
-                double J00 = 0.0, J01 = 0.0, J10 = 0.0, J11 = 0.0;
-#pragma unroll
-                for (int b = 0; b < NN; ++b) {
-                    J00 = fma(tb.dN[p][0][b], x[b], J00);
-                    J01 = fma(tb.dN[p][0][b], y[b], J01);
-                    J10 = fma(tb.dN[p][1][b], x[b], J10);
-                    J11 = fma(tb.dN[p][1][b], y[b], J11);
-                }
-                const double det = J00 * J11 - J01 * J10;
-                const double sc = tb.w[p] * theta * fast_rcp(det);
-                const double da0 = tb.dN[p][0][a], da1 = tb.dN[p][1][a];
-                const double A0 = (J11 * da0 - J01 * da1) * sc, A1 = (J00 * da1 - J10 * da0) * sc;
-                if (WK || WR) {
-#pragma unroll
-                    for (int b = 0; b < NN; ++b) {
-                        const double g0 = J11 * tb.dN[p][0][b] - J01 * tb.dN[p][1][b];
-                        const double g1 = J00 * tb.dN[p][1][b] - J10 * tb.dN[p][0][b];
-                        Kr[b][0] = fma(A0, g0, Kr[b][0]);
-                        Kr[b][1] = fma(A0, g1, Kr[b][1]);
-                        Kr[b][2] = fma(A1, g0, Kr[b][2]);
-                        Kr[b][3] = fma(A1, g1, Kr[b][3]);
-                    }
-                }
-                continue;
+        if constexpr (CF) {
+            // Closed form of the bilinear quad with the owner as local node 0 (nodes counter-clockwise).  With
+            //   8 det J dN_b/dx = C0_b + xi X0_b + eta E0_b,   8 det J dN_b/dy = C1_b + xi X1_b + eta E1_b
+            // (every coefficient is one difference of two node coordinates), 8 det J = d0 + xi dx + eta de and the 2x2
+            // Gauss rule (xi, eta = +-g, w = 1), the geometric sums over the four points are
+            //   S[d][D]_0b = P_d C_Db + Q_d X_Db + R_d E_Db,
+            // P, Q, R built from the moments m0, m_xi, m_eta, m_xi_eta of s_p = theta / (8 det'_p)  (sum_p s_p xi^2 = m0 / 3).
+            // (FEMpy/Elements/Element.py:942-1111,1147-1168 evaluate the same integrals point by point.)
+            const double2 X1 = __ldg(A.coords + node[1]), X2 = __ldg(A.coords + node[2]), X3 = __ldg(A.coords + node[3]);
+            const double th8 = 0.125 * __ldg(A.thick + elemOffset + e);
+            if (fillPending) {
+                fill();
+                fillPending = false;
             }
-            double G0[NN], G1[NN];
-            const double det = point_gradients<NN, NQ>(tb, p, x, y, G0, G1);
-            const double sc = tb.w[p] * det * theta;
-            double g0 = 0.0, g1 = 0.0;  // gradient of "my" shape function: runtime index -> selects, no dynamic registers
+            const double ya = X1.y - X3.y, yb = X2.y - ownX.y, yc = X3.y - X2.y, yd = ownX.y - X1.y, ye = X2.y - X1.y, yf = ownX.y - X3.y;
+            const double xa = X3.x - X1.x, xb = ownX.x - X2.x, xc = X2.x - X3.x, xd = X1.x - ownX.x, xe = X1.x - X2.x, xf = X3.x - ownX.x;
+            constexpr double G = 0.57735026918962576451, THIRD = 1.0 / 3.0;
+            const double d0 = xb * ya - xa * yb;
+            const double gx = G * (xc * yd - xd * yc), ge = G * (xe * yf - xf * ye);
+            const double tp = d0 + gx, tm = d0 - gx;
+            const double spp = th8 * fast_rcp(tp + ge), spm = th8 * fast_rcp(tp - ge);
+            const double smp = th8 * fast_rcp(tm + ge), smm = th8 * fast_rcp(tm - ge);
+            const double up = spp + spm, um = smp + smm, vp = spp - spm, vm = smp - smm;
+            const double m0 = up + um, mx = G * (up - um), me = G * (vp + vm), mxe = THIRD * (vp - vm), m3 = THIRD * m0;
+            const double P0 = fma(m0, ya, fma(mx, yc, me * ye)), Q0 = fma(mx, ya, fma(m3, yc, mxe * ye)), R0 = fma(me, ya, fma(mxe, yc, m3 * ye));
+            const double P1 = fma(m0, xa, fma(mx, xc, me * xe)), Q1 = fma(mx, xa, fma(m3, xc, mxe * xe)), R1 = fma(me, xa, fma(mxe, xc, m3 * xe));
+            if (WK || WR) {
+                // b:        0            1            2            3
+                // C_Db:  ya | xa      yb | xb     -ya | -xa    -yb | -xb
+                // X_Db:  yc | xc     -yc | -xc     yd | xd     -yd | -xd
+                // E_Db:  ye | xe      yf | xf     -yf | -xf    -ye | -xe
+                Kr[0][0] = fma(P0, ya, fma(Q0, yc, R0 * ye));
+                Kr[0][1] = fma(P0, xa, fma(Q0, xc, R0 * xe));
+                Kr[0][2] = fma(P1, ya, fma(Q1, yc, R1 * ye));
+                Kr[0][3] = fma(P1, xa, fma(Q1, xc, R1 * xe));
+                Kr[1][0] = fma(P0, yb, fma(R0, yf, -(Q0 * yc)));
+                Kr[1][1] = fma(P0, xb, fma(R0, xf, -(Q0 * xc)));
+                Kr[1][2] = fma(P1, yb, fma(R1, yf, -(Q1 * yc)));
+                Kr[1][3] = fma(P1, xb, fma(R1, xf, -(Q1 * xc)));
+                Kr[2][0] = fma(Q0, yd, -fma(P0, ya, R0 * yf));
+                Kr[2][1] = fma(Q0, xd, -fma(P0, xa, R0 * xf));
+                Kr[2][2] = fma(Q1, yd, -fma(P1, ya, R1 * yf));
+                Kr[2][3] = fma(Q1, xd, -fma(P1, xa, R1 * xf));
+                Kr[3][0] = -fma(P0, yb, fma(Q0, yd, R0 * ye));
+                Kr[3][1] = -fma(P0, xb, fma(Q0, xd, R0 * xe));
+                Kr[3][2] = -fma(P1, yb, fma(Q1, yd, R1 * ye));
+                Kr[3][3] = -fma(P1, xb, fma(Q1, xd, R1 * xe));
+            }
+        } else {
+            double x[NN], y[NN], ux[NN], uy[NN];
 #pragma unroll
             for (int b = 0; b < NN; ++b) {
-                g0 = (b == a) ? G0[b] : g0;
-                g1 = (b == a) ? G1[b] : g1;
+                const double2 X = (ROT && b == 0) ? ownX
+                                  : (KNOCK & 2) ? make_double2(0.01 * (node[b] & 511) + ((b == 1 || b == 2) ? 0.01 : 0.0), 1e-5 * node[b] + (b >= 2 ? 0.01 : 0.0))
+                                                : __ldg(A.coords + node[b]);
+                x[b] = X.x;
+                y[b] = X.y;
+                if (NL) {
+                    const double2 U = (ROT && b == 0) ? ownU : __ldg(A.states + node[b]);
+                    ux[b] = U.x;
+                    uy[b] = U.y;
+                } else {  // linear model: the states are fetched after the strip (short live range)
+                    ux[b] = uy[b] = 0.0;
+                }
             }
-            if (!NL) {
-                // linear model: accumulate the geometric sums sc * G_d,a * G_D,b; D is applied once below
-                if (WK || WR) {
-                    const double A0 = g0 * sc, A1 = g1 * sc;
+            const double theta = (KNOCK & 2) ? 1.0 + 1e-9 * e : __ldg(A.thick + elemOffset + e);
+            if (fillPending) {
+                fill();
+                fillPending = false;
+            }
+
+            // node-row strip of K_e: blocks (a, b), b = 0..NN-1, and the residual pair of node a
+#pragma unroll
+            for (int b = 0; b < NN; ++b) Kr[b][0] = Kr[b][1] = Kr[b][2] = Kr[b][3] = 0.0;
+#pragma unroll POINT_UNROLL
+            for (int p = 0; p < ((KNOCK & 16) ? 1 : NQ); ++p) {
+                if (!NL) {
+                    // Linear model, division-free gradients: with adj = det * J^-1 and Gh = adj * dN (so G = Gh / det),
+                    //   sc * G_a G_b = (w * theta / det) * Gh_a Gh_b,
+                    // so only the scalar w*theta/det carries the reciprocal.  The gradient of "my" shape function comes
+                    // from the table with a per-thread index (constant-bank load) instead of register selects, and the
+                    // tables are read through uniform registers (rolled loop): FP64 instructions with a constant-bank
+                    // operand issue at half rate on sm_100 (tools/micro/fp64_micro2.cu).
+                    double J00 = 0.0, J01 = 0.0, J10 = 0.0, J11 = 0.0;
 #pragma unroll
                     for (int b = 0; b < NN; ++b) {
-                        Kr[b][0] = fma(A0, G0[b], Kr[b][0]);
-                        Kr[b][1] = fma(A0, G1[b], Kr[b][1]);
-                        Kr[b][2] = fma(A1, G0[b], Kr[b][2]);
-                        Kr[b][3] = fma(A1, G1[b], Kr[b][3]);
+                        J00 = fma(tb.dN[p][0][b], x[b], J00);
+                        J01 = fma(tb.dN[p][0][b], y[b], J01);
+                        J10 = fma(tb.dN[p][1][b], x[b], J10);
+                        J11 = fma(tb.dN[p][1][b], y[b], J11);
                     }
-                }
-            } else {
-                double u[2][2];
-                state_gradient<NN>(G0, G1, ux, uy, u);
-                double Ba[3][2];
-                bmat<true>(g0, g1, u, Ba);
-                if (WR) {
-                    double sig[3];
-                    stresses<true>(D, u, sig);
-                    ra0 = fma(sc, Ba[0][0] * sig[0] + Ba[1][0] * sig[1] + Ba[2][0] * sig[2], ra0);
-                    ra1 = fma(sc, Ba[0][1] * sig[0] + Ba[1][1] * sig[1] + Ba[2][1] * sig[2], ra1);
-                }
-                if (WK) {
-                    double DBa[3][2];
+                    const double det = J00 * J11 - J01 * J10;
+                    const double sc = tb.w[p] * theta * fast_rcp(det);
+                    const double da0 = tb.dN[p][0][a], da1 = tb.dN[p][1][a];
+                    const double A0 = (J11 * da0 - J01 * da1) * sc, A1 = (J00 * da1 - J10 * da0) * sc;
+                    if (WK || WR) {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        DBa[0][s] = sc * (D.d00 * Ba[0][s] + D.d01 * Ba[1][s]);
-                        DBa[1][s] = sc * (D.d01 * Ba[0][s] + D.d11 * Ba[1][s]);
-                        DBa[2][s] = sc * (D.d22 * Ba[2][s]);
+                        for (int b = 0; b < NN; ++b) {
+                            const double g0 = J11 * tb.dN[p][0][b] - J01 * tb.dN[p][1][b];
+                            const double g1 = J00 * tb.dN[p][1][b] - J10 * tb.dN[p][0][b];
+                            Kr[b][0] = fma(A0, g0, Kr[b][0]);
+                            Kr[b][1] = fma(A0, g1, Kr[b][1]);
+                            Kr[b][2] = fma(A1, g0, Kr[b][2]);
+                            Kr[b][3] = fma(A1, g1, Kr[b][3]);
+                        }
                     }
+                    continue;
+                }
+                double G0[NN], G1[NN];
+                const double det = point_gradients<NN, NQ>(tb, p, x, y, G0, G1);
+                const double sc = tb.w[p] * det * theta;
+                double g0 = 0.0, g1 = 0.0;  // gradient of "my" shape function: runtime index -> selects, no dynamic registers
 #pragma unroll
-                    for (int b = 0; b < NN; ++b) {
-                        double Bb[3][2];
-                        bmat<true>(G0[b], G1[b], u, Bb);
+                for (int b = 0; b < NN; ++b) {
+                    g0 = (b == a) ? G0[b] : g0;
+                    g1 = (b == a) ? G1[b] : g1;
+                }
+                if (!NL) {
+                    // linear model: accumulate the geometric sums sc * G_d,a * G_D,b; D is applied once below
+                    if (WK || WR) {
+                        const double A0 = g0 * sc, A1 = g1 * sc;
 #pragma unroll
-                        for (int s = 0; s < 2; ++s)
+                        for (int b = 0; b < NN; ++b) {
+                            Kr[b][0] = fma(A0, G0[b], Kr[b][0]);
+                            Kr[b][1] = fma(A0, G1[b], Kr[b][1]);
+                            Kr[b][2] = fma(A1, G0[b], Kr[b][2]);
+                            Kr[b][3] = fma(A1, G1[b], Kr[b][3]);
+                        }
+                    }
+                } else {
+                    double u[2][2];
+                    state_gradient<NN>(G0, G1, ux, uy, u);
+                    double Ba[3][2];
+                    bmat<true>(g0, g1, u, Ba);
+                    if (WR) {
+                        double sig[3];
+                        stresses<true>(D, u, sig);
+                        ra0 = fma(sc, Ba[0][0] * sig[0] + Ba[1][0] * sig[1] + Ba[2][0] * sig[2], ra0);
+                        ra1 = fma(sc, Ba[0][1] * sig[0] + Ba[1][1] * sig[1] + Ba[2][1] * sig[2], ra1);
+                    }
+                    if (WK) {
+                        double DBa[3][2];
 #pragma unroll
-                            for (int S = 0; S < 2; ++S)
-                                Kr[b][2 * s + S] += DBa[0][s] * Bb[0][S] + DBa[1][s] * Bb[1][S] + DBa[2][s] * Bb[2][S];
+                        for (int s = 0; s < 2; ++s) {
+                            DBa[0][s] = sc * (D.d00 * Ba[0][s] + D.d01 * Ba[1][s]);
+                            DBa[1][s] = sc * (D.d01 * Ba[0][s] + D.d11 * Ba[1][s]);
+                            DBa[2][s] = sc * (D.d22 * Ba[2][s]);
+                        }
+#pragma unroll
+                        for (int b = 0; b < NN; ++b) {
+                            double Bb[3][2];
+                            bmat<true>(G0[b], G1[b], u, Bb);
+#pragma unroll
+                            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                                for (int S = 0; S < 2; ++S)
+                                    Kr[b][2 * s + S] += DBa[0][s] * Bb[0][S] + DBa[1][s] * Bb[1][S] + DBa[2][s] * Bb[2][S];
+                        }
                     }
                 }
             }
@@ -363,7 +416,7 @@ __global__ void __launch_bounds__(BLOCK, resident_threads<NN, NL>() / BLOCK) k_a
                 Kr[b][2] = fma(d01, s10, d22 * s01);
                 Kr[b][3] = fma(d11, s11, d22 * s00);
                 if (WR) {  // R_a = sum_b K_ab q_b
-                    const double2 q = (ROT && b == 0) ? ownU : (KNOCK & 2) ? make_double2(1e-3, 1e-4 * node[b]) : __ldg(A.states + node[b]);
+                    const double2 q = ((ROT || CF) && b == 0) ? ownU : (KNOCK & 2) ? make_double2(1e-3, 1e-4 * node[b]) : __ldg(A.states + node[b]);
                     ra0 = fma(Kr[b][0], q.x, fma(Kr[b][1], q.y, ra0));
                     ra1 = fma(Kr[b][2], q.x, fma(Kr[b][3], q.y, ra1));
                 }

@@ -41,24 +41,6 @@ int femb_fail(const char* fmt, ...);
 // ---------------------------------------------------------------------------------------------
 static constexpr int MAX_BLOCKS = 8;
 
-// Gather program of one element block over the plan's node patches ("write-once" assembly):
-// a CTA owns a patch of nodes, evaluates every element touching them into shared memory and then
-// sums, for each (owned node, neighbour node) block of the global matrix, its element contributions.
-struct PatchProgram {
-    bool built = false;
-    int maxElems = 0;             // largest patch element count (shared-memory sizing)
-    int64_t totalElems = 0;       // sum over patches (includes elements evaluated by several patches)
-    int maxBlobBytes = 0;         // largest program blob
-    int maxLocal = 0;             // largest local-node count (owned + halo)
-    int maxNodeBlocks = 0;        // largest number of (owned node, neighbour) blocks of a patch (accumulator sizing)
-    int maxColours = 0;           // largest number of colours of a scatter phase
-    int64_t blobBytes = 0;        // total size of the program blobs
-    int* d_pePtr = nullptr;       // (numPatches+1) patch -> range of patch elements
-    int* d_peElem = nullptr;      // (build only) block-local element id of each patch element, sorted within a patch
-    int* d_blobPtr = nullptr;     // (numPatches+1) patch -> blob offset in 16-byte units
-    unsigned char* d_blob = nullptr;  // program blobs (patch_blob.h)
-};
-
 struct BlockData {
     int nn = 0, nq = 0;
     int64_t numElems = 0;
@@ -66,12 +48,17 @@ struct BlockData {
     int64_t pointOffset = 0;  // first global Gauss point (for FEMB_REDUCE_NONE output)
     int64_t keOffset = 0, reOffset = 0;
     std::vector<double> N, dN, w;
+    bool closedForm = false;  // 4 nodes: standard bilinear tables + 2x2 Gauss rule -> closed-form row-owner kernel (plan.cu: standard_q4)
+    bool cyclic = true;       // 3/4 nodes: tables invariant under cyclic renumbering -> corner records rotated to the owner
     int* d_conn = nullptr;  // node-major int32: conn[a * E + e]
     int* d_slot = nullptr;  // [(a*nn + b) * E + e] -> position of (node_a, node_b) in the node-level CSR
     int4* d_connE = nullptr;   // element-major connectivity, ceil(nn/4) words per element (row-owner kernel)
     void* d_corners = nullptr; // corner records of this block, indexed by the global corner number (plan.cu: k_corners)
     int* d_cornerElem = nullptr;  // rotated 4-node records: element id of each corner
-    PatchProgram prog;
+    int4* d_fanRec = nullptr;     // fan-ordered corner records of the write-once kernel (plan.cu: k_fan_corners)
+    int* d_fanElem = nullptr;     // 4 nodes: element id of each fan-ordered corner
+    bool fanCompact = false;      // 4 nodes: node / element ids as 24-bit differences to the owner, no element array
+    bool fanOK = false;           // the corners of every node chain into fans: the write-once kernel applies
 };
 
 struct BlockTable {  // kernel-side view of all blocks (pattern build)
@@ -92,22 +79,15 @@ struct femb_plan {
     int* d_nrowptr = nullptr;  // node-level CSR row pointers (numNodes + 1)
     int* d_ncols = nullptr;    // node-level CSR column nodes, sorted within a row
     int64_t nnzNode = 0;
-    int* d_adjPtr = nullptr;   // node -> adjacent elements (global element ids), kept for the patch programs
+    int* d_adjPtr = nullptr;   // node -> adjacent elements (global element ids), sorted per node
     int* d_adj = nullptr;
     cudaStream_t ownStream = nullptr, stream = nullptr;
     float buildMs = 0.f;
     int64_t launches = 0;
-    // node patches (shared by all blocks)
-    bool patchesBuilt = false;
-    int patchNodes = 0;          // owned nodes per patch
-    int teamWarps = 2;           // warps that share a patch in the assembly kernel (1 or 2): a patch holds <= 32*teamWarps elements
-    int64_t numPatches = 0;
-    double* d_hintCoords = nullptr;  // optional locality hint (node coordinates at plan time)
-    int* d_order = nullptr;      // patch order: owned nodes of patch p = order[p*patchNodes ...]
-    int* d_nbStart = nullptr;    // (numNodes+1) prefix of node degrees in patch order = first node-block of a node
-    long long* d_pipeStats = nullptr;  // measurement only
-    int debugFlags = 0;                // measurement only
-    int usePatch = 2;            // assembly path: 2 row-owner kernel, 1 write-once patch pipeline, 0 slot-map scatter with FP64 atomics
+    long long* d_rowStats = nullptr;  // measurement builds only (ROWS_TRACE): warp lifetime statistics
+    int assemblyPath = 2;        // 2 row-owner kernel, 0 slot-map scatter with FP64 atomics
+    bool fanCompactAllowed = true;  // option "fan_compact" (tests): 0 keeps the wide fan records even when the differences fit
+    bool useFan = true;          // option "fan_rows": write-once fan kernel where it applies (else the accumulating row-owner kernel)
     int* d_blockAdj = nullptr;   // (numBlocks+1) x numNodes: start of each block's corners in a node's adjacency list (row-owner kernel)
     int* d_rowOrder = nullptr;   // plan-time temporary: balanced row order (plan.cu: k_row_order), node of every thread slot, -1 = padding
     int4* d_slotRec = nullptr;   // balanced row schedule: one record per thread slot (plan.cu: k_slot_records); NULL = node order
@@ -129,7 +109,6 @@ struct femb_plan {
     int* d_bcInfo = nullptr;        // (numNodes) (index of the constrained node + 1) << 9 | position in own row << 2 | DOF bits; 0 = unconstrained
     double* d_bcNodeCnt = nullptr;  // per constrained node: diagonal values (occurrence counts) of its two DOFs
     double* d_bcNodeVal = nullptr;  // per constrained node: prescribed values of its two DOFs
-    unsigned char* d_bcMaskPerm = nullptr;  // the same mask in patch order (padded to a multiple of 16 nodes)
     // scratch for the host-pointer API
     double *s_coords = nullptr, *s_states = nullptr, *s_thick = nullptr, *s_loads = nullptr, *s_K = nullptr,
            *s_R = nullptr, *s_out = nullptr;
@@ -193,14 +172,8 @@ static inline int need_final(const femb_plan* p, const char* who) {
 int exclusive_scan(const int* d_in, int* d_out, int64_t n, cudaStream_t st, int64_t& launches);
 
 bool rows_path_available(const femb_plan* p);
+bool fan_path_available(const femb_plan* p);  // assemble.cu: the write-once fan kernel will run (small-strain model)
 int ensure_slot_maps(femb_plan* p);  // plan.cu: builds the scatter kernels' slot maps on first use
-// true when the write-once patch pipeline will run for this plan (assemble.cu)
-bool patch_path_available(const femb_plan* p, bool wk, bool wr);
-
-// patch programs (plan_patch.cu)
-int build_patches(femb_plan* p, int64_t& launches);
-void free_patches(femb_plan* p);
-bool patch_family_supported(int nn, int nq);
 
 // ---------------------------------------------------------------------------------------------
 // kernel argument blocks

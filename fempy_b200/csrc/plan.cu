@@ -1,4 +1,6 @@
 // Plan: mesh topology + element tables -> node adjacency, sorted CSR pattern, scatter map, BC staging.
+#include <cmath>
+
 #include "femb_internal.h"
 
 using namespace femb;
@@ -261,12 +263,6 @@ __global__ void k_slot_records(long long slots, const int* __restrict__ order, c
     rec[s] = make_int4(i, off, (nrowptr[i + 1] - off) | ((cLast[i] - c0) << 8), c0);
 }
 
-__global__ void k_permute_mask(const int* __restrict__ order, const unsigned char* __restrict__ mask, long long N,
-                               unsigned char* __restrict__ maskPerm) {
-    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos < N) maskPerm[pos] = mask[order[pos]];
-}
-
 // adds the position of each constrained node in its own sorted row to its bcInfo word: (index + 1) << 9 | diagK << 2 | bits
 __global__ void k_bc_diag(long long N, const int* __restrict__ nrowptr, const int* __restrict__ ncols, int* __restrict__ info) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,6 +279,230 @@ __global__ void k_check_bcs(long long nBC, const int* __restrict__ bcDof, const 
     if (t >= nBC) return;
     const int i = bcDof[t] >> 1;
     if (nrowptr[i + 1] == nrowptr[i]) atomicExch(flag, 2);
+}
+
+
+// =============================================================================================
+// table checks of 3- and 4-node blocks (host, at add_block)
+// =============================================================================================
+// Geometric sums S[a][b][d][D] = sum_p w_p / det_p * Gh_d,a Gh_D,b (Gh = adj(J) dN) of one fixed, irregular element:
+// what the assembly kernels integrate, up to the constitutive matrix.
+static void geometric_sums(int nn, int nq, const double* dN, const double* w, const double* X, double* S) {
+    std::fill(S, S + nn * nn * 4, 0.0);
+    for (int p = 0; p < nq; ++p) {
+        const double* d0 = dN + (size_t)(p * 2) * nn;
+        const double* d1 = d0 + nn;
+        double J00 = 0, J01 = 0, J10 = 0, J11 = 0;
+        for (int a = 0; a < nn; ++a) {
+            J00 += d0[a] * X[2 * a];
+            J01 += d0[a] * X[2 * a + 1];
+            J10 += d1[a] * X[2 * a];
+            J11 += d1[a] * X[2 * a + 1];
+        }
+        const double det = J00 * J11 - J01 * J10;
+        for (int a = 0; a < nn; ++a)
+            for (int b = 0; b < nn; ++b) {
+                const double ga[2] = {J11 * d0[a] - J01 * d1[a], J00 * d1[a] - J10 * d0[a]};
+                const double gb[2] = {J11 * d0[b] - J01 * d1[b], J00 * d1[b] - J10 * d0[b]};
+                for (int d = 0; d < 2; ++d)
+                    for (int D = 0; D < 2; ++D) S[((a * nn + b) * 2 + d) * 2 + D] += w[p] / det * ga[d] * gb[D];
+            }
+    }
+}
+
+// The rotated corner records of the row-owner kernel (k_corners) hand every thread its element renumbered cyclically so
+// that the owning node is local node 0, and the kernel evaluates it with the caller's tables as they are.  That is exact
+// only when basis and rule are invariant under a cyclic renumbering of the nodes (counter-clockwise node order, rotation-
+// symmetric rule: the reference's Tri/Quad order 1).  Checked numerically on one irregular element: the matrix of the
+// renumbered element must be the renumbered matrix.
+static bool tables_cyclic_invariant(int nn, int nq, const double* dN, const double* w) {
+    static const double X0[8] = {0.03, -0.02, 1.11, 0.07, 1.26, 0.93, -0.09, 1.17};  // (3 nodes: the first three)
+    std::vector<double> S((size_t)nn * nn * 4), Sr(S.size()), Xr(2 * nn);
+    geometric_sums(nn, nq, dN, w, X0, S.data());
+    double scale = 0.0;
+    for (double v : S) scale = std::max(scale, std::fabs(v));
+    for (int r = 1; r < nn; ++r) {
+        for (int a = 0; a < nn; ++a) {
+            Xr[2 * a] = X0[2 * ((a + r) % nn)];
+            Xr[2 * a + 1] = X0[2 * ((a + r) % nn) + 1];
+        }
+        geometric_sums(nn, nq, dN, w, Xr.data(), Sr.data());
+        for (int a = 0; a < nn; ++a)
+            for (int b = 0; b < nn; ++b)
+                for (int k = 0; k < 4; ++k)
+                    if (!(std::fabs(Sr[(a * nn + b) * 4 + k] - S[(((a + r) % nn) * nn + (b + r) % nn) * 4 + k]) <= 1e-12 * scale)) return false;
+    }
+    return true;
+}
+
+// true when a 4-node block carries the standard bilinear quad -- nodes counter-clockwise from (-1, -1), 2x2 Gauss rule
+// (points (+-1/sqrt 3, +-1/sqrt 3) in any order, unit weights): QuadElement2D order 1 (FEMpy/Elements/QuadElement2D.py:
+// 65-111,181-186) -- for which the row-owner kernel has a closed form
+static bool standard_q4(int nq, const double* dN, const double* w) {
+    if (nq != 4) return false;
+    static const double xs[4] = {-1, 1, 1, -1}, es[4] = {-1, -1, 1, 1};
+    const double g = 0.57735026918962576451, tol = 1e-13;
+    int seen = 0;
+    for (int p = 0; p < 4; ++p) {
+        if (std::fabs(w[p] - 1.0) > tol) return false;
+        const double* d0 = dN + (size_t)(p * 2) * 4;
+        const double* d1 = d0 + 4;
+        const double eta = 1.0 + 4.0 * d0[0], xi = 1.0 + 4.0 * d1[0];  // dN_0/dxi = -(1 - eta)/4, dN_0/deta = -(1 - xi)/4
+        if (std::fabs(std::fabs(xi) - g) > tol || std::fabs(std::fabs(eta) - g) > tol) return false;
+        for (int a = 0; a < 4; ++a)
+            if (std::fabs(d0[a] - 0.25 * xs[a] * (1.0 + es[a] * eta)) > tol || std::fabs(d1[a] - 0.25 * es[a] * (1.0 + xs[a] * xi)) > tol) return false;
+        seen |= 1 << ((xi > 0 ? 1 : 0) | (eta > 0 ? 2 : 0));
+    }
+    return seen == 15;
+}
+
+
+// Fan-ordered corner records of the write-once kernel (assemble_fan.cuh), 3- and 4-node blocks of single-block plans.
+// The corners of a node are chained so that the last node of one corner is the first node of the next (consistently
+// oriented elements around a node form such a fan: an edge is shared by the two elements on either side of it).  Walking
+// the fan, a thread then completes every block of its row in registers -- own block: sum over all corners; edge
+// neighbour: the last block of one corner + the first block of the next; diagonal neighbour: one corner -- and stores it
+// ONCE: no zero-fill, no read-modify-write of shared-memory accumulators.
+//   record: {k_0 | k_1 << 7 | .. | linkNext << 28 | closedLast << 29, node 1, node 2, node 3 (4 nodes) or element id (3 nodes)}
+//   linkNext: the next corner of the node continues this one; closedLast (last corner only): it continues into the first.
+// bad[0] is set when some node's corners cannot be ordered that way (a row position would receive two unlinked
+// contributions: inconsistent element orientation, elements sharing two nodes but no edge); the plan then keeps the
+// accumulating row-owner kernel.
+constexpr int FAN_MAXC = 48;
+__global__ void k_fan_corners(long long N, int nn, const int* __restrict__ cBegin, const int* __restrict__ cEnd,
+                              const int4* __restrict__ rotRec, const int* __restrict__ rotElem, int4* __restrict__ fanRec,
+                              int* __restrict__ fanElem, int* __restrict__ bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int c0 = cBegin[i], nc = cEnd[i] - c0;
+    if (nc <= 0) return;
+    if (nc > FAN_MAXC) {
+        atomicExch(bad, 1);
+        return;
+    }
+    int first[FAN_MAXC], last[FAN_MAXC], order[FAN_MAXC];
+    unsigned slots[FAN_MAXC];
+    bool used[FAN_MAXC], link[FAN_MAXC];
+    for (int k = 0; k < nc; ++k) {
+        const int4 r = rotRec[c0 + k];
+        if (nn == 3) {  // {e, slots << 4, n1, n2}
+            first[k] = r.z;
+            last[k] = r.w;
+            slots[k] = ((unsigned)r.y >> 4) & 0x1fffffu;
+        } else {  // {slots, n1, n2, n3}
+            first[k] = r.y;
+            last[k] = r.w;
+            slots[k] = (unsigned)r.x & 0x0fffffffu;
+        }
+        used[k] = false;
+    }
+    // chains: start at a corner nobody continues into (open fan); when none is left the rest are closed loops
+    int placed = 0, chains = 0;
+    bool closed = false;
+    while (placed < nc) {
+        int start = -1;
+        for (int k = 0; k < nc && start < 0; ++k) {
+            if (used[k]) continue;
+            bool hasPred = false;
+            for (int j = 0; j < nc; ++j) hasPred = hasPred || (!used[j] && j != k && last[j] == first[k]);
+            if (!hasPred) start = k;
+        }
+        bool loop = false;
+        if (start < 0) {
+            loop = true;
+            for (int k = 0; k < nc && start < 0; ++k)
+                if (!used[k]) start = k;
+        }
+        ++chains;
+        int cur = start;
+        while (true) {
+            used[cur] = true;
+            order[placed] = cur;
+            int next = -1;
+            for (int j = 0; j < nc && next < 0; ++j)
+                if (!used[j] && first[j] == last[cur]) next = j;
+            link[placed] = next >= 0;
+            ++placed;
+            if (next < 0) break;
+            cur = next;
+        }
+        if (loop && chains == 1 && placed == nc && last[cur] == first[start]) closed = true;
+    }
+    // every row position other than the node's own may be hit twice only through a link (or the closing wrap)
+    const int diag = (int)(slots[0] & 0x7fu);
+    bool ok = true;
+    for (int a = 0; a < nc && ok; ++a) {
+        const int ka = order[a];
+        ok = ok && (int)(slots[ka] & 0x7fu) == diag;
+        for (int ba = 1; ba < nn && ok; ++ba) {
+            const int sa = (int)((slots[ka] >> (7 * ba)) & 0x7fu);
+            if (sa == diag) ok = false;  // an element naming the node twice
+            for (int b2 = a; b2 < nc && ok; ++b2) {
+                const int kb = order[b2];
+                for (int bb = 1; bb < nn && ok; ++bb) {
+                    if (b2 == a && bb <= ba) continue;
+                    const int sb = (int)((slots[kb] >> (7 * bb)) & 0x7fu);
+                    if (sa != sb) continue;
+                    const bool linked = (b2 == a + 1 && link[a] && ba == nn - 1 && bb == 1) ||
+                                        (closed && a == 0 && b2 == nc - 1 && ba == 1 && bb == nn - 1 && nc > 1);
+                    if (!linked) ok = false;
+                }
+            }
+        }
+    }
+    if (closed && nc == 1) ok = false;
+    if (!ok) {
+        atomicExch(bad, 1);
+        return;
+    }
+    for (int k = 0; k < nc; ++k) {
+        const int4 r = rotRec[c0 + order[k]];
+        const unsigned flags = (link[k] ? 1u << 28 : 0u) | ((closed && k == nc - 1) ? 1u << 29 : 0u);
+        if (nn == 3) {
+            fanRec[c0 + k] = make_int4((int)(slots[order[k]] | flags), r.z, r.w, r.x);
+        } else {
+            fanRec[c0 + k] = make_int4((int)(slots[order[k]] | flags), r.y, r.z, r.w);
+            fanElem[c0 + k] = rotElem[c0 + order[k]];
+        }
+    }
+}
+
+// Compact 4-node fan records: node and element ids as signed 24-bit differences to the owning node's id, so that the
+// element id (thickness index) rides in the same 16 bytes:
+//   {slots | flags, d1 | d2 << 24, d2 >> 8 | d3 << 16, d3 >> 16 | de << 8}      d_k = node_k - i, de = element - i
+// Numberings with some locality fit (|difference| < 2^23); otherwise the plan keeps the wide records + element array.
+__global__ void k_fan_fits(long long N, const int* __restrict__ cBegin, const int* __restrict__ cEnd, const int4* __restrict__ fanRec,
+                           const int* __restrict__ fanElem, int* __restrict__ bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int lim = 1 << 23;
+    for (int c = cBegin[i]; c < cEnd[i]; ++c) {
+        const int4 r = fanRec[c];
+        const long long d[4] = {r.y - i, r.z - i, r.w - i, fanElem[c] - i};
+        for (int k = 0; k < 4; ++k)
+            if (d[k] < -lim || d[k] >= lim) atomicExch(bad, 1);
+    }
+}
+__global__ void k_fan_compact(long long N, const int* __restrict__ cBegin, const int* __restrict__ cEnd, int4* __restrict__ fanRec,
+                              const int* __restrict__ fanElem) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    for (int c = cBegin[i]; c < cEnd[i]; ++c) {
+        const int4 r = fanRec[c];
+        const unsigned d1 = (unsigned)(r.y - (int)i) & 0xffffffu, d2 = (unsigned)(r.z - (int)i) & 0xffffffu;
+        const unsigned d3 = (unsigned)(r.w - (int)i) & 0xffffffu, de = (unsigned)(fanElem[c] - (int)i) & 0xffffffu;
+        fanRec[c] = make_int4(r.x, (int)(d1 | (d2 << 24)), (int)((d2 >> 8) | (d3 << 16)), (int)((d3 >> 16) | (de << 8)));
+    }
+}
+
+// standard linear triangle: N = (1 - xi - eta, xi, eta), centroid rule with weight 1/2 (TriElement2D order 1,
+// FEMpy/Elements/TriElement2D.py:69-169, Quadrature/TriQuad.py:78-86)
+static bool standard_t3(int nq, const double* dN, const double* w) {
+    if (nq != 1 || std::fabs(w[0] - 0.5) > 1e-14) return false;
+    static const double ref[6] = {-1, 1, 0, -1, 0, 1};
+    for (int k = 0; k < 6; ++k)
+        if (std::fabs(dN[k] - ref[k]) > 1e-14) return false;
+    return true;
 }
 
 // =============================================================================================
@@ -338,6 +558,8 @@ extern "C" int femb_plan_add_block(femb_plan* p, int32_t nn, int32_t nq, const d
     b.N.assign(N, N + (size_t)nq * nn);
     b.dN.assign(dNdxi, dNdxi + (size_t)nq * 2 * nn);
     b.w.assign(w, w + nq);
+    if (nn <= 4) b.cyclic = tables_cyclic_invariant(nn, nq, dNdxi, w);
+    b.closedForm = b.cyclic && ((nn == 4 && standard_q4(nq, dNdxi, w)) || (nn == 3 && standard_t3(nq, dNdxi, w)));
     long long* d_conn64 = nullptr;
     const size_t cnt = (size_t)numElems * nn;
     CUDA_TRY(cudaMalloc(&d_conn64, cnt * sizeof(long long)));
@@ -376,7 +598,7 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
     int64_t launches = 0;
     int *d_adjCount = nullptr, *d_candCount = nullptr, *d_candPtr = nullptr, *d_cursor = nullptr;
     int *d_cand = nullptr, *d_deg = nullptr;
-    int*& d_adjPtr = p->d_adjPtr;  // kept: the patch programs walk the node -> element adjacency
+    int*& d_adjPtr = p->d_adjPtr;
     int*& d_adj = p->d_adj;
     CUDA_TRY(cudaMalloc(&d_adjCount, (N + 1) * sizeof(int)));
     CUDA_TRY(cudaMalloc(&d_candCount, (N + 1) * sizeof(int)));
@@ -455,6 +677,36 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
                 launches += 2;
             }
             p->rowsBuilt = true;
+            if (nb == 1 && p->blocks[0].nn <= 4 && p->blocks[0].closedForm && (p->blocks[0].nn == 3 || FEMB_ROT4)) {
+                auto& b = p->blocks[0];
+                CUDA_TRY(cudaMalloc(&b.d_fanRec, std::max<int64_t>(totalAdj, 1) * sizeof(int4)));
+                if (b.nn == 4) CUDA_TRY(cudaMalloc(&b.d_fanElem, std::max<int64_t>(totalAdj, 1) * sizeof(int)));
+                CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
+                k_fan_corners<<<grid_for(N, 128), 128, 0, st>>>(N, b.nn, p->d_blockAdj, p->d_blockAdj + (size_t)N, (const int4*)b.d_corners,
+                                                               b.d_cornerElem, b.d_fanRec, b.d_fanElem, p->d_flag);
+                launches++;
+                int bad = 0;
+                CUDA_TRY(cudaMemcpyAsync(&bad, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                b.fanOK = bad == 0;
+                if (!b.fanOK) {
+                    dfree(b.d_fanRec);
+                    dfree(b.d_fanElem);
+                } else if (b.nn == 4 && p->fanCompactAllowed) {  // element id into the record when the numbering has the locality for it
+                    CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
+                    k_fan_fits<<<grid_for(N, 128), 128, 0, st>>>(N, p->d_blockAdj, p->d_blockAdj + (size_t)N, b.d_fanRec, b.d_fanElem, p->d_flag);
+                    CUDA_TRY(cudaMemcpyAsync(&bad, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    launches++;
+                    if (!bad) {
+                        k_fan_compact<<<grid_for(N, 128), 128, 0, st>>>(N, p->d_blockAdj, p->d_blockAdj + (size_t)N, b.d_fanRec, b.d_fanElem);
+                        CUDA_TRY(cudaStreamSynchronize(st));
+                        launches++;
+                        dfree(b.d_fanElem);
+                        b.fanCompact = true;
+                    }
+                }
+            }
             {  // balanced row schedule: kept only when it saves more than 8 % of the warps' corner iterations
                 const long long windows = (N + ROW_WINDOW - 1) / ROW_WINDOW;
                 unsigned long long* d_iters = nullptr;
@@ -485,9 +737,6 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
-    cudaFree(d_cand);  // the largest temporary: release it before the patch programs allocate theirs
-    d_cand = nullptr;
-    if (p->usePatch == 1) TRY(build_patches(p, launches));  // the patch pipeline is opt-in: its programs are the costly part of a plan
     CUDA_TRY(cudaEventRecord(ev1, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
@@ -529,15 +778,14 @@ extern "C" void femb_plan_destroy(femb_plan* p) {
         b.d_corners = nullptr;
         if (b.d_cornerElem) cudaFree(b.d_cornerElem);
         b.d_cornerElem = nullptr;
+        dfree(b.d_fanRec);
+        dfree(b.d_fanElem);
     }
-    dfree(p->d_hintCoords);
     dfree(p->d_bcMask);
     dfree(p->d_bcInfo);
     dfree(p->d_bcNodeCnt);
     dfree(p->d_bcNodeVal);
-    dfree(p->d_bcMaskPerm);
-    dfree(p->d_pipeStats);
-    free_patches(p);
+    dfree(p->d_rowStats);
     dfree(p->d_bcDof);
     dfree(p->d_bcVal);
     dfree(p->d_bcCount);
@@ -563,40 +811,21 @@ extern "C" int femb_plan_set_stream(femb_plan* p, void* cudaStream, int32_t exte
     return 0;
 }
 
-extern "C" int femb_plan_set_locality_hint(femb_plan* p, const double* coords) {
-    if (!p) return fail("femb_plan_set_locality_hint: plan is NULL");
-    if (p->finalized) return fail("femb_plan_set_locality_hint: plan already finalized");
-    TRY(use_device(p));
-    dfree(p->d_hintCoords);
-    if (!coords) return 0;
-    const size_t n = (size_t)p->numNodes * p->numDim;
-    CUDA_TRY(cudaMalloc(&p->d_hintCoords, n * sizeof(double)));
-    CUDA_TRY(cudaMemcpyAsync(p->d_hintCoords, coords, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
-    return 0;
-}
-
 extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t value) {
     if (!p || !name) return fail("femb_plan_set_option: NULL argument");
-    if (!strcmp(name, "patch_nodes")) {
-        if (p->finalized) return fail("femb_plan_set_option: patch_nodes must be set before finalize");
-        if (value < 0 || value > 1024) return fail("femb_plan_set_option: patch_nodes out of range");
-        p->patchNodes = (int)value;
-    } else if (!strcmp(name, "team_warps")) {
-        if (p->finalized) return fail("femb_plan_set_option: team_warps must be set before finalize");
-        if (value != 1 && value != 2) return fail("femb_plan_set_option: team_warps must be 1 or 2");
-        p->teamWarps = (int)value;
-    } else if (!strcmp(name, "use_patches") || !strcmp(name, "assembly_path")) {
-        if (value < 0 || value > 2) return fail("femb_plan_set_option: assembly_path must be 0 (scatter), 1 (patch pipeline) or 2 (row owner)");
-        if (value == 1 && p->finalized && !p->patchesBuilt) return fail("femb_plan_set_option: the patch pipeline must be selected before finalize");
-        p->usePatch = (int)value;
+    if (!strcmp(name, "assembly_path")) {
+        if (value != 0 && value != 2) return fail("femb_plan_set_option: assembly_path must be 0 (scatter) or 2 (row owner)");
+        p->assemblyPath = (int)value;
+    } else if (!strcmp(name, "fan_compact")) {
+        if (p->finalized) return fail("femb_plan_set_option: fan_compact must be set before finalize");
+        p->fanCompactAllowed = value != 0;
+    } else if (!strcmp(name, "fan_rows")) {
+        if (value != 0 && value != 1) return fail("femb_plan_set_option: fan_rows must be 0 or 1");
+        p->useFan = value != 0;
     } else if (!strcmp(name, "balance_rows")) {
         if (p->finalized) return fail("femb_plan_set_option: balance_rows must be set before finalize");
         if (value < 0 || value > 2) return fail("femb_plan_set_option: balance_rows must be 0 (never), 1 (when it pays) or 2 (always)");
         p->balanceRows = (int)value;
-    } else if (!strcmp(name, "debug_flags")) {
-        p->debugFlags = (int)value;
-
     } else {
         return fail("femb_plan_set_option: unknown option %s", name);
     }
@@ -605,36 +834,23 @@ extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t valu
 
 extern "C" int64_t femb_plan_get_info(const femb_plan* p, const char* name) {
     if (!p || !name) return -1;
-    if (!strcmp(name, "num_patches")) return p->numPatches;
-    if (!strcmp(name, "patch_nodes")) return p->patchNodes;
-    if (!strcmp(name, "team_warps")) return p->teamWarps;
-    if (!strcmp(name, "patch_elems_total")) {
-        int64_t t = 0;
-        for (auto& b : p->blocks) t += b.prog.totalElems;
-        return t;
-    }
-    if (!strcmp(name, "patch_elems_max")) {
-        int64_t t = 0;
-        for (auto& b : p->blocks) t = std::max<int64_t>(t, b.prog.maxElems);
-        return t;
-    }
-    if (!strcmp(name, "patch_blob_bytes")) {
-        int64_t t = 0;
-        for (auto& b : p->blocks) t += b.prog.blobBytes;
-        return t;
-    }
-    if (!strcmp(name, "patch_colours_max")) {
-        int64_t t = 0;
-        for (auto& b : p->blocks) t = std::max<int64_t>(t, b.prog.maxColours);
-        return t;
-    }
-    if (!strcmp(name, "assembly_path")) return p->usePatch;
+    if (!strcmp(name, "assembly_path")) return p->assemblyPath;
     if (!strcmp(name, "rows_path")) return rows_path_available(p) ? 1 : 0;
     if (!strcmp(name, "max_degree")) return p->maxDeg;
     if (!strcmp(name, "rows_balanced")) return p->rowsBalanced ? 1 : 0;
+    if (!strcmp(name, "fan_path")) return fan_path_available(p) ? 1 : 0;
+    if (!strcmp(name, "fan_compact")) return (!p->blocks.empty() && p->blocks[0].fanCompact) ? 1 : 0;
+    if (!strcmp(name, "closed_form_q4")) {
+        bool any = false, all = true;
+        for (auto& b : p->blocks)
+            if (b.nn == 4) {
+                any = true;
+                all = all && b.closedForm;
+            }
+        return (any && all) ? 1 : 0;
+    }
     if (!strcmp(name, "row_iters_node_order")) return p->rowIters[0];
     if (!strcmp(name, "row_iters_balanced")) return p->rowIters[1];
-    if (!strcmp(name, "patch_path")) return patch_path_available(p, true, true) ? 1 : 0;
     return -1;
 }
 
@@ -683,7 +899,7 @@ extern "C" int femb_plan_pattern(femb_plan* p, int64_t* indptr, int64_t* indices
 }
 
 // The element -> CSR slot map of the scatter kernels (4*nn^2 bytes per element) is only built when those kernels are
-// going to run: the row-owner and patch paths never read it.
+// going to run: the row-owner path never reads it.
 int ensure_slot_maps(femb_plan* p) {
     for (auto& b : p->blocks) {
         if (b.d_slot) continue;
@@ -778,12 +994,6 @@ extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const doubl
         CUDA_TRY(cudaMemcpyAsync(p->d_bcNodeVal, val2.data(), val2.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         k_bc_diag<<<grid_for(p->numNodes, 256), 256, 0, p->stream>>>(p->numNodes, p->d_nrowptr, p->d_ncols, p->d_bcInfo);
         CUDA_TRY(cudaStreamSynchronize(p->stream));  // the host vectors go out of scope
-    }
-    if (p->patchesBuilt && p->d_order) {  // the same mask in patch order: each patch bulk-copies its slice
-        const size_t padded = (size_t)p->numPatches * p->patchNodes;
-        TRY(dalloc(&p->d_bcMaskPerm, padded));
-        CUDA_TRY(cudaMemsetAsync(p->d_bcMaskPerm, 0, padded, p->stream));
-        k_permute_mask<<<grid_for(p->numNodes, 256), 256, 0, p->stream>>>(p->d_order, p->d_bcMask, p->numNodes, p->d_bcMaskPerm);
     }
     CUDA_TRY(cudaMalloc(&p->d_bcDof, n * sizeof(int)));
     CUDA_TRY(cudaMalloc(&p->d_bcVal, n * sizeof(double)));

@@ -228,7 +228,6 @@ class GpuLocalAssembler:
         self.device = torch.device("cuda", device)
         self.localCoords = np.ascontiguousarray(np.asarray(coords, dtype=np.float64)[partition.localNodes])
         self.plan = AssemblyPlan(partition.numLocalNodes, 2, 2, device=device)
-        self.plan.setLocalityHint(self.localCoords)
         for elType, conn in partition.localConn.items():
             N, dN, w = elementTables[elType]
             self.plan.addBlock(N, dN, w, conn)

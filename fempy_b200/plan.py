@@ -90,13 +90,6 @@ class AssemblyPlan:
         else:
             check(self._lib.femb_plan_set_stream(self._h, C.c_void_p(int(cudaStream)), 1))
 
-    def setLocalityHint(self, coords):
-        """Node coordinates used only to cut spatially compact node patches (before finalize)."""
-        coords = as_f64(coords)
-        if coords.shape != (self.numNodes, self.numDim):
-            raise ValueError("coords must be numNodes x numDim")
-        check(self._lib.femb_plan_set_locality_hint(self._h, dptr(coords)))
-
     def setOption(self, name, value):
         check(self._lib.femb_plan_set_option(self._h, name.encode(), int(value)))
 

@@ -1,30 +1,19 @@
-"""FEMpyProblem on the B200 path.
+"""The reference's FEMpyProblem on the B200 path.
 
 `B200AssemblyMixin` overrides exactly the three methods of the reference's problem class that make up
 the assembly hot path -- `_assembleMatrix`, `_assembleResidual` (reference FEMpy/Problem.py:565-661)
 and `computeFunction` (:282-355) -- and routes them through one fused CUDA assembly call.  It only
 reads what SURVEY.md section 8b lists (model.nodeCoords, model.elements[type][...], model.dvs,
-constitutive parameters, problem.states / getBCs() / loads), so it can be mixed into the reference's own
-`FEMpyProblem` as well as into the host-side mirror below.
-
-`FEMpyProblem` here is that mirror: same public methods, attributes and error behaviour as the
-reference class (Problem.py:38-692), minus file output, so the parity tests read like the
-reference's own tests on a machine where the reference's dependencies are not installed.
+constitutive parameters, problem.states / getBCs() / loads), so it is mixed into the reference's own
+`FEMpyProblem` (`b200ProblemClass`, `install`).  Everything else of the load case -- solve driver,
+caching flags, BC / load bookkeeping, output -- stays the reference's code.
 """
-import copy
-import time
-
 import numpy as np
 from scipy.sparse import csr_array
 
 from . import assembly_utils as AssemblyUtils
 from .constitutive import FUNC_MASS, FUNC_VON_MISES, PLANE_STRAIN, PLANE_STRESS
 from .plan import AssemblyPlan
-
-try:  # same optional dependency as the reference (Problem.py:26-29); the solve is outside the hot path
-    from pypardiso import factorized
-except ModuleNotFoundError:
-    from scipy.sparse.linalg import factorized
 
 
 def materialFor(constitutiveModel):
@@ -45,7 +34,6 @@ def planFor(model, device=0):
     if plan is not None:
         return plan
     plan = AssemblyPlan(model.numNodes, model.numDim, model.constitutiveModel.numStates, device=device)
-    plan.setLocalityHint(model.nodeCoords)
     for elType, elData in model.elements.items():
         el = elData["elementObject"]
         pts = np.atleast_2d(el.getIntegrationPointCoords())
@@ -156,152 +144,14 @@ class B200AssemblyMixin:
         return functionValues
 
 
-class _ProblemBase:
-    """Everything of the reference's FEMpyProblem that is NOT the hot path (Problem.py:53-504),
-    restated without the mdolab-baseclasses dependency."""
-
-    def __init__(self, name, model, options=None):
-        self.name = name
-        self.model = model
-        self.states = np.zeros((self.numNodes, self.numStates))
-        self.Jacobian = None
-        self.jacUpToDate = False
-        self.factorizedJac = None
-        self.jacIsFactorized = False
-        self.Res = np.zeros(self.numNodes * self.numStates)
-        self.resUpToDate = False
-        self.solveCounter = 0
-        self.BCs = {}
-        self.loads = {}
-        self.options = {"printTiming": False, "outputDir": None, "outputFormat": None, "outputFunctions": None}
-        for key, value in (options or {}).items():
-            if key not in self.options:
-                raise KeyError(f"Option {key} is not a valid FEMpyProblem option")
-            self.options[key] = value
-        for option in ("outputDir", "outputFormat", "outputFunctions"):
-            if self.options[option] is None:
-                self.options[option] = self.model.getOption(option)
-
-    def getOption(self, name):
-        return self.options[name]
-
-    def setOption(self, name, value):
-        self.options[name] = value
-
-    constitutiveModel = property(lambda self: self.model.constitutiveModel)
-    isLinear = property(lambda self: self.constitutiveModel.isLinear)
-    numDim = property(lambda self: self.model.numDim)
-    numNodes = property(lambda self: self.model.numNodes)
-    numDOF = property(lambda self: self.model.numDOF)
-    numStates = property(lambda self: self.constitutiveModel.numStates)
-    elements = property(lambda self: self.model.elements)
-
-    def solve(self):
-        """Residual + Jacobian assembly, linear solve, state increment (Problem.py:137-169)."""
-        times = {"Start": time.time()}
-        self.updateResidual(applyBCs=True)
-        times["ResAssembled"] = time.time()
-        self.updateJacobian(applyBCs=True)
-        times["JacAssembled"] = time.time()
-        update = self.solveJacLinear(-self.Res)
-        times["Solved"] = time.time()
-        self.incrementState(update)
-        if self.getOption("printTiming"):
-            self._printTiming(times)
-        self.solveCounter += 1
-        return times
-
-    def solveJacLinear(self, RHS):
-        if not self.jacUpToDate:
-            self.updateJacobian()
-        if self.factorizedJac is None or not self.jacIsFactorized:
-            self.factorizedJac = factorized(self.Jacobian.tocsc())
-            self.jacIsFactorized = True
-        return self.factorizedJac(RHS)
-
-    def incrementState(self, update):
-        self.states += update if update.shape == self.states.shape else update.reshape(self.states.shape)
-        self.markResOutOfDate()
-        if not self.isLinear:
-            self.markJacOutOfDate()
-
-    def updateState(self, update):
-        self.states[:] = update if update.shape == self.states.shape else update.reshape(self.states.shape)
-        self.markResOutOfDate()
-        if not self.isLinear:
-            self.markJacOutOfDate()
-
-    def reset(self):
-        self.updateState(np.zeros((self.numNodes, self.numStates)))
-
-    def updateResidual(self, applyBCs=True):
-        if not self.resUpToDate:
-            self.Res = self._assembleResidual(self.states, applyBCs=applyBCs)
-            self.markResUpToDate()
-
-    def updateJacobian(self, applyBCs=True):
-        if not self.jacUpToDate:
-            self.Jacobian = self._assembleMatrix(self.states, applyBCs=applyBCs)
-            self.markJacUpToDate()
-            self.jacIsFactorized = False
-
-    def markResOutOfDate(self):
-        self.resUpToDate = False
-
-    def markJacOutOfDate(self):
-        self.jacUpToDate = False
-
-    def markResUpToDate(self):
-        self.resUpToDate = True
-
-    def markJacUpToDate(self):
-        self.jacUpToDate = True
-
-    def _nodeDofLists(self, nodeInds, dof, value, scale=1.0):
-        if isinstance(nodeInds, (int, np.integer)):
-            nodeInds = [nodeInds]
-        if isinstance(dof, (int, np.integer)):
-            dof = [dof]
-        if isinstance(value, (float, int)):
-            value = [value] * len(dof)
-        elif len(value) != len(dof):
-            raise Exception("value should be a single entry or a list of values the same length as the DOF list.")
-        dofNodes, valDOF = [], []
-        for i in range(len(nodeInds)):
-            for j in range(len(dof)):
-                dofNodes.append(int(nodeInds[i]) * self.numStates + dof[j])
-                valDOF.append(value[j] / scale)
-        return dofNodes, valDOF
-
-    def addFixedBCToNodes(self, name, nodeInds, dof, value):
-        """Problem.py:357-402."""
-        dofNodes, valDOF = self._nodeDofLists(nodeInds, dof, value)
-        self.BCs[name] = {"DOF": dofNodes, "Value": valDOF}
-
-    def addLoadToNodes(self, name, nodeInds, dof, value, totalLoad=False):
-        """Problem.py:404-453."""
-        scale = float(len(nodeInds)) if totalLoad else 1.0
-        dofNodes, valDOF = self._nodeDofLists(nodeInds, dof, value, scale)
-        self.loads[name] = {"DOF": dofNodes, "Value": valDOF}
-
-    def addBodyLoad(self, name, loadingFunction):
-        raise NotImplementedError("Body loads are not yet implemented, sorry :(")
-
-    def getBCs(self):
-        BCs = copy.deepcopy(self.model.BCs)
-        BCs.update(self.BCs)
-        return BCs
-
-    def getElementStates(self, elementType):
-        """(E, n, s) nodal states per element (Problem.py:485-504), as one fancy-index gather."""
-        return self.states[self.elements[elementType]["connectivity"]]
-
-    def _printTiming(self, times):
-        print(f"\n Timing information for FEMpy problem: {self.name}")
-        print("Residual Assembly: {:11.5e} s".format(times["ResAssembled"] - times["Start"]))
-        print("Jacobian Assembly: {:11.5e} s".format(times["JacAssembled"] - times["ResAssembled"]))
-        print("Linear Solution:   {:11.5e} s".format(times["Solved"] - times["JacAssembled"]))
+def b200ProblemClass(referenceProblemClass):
+    """`class B200Problem(B200AssemblyMixin, FEMpyProblem)` for the reference's (or any compatible) problem class."""
+    return type("B200Problem", (B200AssemblyMixin, referenceProblemClass), {"__doc__": "FEMpyProblem whose K / R assembly and element functions run on the B200."})
 
 
-class FEMpyProblem(B200AssemblyMixin, _ProblemBase):
-    """Drop-in for the reference's FEMpyProblem with the assembly hot path on the GPU."""
+def install(FEMpy):
+    """Make `FEMpyModel.addProblem` of an imported reference package create B200 problems (FEMpy/Model.py:374-385
+    instantiates the module-level name `FEMpyProblem`).  Returns the new problem class."""
+    cls = b200ProblemClass(FEMpy.Problem.FEMpyProblem)
+    FEMpy.Model.FEMpyProblem = cls
+    return cls

@@ -76,31 +76,27 @@ int femb_plan_create(int64_t numNodes, int32_t numDim, int32_t numStates, int32_
 int femb_plan_add_block(femb_plan* plan, int32_t nodesPerElem, int32_t numQuad, const double* N, const double* dNdxi,
                         const double* w, int64_t numElems, const int64_t* conn);
 
-/* builds the node->element adjacency, the sorted structural CSR pattern, the corner records of the row-owner
- * kernel, the element scatter map of the fallback kernels and (assembly_path 1 only) the node-patch programs */
+/* builds the node->element adjacency, the sorted structural CSR pattern and the corner records of the row-owner
+ * kernel (the element scatter map of the fallback kernels is built on their first use) */
 int femb_plan_finalize(femb_plan* plan);
 void femb_plan_destroy(femb_plan* plan);
 
-/* optional, before finalize: node coordinates (numNodes, numDim) used ONLY to order nodes for locality when
- * the node patches of the opt-in patch pipeline are cut (Morton order); results do not depend on it */
-int femb_plan_set_locality_hint(femb_plan* plan, const double* coords);
-
 /* options:
- *   "assembly_path" (alias "use_patches"): 2 (default) row-owner kernel -- one thread per node row, one launch per
- *       element block, no atomics, bit-reproducible; 3/4/6/9/10-node elements, node degree <= 48, else the scatter
- *       kernels run; 1: patch pipeline (3/4-node elements, must be chosen before finalize); 0: slot-map scatter
- *       kernels with FP64 atomics (every family);
- *   "patch_nodes" (owned nodes per patch, before finalize; 0 = default), "team_warps" (1 or 2, before finalize):
- *       patch pipeline only;
+ *   "assembly_path": 2 (default) row-owner kernel -- one thread per node row, one launch per element block, no
+ *       atomics, bit-reproducible; 3/4/6/9/10-node elements, node degree <= 48, else the scatter kernels run;
+ *       0: slot-map scatter kernels with FP64 atomics (every family);
+ *   "fan_rows": 1 (default) single-block plans of 3- / 4-node elements with the reference's order-1 tables run the
+ *       write-once fan kernel for the small-strain model (corners of a node chained into fans, every row block finished
+ *       in registers and stored once); 0: the accumulating row-owner kernel.  "fan_compact" (before finalize): 0 keeps the
+ *       wide fan records even when node / element ids fit 24-bit differences (tests);
  *   "balance_rows" (before finalize): row schedule of the row-owner kernel -- 0 threads take nodes in node order,
  *       1 (default) nodes of every 256-node window are ordered by their number of adjacent elements when that saves
- *       more than 8 % of the warps' element iterations (9-node quads, mixed meshes), 2 always; results do not depend on it;
- *   "debug_flags": measurement builds only */
+ *       more than 8 % of the warps' element iterations (9-node quads, mixed meshes), 2 always; results do not depend on it */
 int femb_plan_set_option(femb_plan* plan, const char* name, int64_t value);
 /* "assembly_path", "rows_path" (1: the row-owner kernel will run), "max_degree", "rows_balanced", "row_iters_node_order",
- * "row_iters_balanced" (sum over warps of the longest element walk in either schedule), "patch_path", "num_patches",
- * "patch_nodes", "team_warps", "patch_elems_total", "patch_elems_max", "patch_blob_bytes", "patch_colours_max";
- * -1 for an unknown name */
+ * "row_iters_balanced" (sum over warps of the longest element walk in either schedule), "closed_form_q4" (1: every
+ * 4-node block carries the standard bilinear tables and runs the closed-form kernel), "fan_path" (1: the write-once fan
+ * kernel will run for the small-strain model), "fan_compact"; -1 for an unknown name */
 int64_t femb_plan_get_info(const femb_plan* plan, const char* name);
 
 /* external != 0: run the plan's kernels on the caller's CUDA stream (e.g.
@@ -151,9 +147,9 @@ int femb_assemble_dev(femb_plan* plan, const double* d_coords, const double* d_s
 int femb_plan_profile(femb_plan* plan, int32_t enable);
 int femb_plan_profile_read(femb_plan* plan, double* sumMs, int64_t* count);
 
-/* measurement only: per-CTA cycle counters of the pipeline roles.  enable != 0 / out == NULL switches
- * the counters on (0 off); out != NULL copies up to `capacity` int64 values (16 per CTA) back. */
-int femb_plan_pipe_stats(femb_plan* plan, int32_t enable, int64_t* out, int64_t capacity);
+/* measurement builds only (-DROWS_TRACE=1): warp lifetime statistics of the row-owner kernel.  enable != 0 /
+ * out == NULL switches the counters on (0 off); out != NULL copies up to `capacity` int64 values back. */
+int femb_plan_row_stats(femb_plan* plan, int32_t enable, int64_t* out, int64_t capacity);
 
 /* ---- element functions: FEMpyProblem.computeFunction / Element.computeFunction
  * (FEMpy/Problem.py:282-355, FEMpy/Elements/Element.py:163-273).  out: (numElems) or (sum_b E_b*P_b)

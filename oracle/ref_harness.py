@@ -1,8 +1,9 @@
 """Import and drive the UNMODIFIED reference (FEMpy at /root/reference) inside the build container.
 
-TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  /root/reference does not exist on the GPU box, so nothing
-run there may import this module; it is used by ``oracle/gen_golden.py`` (fixture generation) and by
-the ``-m "not gpu"`` tests that pin the oracle, which skip when the reference is absent.
+TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  /root/reference does not exist on the GPU box; there the
+pip-installed copy under ``oracle/_ref`` (``oracle/make_ref.sh``, git-ignored) is used.  Users:
+``oracle/gen_golden.py`` (fixture generation), ``oracle/ref_timing.py`` (the timed CPU baseline of bench.py)
+and the tests that pin the oracle, which skip when no reference is found.
 
 Three stub packages under ``oracle/stubs`` (baseclasses, meshio, parameterized) replace the
 reference's un-installed dependencies; the reference sources themselves are
@@ -11,8 +12,20 @@ imported from where they lie and are never copied.
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("FEMPY_REFERENCE_ROOT", "/root/reference")
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STUBS = os.path.join(_HERE, "stubs")
+
+
+def _find_reference():
+    """The reference checkout in the build container, else the pip-installed copy oracle/make_ref.sh left in
+    oracle/_ref (git-ignored, travels to the GPU box)."""
+    for cand in (os.environ.get("FEMPY_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "FEMpy", "Problem.py")):
+            return cand
+    return os.environ.get("FEMPY_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def available():

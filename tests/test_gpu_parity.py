@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 from scipy.sparse import csr_array
 
-from fempy_b200 import AssemblyPlan, AssemblyUtils, FEMpyModel, meshes
+from fempy_b200 import AssemblyPlan, AssemblyUtils, meshes
+from hostmirror import FEMpyModel
 from oracle import fem_oracle as fo
 from test_oracle_golden import COO_COLS, COO_DOF, COO_MATS, COO_ROWS, COO_VALS, KNOWN_QUAD_K, KNOWN_QUAD_X, two_quad_problem
 from util import ELEMENT_FOR, FAMILY_ELEMENT, MAT, build_problem, golden, make_cm, mesh_case, mesh_case_names, oracle_blocks, relerr
@@ -417,21 +418,19 @@ def test_full_size_properties(elType, n, label):
     assert np.abs(K2.data - K.data).max() < 1e-13 * scale
 
 
-# ---- the assembly paths: row-owner kernel (default), write-once patch pipeline (opt-in), slot-map scatter with FP64
-#      atomics (general fallback: several element blocks, 6/9/10/16-node families) ---------------------------------------
-PATHS = {"scatter": 0, "patch": 1, "rows": 2}
+# ---- the assembly paths: row-owner kernel (default), slot-map scatter with FP64 atomics (general fallback: 16-node
+#      families, node degree above the row-owner limit) ------------------------------------------------------------------
+PATHS = {"scatter": 0, "rows": 2}
 
 
-def _raw_plan(elType, coords, conn, hint=True, patchNodes=None, path="rows", teamWarps=None, balance=None):
+def _raw_plan(elType, coords, conn, path="rows", balance=None, fan=None, fanCompact=None):
     el = ELEMENT_FOR[elType]()
     plan = AssemblyPlan(coords.shape[0])
-    if hint:
-        plan.setLocalityHint(coords)
     plan.setOption("assembly_path", PATHS[path])
-    if patchNodes is not None:
-        plan.setOption("patch_nodes", patchNodes)
-    if teamWarps is not None:
-        plan.setOption("team_warps", teamWarps)
+    if fan is not None:
+        plan.setOption("fan_rows", fan)
+    if fanCompact is not None:
+        plan.setOption("fan_compact", fanCompact)
     if balance is not None:
         plan.setOption("balance_rows", balance)
     N_, dN, w = el.tables()
@@ -495,22 +494,6 @@ def test_default_path_matches_scatter_path_and_oracle(elType, n):
     plan.close()
 
 
-@pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29)])
-@pytest.mark.parametrize("hint", [True, False])
-@pytest.mark.parametrize("patchNodes,teamWarps", [(5, 1), (20, 1), (40, 2), (64, 2), (1000, 2)])
-def test_patch_pipeline_matches_oracle(elType, n, hint, patchNodes, teamWarps):
-    """opt-in path: persistent kernel of self-prefetching warp teams over node patches = 1 launch"""
-    case = _path_case(elType, n)
-    plan = _raw_plan(elType, case[0], case[1], hint, patchNodes, path="patch", teamWarps=teamWarps)
-    pn = -(-patchNodes // 4) * 4
-    assert plan.info("patch_nodes") == pn and plan.info("num_patches") == -(-case[0].shape[0] // pn)
-    onPatchPath = plan.info("patch_path") == 1
-    if not onPatchPath:  # patches with more elements than a team has threads fall back to the scatter kernels
-        assert plan.info("patch_elems_max") > 32 * teamWarps
-    _check_against_oracle(plan, elType, case, launchesExpected=1 if onPatchPath else 3)
-    plan.close()
-
-
 def _renumbered(case, seed=3):
     """the same mesh with randomly permuted node numbers (no locality in the numbering, irregular row order)"""
     coords, conn, states, thick, loads, bcDOF, bcVal = case
@@ -533,7 +516,7 @@ def test_row_owner_kernel_matches_oracle(elType, n, renumber, balance):
     if renumber:
         case = _renumbered(case)
     plan = _raw_plan(elType, case[0], case[1], path="rows", balance=balance)
-    assert plan.info("rows_path") == 1 and plan.info("num_patches") == 0  # no patch programs are built for this path
+    assert plan.info("rows_path") == 1
     assert plan.info("rows_balanced") == (1 if balance == 2 else 0)
     assert 0 < plan.info("row_iters_balanced") <= plan.info("row_iters_node_order")
     _check_against_oracle(plan, elType, case, launchesExpected=1)
@@ -548,6 +531,102 @@ def test_row_owner_kernel_matches_oracle(elType, n, renumber, balance):
     Ro = fo.assemble_residual(blocks, coords, 50 * states, thick, 1, MAT["E"], MAT["nu"], loads, bcDOF, bcVal, nonlinear=True)
     assert relerr(K, Ko.data) < TOL and relerr(R, Ro) < TOL
     plan.close()
+
+
+@pytest.mark.parametrize("elType,n", [("quad", 37), ("triangle", 29)])
+@pytest.mark.parametrize("renumber", [False, True])
+@pytest.mark.parametrize("fan,compact", [(1, 1), (1, 0), (0, 1)])
+def test_fan_kernel_matches_oracle(elType, n, renumber, fan, compact):
+    """write-once fan kernel (single block of 3- / 4-node elements, small strain): corners of a node chained into fans,
+    every row block finished in registers and stored once; compact (24-bit differences, element id inline) and wide
+    records; fan_rows = 0 runs the accumulating row-owner kernel on the same plan"""
+    case = _path_case(elType, n)
+    if renumber:
+        case = _renumbered(case)
+    plan = _raw_plan(elType, case[0], case[1], fan=fan, fanCompact=compact)
+    assert plan.info("rows_path") == 1 and plan.info("fan_path") == fan
+    assert plan.info("fan_compact") == (1 if (compact and elType == "quad") else 0)
+    K1, R1 = _check_against_oracle(plan, elType, case, launchesExpected=1)
+    plan.setOption("fan_rows", 1 - fan)  # the other kernel on the same plan: same values to rounding
+    mat = make_cm(0).material()
+    K0, R0 = plan.assemble(case[0], case[2], case[3], mat, case[5], case[6], True, case[4])
+    assert relerr(K1, K0) < 1e-13 and relerr(R1, R0) < 1e-13
+    # K only / R only variants
+    Kk, _ = plan.assemble(case[0], case[2], case[3], mat, case[5], case[6], True, case[4], wantR=False)
+    _, Rr = plan.assemble(case[0], case[2], case[3], mat, case[5], case[6], True, case[4], wantK=False)
+    np.testing.assert_array_equal(Kk, K0)
+    np.testing.assert_array_equal(Rr, R0)
+    plan.close()
+
+
+def _check_small(coords, conn, elType, expectFan, expectRows=1):
+    N = coords.shape[0]
+    numEl = conn[elType].shape[0]
+    rng = np.random.default_rng(5)
+    case = (coords, conn, 1e-3 * rng.random((N, 2)), rng.random(numEl) + 0.5, rng.random(2 * N), np.array([0, 1, 3]), np.array([1e-4, 0.0, 2e-4]))
+    plan = _raw_plan(elType, coords, conn)
+    assert plan.info("rows_path") == expectRows and plan.info("fan_path") == expectFan
+    _check_against_oracle(plan, elType, case, launchesExpected=1 if expectRows else 3)
+    plan.close()
+
+
+def test_fan_kernel_open_fans_bow_ties_and_fallbacks():
+    """fans that are open (boundary nodes), several fans at one node (two quads touching in a point), and meshes whose
+    corners do not chain (one element with reversed orientation): the plan falls back to the accumulating kernel"""
+    # 2 x 1 quads: every node has an open fan
+    coords, conn = meshes.quad4_grid(2, 1)
+    _check_small(coords + 0.01 * np.random.default_rng(1).random(coords.shape), conn, "quad", expectFan=1)
+    # bow tie: two quads sharing only node 2
+    coords = np.array([[0.0, 0.0], [1.0, 0.1], [1.1, 1.0], [0.0, 1.2], [2.2, 1.1], [2.3, 2.0], [1.2, 2.1]])
+    conn = {"quad": np.array([[0, 1, 2, 3], [2, 4, 5, 6]])}
+    _check_small(coords, conn, "quad", expectFan=1)
+    # 3 x 3 quads with one element listed clockwise: its corners do not chain with their neighbours
+    coords, conn = meshes.quad4_grid(3, 3)
+    coords = coords + 0.01 * np.random.default_rng(2).random(coords.shape)
+    q = conn["quad"].copy()
+    q[4] = q[4][[0, 3, 2, 1]]
+    _check_small(coords, {"quad": q}, "quad", expectFan=0)
+    # triangles: a closed fan of 5 around node 0 and the same fan with one triangle reversed
+    ang = 2 * np.pi * np.arange(5) / 5
+    coords = np.vstack(([[0.0, 0.0]], np.stack((np.cos(ang), np.sin(ang)), axis=1) * (1.0 + 0.1 * np.cos(2 * ang))[:, None]))
+    tri = np.stack((np.zeros(5, dtype=np.int64), 1 + np.arange(5), 1 + (np.arange(5) + 1) % 5), axis=1)
+    _check_small(coords, {"triangle": tri}, "triangle", expectFan=1)
+    tri2 = tri.copy()
+    tri2[2] = tri2[2][[0, 2, 1]]
+    _check_small(coords, {"triangle": tri2}, "triangle", expectFan=0)
+
+
+def test_tables_without_cyclic_symmetry_leave_the_row_owner_path():
+    """the rotated corner records need basis + rule invariant under cyclic renumbering; a 4-node block whose tables are
+    in tensor order (0,1,2,3 = BL,BR,TL,TR) is not: the plan runs the scatter kernels for it and stays exact"""
+    coords, conn = meshes.quad4_grid(9, 7)
+    coords = coords + 0.01 * np.random.default_rng(3).random(coords.shape)
+    perm = [0, 1, 3, 2]
+    N_, dN, w = ELEMENT_FOR["quad"]().tables()
+    connT = conn["quad"][:, perm]  # tensor-ordered connectivity goes with tensor-ordered tables
+    N = coords.shape[0]
+    rng = np.random.default_rng(6)
+    states, thick, loads = 1e-3 * rng.random((N, 2)), rng.random(63) + 0.5, rng.random(2 * N)
+    bcDOF, bcVal = np.array([0, 1, 5]), np.array([0.0, 1e-4, 0.0])
+    plan = AssemblyPlan(N)
+    plan.addBlock(N_[:, perm], dN[:, :, perm], w, connT)
+    plan.finalize()
+    assert plan.info("rows_path") == 0 and plan.info("fan_path") == 0 and plan.info("closed_form_q4") == 0
+    K, R = plan.assemble(coords, states, thick, make_cm(0).material(), bcDOF, bcVal, True, loads)
+    blocks = oracle_blocks(conn)
+    Ko = fo.assemble_matrix(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], bcDOF, dropZeros=False)
+    Ko.sort_indices()
+    Ro = fo.assemble_residual(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], loads, bcDOF, bcVal)
+    np.testing.assert_array_equal(plan.pattern()[1], Ko.indices)
+    assert relerr(K, Ko.data) < TOL and relerr(R, Ro) < TOL
+    # a rule with unequal weights breaks the symmetry as well; the same rule with the standard tables keeps it
+    w2 = w * np.array([1.0, 1.1, 0.9, 1.0])
+    plan2 = AssemblyPlan(N)
+    plan2.addBlock(N_, dN, w2, conn["quad"])
+    plan2.finalize()
+    assert plan2.info("rows_path") == 0
+    plan.close()
+    plan2.close()
 
 
 @pytest.mark.parametrize("order", [("quad", "triangle"), ("triangle", "quad")])
@@ -571,7 +650,6 @@ def test_mixed_mesh_row_owner_matches_oracle(order, balance):
     bcDOF = np.concatenate((2 * left, 2 * left + 1, 2 * left[:2]))
     bcVal = rng.random(bcDOF.size) * 1e-4
     plan = AssemblyPlan(N)
-    plan.setLocalityHint(coords)
     plan.setOption("balance_rows", balance)
     for elType, c in conn.items():
         plan.addBlock(*ELEMENT_FOR[elType]().tables(), c)
@@ -611,8 +689,7 @@ def test_high_degree_node_falls_back_to_scatter_kernels():
     plan.close()
 
 
-@pytest.mark.parametrize("path", ["rows", "patch"])
-def test_write_once_path_is_deterministic(path):
+def test_write_once_path_is_deterministic(path="rows"):
     """write-once assembly has a fixed summation order: two runs are bit-identical"""
     coords, conn = meshes.quad4_grid(200, 150)
     N = coords.shape[0]
@@ -632,7 +709,7 @@ def test_write_once_path_is_deterministic(path):
 def test_isolated_nodes_get_minus_load():
     coords = np.array([[0.0, 0.0], [2.0, 0.1], [2.2, 1.0], [0.1, 1.5], [5.0, 5.0], [6.0, 7.0]])
     conn = {"quad": np.array([[0, 1, 2, 3]])}
-    for path in ("rows", "patch", "scatter"):
+    for path in ("rows", "scatter"):
         plan = _raw_plan("quad", coords, conn, path=path)
         loads = np.arange(12.0)
         _, R = plan.assemble(coords, np.zeros((6, 2)), np.ones(1), make_cm(0).material(), applyBCs=False, loads=loads)

@@ -8,7 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from fempy_b200 import Constitutive, Elements, FEMpyModel, meshes  # noqa: E402
+from fempy_b200 import Constitutive, Elements, meshes  # noqa: E402
+from hostmirror import FEMpyModel  # noqa: E402
 from oracle import fem_oracle as fo  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")

@@ -40,7 +40,6 @@ for mode, elType, n in (("halo", "quad", 96), ("halo", "triangle", 70), ("exchan
     dist.all_gather_object(gathered, (da.blockIndptr, da.blockIndices, Kb.cpu().numpy(), Rb.cpu().numpy()))
     if rank == 0:
         plan = AssemblyPlan(N, device=local)
-        plan.setLocalityHint(coords)
         plan.addBlock(*el.tables(), conn[elType])
         plan.finalize()
         Kref, Rref = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)

@@ -10,7 +10,7 @@ from fempy_b200._lib import iptr, check
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 coords, conn = meshes.quad4_grid(n, n)
 N = coords.shape[0]; E = n * n
-plan = AssemblyPlan(N); plan.setLocalityHint(coords)
+plan = AssemblyPlan(N)
 Nn, dN, w = Elements.QuadElement2D(1).tables(); plan.addBlock(Nn, dN, w, conn["quad"]); plan.finalize()
 left = meshes.edge_nodes(coords, x=0.0); bc = np.concatenate((2 * left, 2 * left + 1)); plan.setBCs(bc, np.zeros(bc.size))
 dev = torch.device("cuda")
@@ -23,11 +23,11 @@ lib = _lib.load()
 for _ in range(3):
     plan.assembleDev(dc, ds, dt, mat, True, dl, dK, dR)
 torch.cuda.synchronize()
-check(lib.femb_plan_pipe_stats(plan.handle, 1, None, 0))
+check(lib.femb_plan_row_stats(plan.handle, 1, None, 0))
 flush.zero_(); flush.sum(); torch.cuda.synchronize()
 plan.assembleDev(dc, ds, dt, mat, True, dl, dK, dR); plan.sync(); torch.cuda.synchronize()
 out = np.zeros(16 * 256, dtype=np.int64)
-check(lib.femb_plan_pipe_stats(plan.handle, 1, iptr(out), out.size))
+check(lib.femb_plan_row_stats(plan.handle, 1, iptr(out), out.size))
 warps = out[1]
 print(f"nx {n}: warps {warps}, lifetime cycles mean {out[0] / max(warps, 1):.0f} min {out[5]} max {out[2]}, first start -> last end {1e-3 * (out[4] - out[3]):.1f} us")
 print("starts per us:", out[16:80][: int(1e-3 * (out[4] - out[3])) + 2].tolist())

