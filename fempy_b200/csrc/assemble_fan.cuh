@@ -63,6 +63,14 @@ __device__ __forceinline__ int4 ld_stream(const int4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+// neighbour states: volatile so that the compiler keeps the requests where they are written -- at the top of a corner,
+// ahead of the record prefetch -- instead of sinking them next to their use at the end of it (lower register pressure,
+// but the full memory latency in every corner)
+__device__ __forceinline__ double2 ld_early(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ int ld_stream(const int* p) {
     int v;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -92,13 +100,27 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
         ownX = __ldg(A.coords + i);
         ownU = __ldg(A.states + i);
     }
-    // first corner's record (and element id) are requested before anything waits
+    // Software pipeline over the corners: a corner's record is requested one corner ahead, and the coordinates of its
+    // nodes as soon as the current corner has finished its geometry (its own coordinates are differences by then), so the
+    // dependent chain record -> coordinates -> geometry waits on memory for the first corner only.
     int4 rec = make_int4(0, 0, 0, 0);
     int el = 0;
     if (c0 < c1) {
         rec = ld_stream(A.rec + c0);
         if (NN == 4 && !CMP) el = ld_stream(A.elem + c0);
     }
+    // node ids / element id of a record (CMP: four signed 24-bit differences to my node id)
+    auto decode = [&](const int4 r, const int relem, int& n1, int& n2, int& n3, int& e) {
+        n1 = r.y, n2 = r.z, n3 = r.w;  // 3 nodes: the fourth word is the element id
+        e = NN == 4 ? relem : r.w;
+        if constexpr (CMP) {
+            const int me = (int)i;
+            e = me + (r.w >> 8);
+            n3 = me + ((int)(__funnelshift_r((unsigned)r.z, (unsigned)r.w, 16) << 8) >> 8);
+            n2 = me + ((int)(__funnelshift_r((unsigned)r.y, (unsigned)r.z, 24) << 8) >> 8);
+            n1 = me + ((r.y << 8) >> 8);
+        }
+    };
     const int base = __shfl_sync(0xffffffffu, off, 0);
     const int ownStart = 2 * (off - base);  // my first position in the warp's run of values
     auto swz = [](int p) { return p ^ ((p >> 3) & 1); };
@@ -110,55 +132,65 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
 
     double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;  // own block, summed over the fan
     double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0;  // block carried from the previous corner into this one's first neighbour
-    double ra0 = 0.0, ra1 = 0.0;                     // residual pair R_a = sum over corners of K_ab q_b
-    int firstSlot = 0;                               // row position of the first corner's first neighbour (closed fans wrap into it)
+    double ra0 = 0.0, ra1 = 0.0;                     // residual pair R_i = sum_j K_ij q_j, taken from the FINISHED row blocks
+    int firstSlot = 0, firstNode = 0;                // the first corner's first neighbour (closed fans wrap into its block)
     unsigned lastFlags = 0u;
 
-    // one 2x2 block: geometric sums -> D -> residual; returns the block
-    auto finish = [&](double s00, double s01, double s10, double s11, const double2 q, double& b0, double& b1, double& b2, double& b3) {
+    // geometric sums -> 2x2 block: K = [[D00 S00 + D22 S11, D01 S01 + D22 S10], [D01 S10 + D22 S01, D11 S11 + D22 S00]]
+    auto apply_d = [&](double s00, double s01, double s10, double s11, double& b0, double& b1, double& b2, double& b3) {
         b0 = fma(d00, s00, d22 * s11);
         b1 = fma(d01, s01, d22 * s10);
         b2 = fma(d01, s10, d22 * s01);
         b3 = fma(d11, s11, d22 * s00);
+    };
+    auto residual = [&](double b0, double b1, double b2, double b3, const double2 q) {
         if (WR) {
             ra0 = fma(b0, q.x, fma(b1, q.y, ra0));
             ra1 = fma(b2, q.x, fma(b3, q.y, ra1));
         }
     };
-    auto store = [&](int k, double b0, double b1, double b2, double b3) {
+    // a finished row block: its share of the residual, then its place in the staged row
+    auto store = [&](int k, double b0, double b1, double b2, double b3, const double2 q) {
+        residual(b0, b1, b2, b3, q);
         if (WK) {
             slot(k) = make_double2(b0, b1);
             slot(deg + k) = make_double2(b2, b3);
         }
     };
 
+    int n1 = 0, n2 = 0, n3 = 0, e = 0;
+    double2 X1 = make_double2(0.0, 0.0), X2 = X1, X3 = X1;
+    if (c0 < c1) {
+        decode(rec, el, n1, n2, n3, e);
+        X1 = __ldg(A.coords + n1);
+        X2 = __ldg(A.coords + n2);
+        if (NN == 4) X3 = __ldg(A.coords + n3);
+        firstSlot = ((unsigned)rec.x >> 7) & 0x7f;
+        firstNode = n1;
+    }
     for (int c = c0; c < c1; ++c) {
         const unsigned kw = (unsigned)rec.x;
-        int n1 = rec.y, n2 = rec.z, n3 = rec.w;  // 3 nodes: n3 is the element id
-        int e = NN == 4 ? el : n3;
-        if constexpr (CMP) {  // four signed 24-bit differences to my node id
-            const int me = (int)i;
-            e = me + (rec.w >> 8);
-            n3 = me + ((int)(__funnelshift_r((unsigned)rec.z, (unsigned)rec.w, 16) << 8) >> 8);
-            n2 = me + ((int)(__funnelshift_r((unsigned)rec.y, (unsigned)rec.z, 24) << 8) >> 8);
-            n1 = me + ((rec.y << 8) >> 8);
-        }
-        const double2 X1 = __ldg(A.coords + n1), X2 = __ldg(A.coords + n2);
-        double2 X3 = make_double2(0.0, 0.0);
-        if (NN == 4) X3 = __ldg(A.coords + n3);
+        const int nLast = NN == 4 ? n3 : n2;
         const double theta = __ldg(A.thick + e);
-        double2 q1 = make_double2(0.0, 0.0), q2 = q1, q3 = q1;
+        double2 q1 = make_double2(0.0, 0.0), q2 = q1;
         if (WR) {
-            q1 = __ldg(A.states + n1);
-            q2 = __ldg(A.states + n2);
-            if (NN == 4) q3 = __ldg(A.states + n3);
+            q1 = ld_early(A.states + n1);
+            if (NN == 4) q2 = ld_early(A.states + n2);
         }
-        if (c + 1 < c1) {  // next corner's record: one iteration ahead of its use
+        if (c + 1 < c1) {
             rec = ld_stream(A.rec + c + 1);
             if (NN == 4 && !CMP) el = ld_stream(A.elem + c + 1);
         }
-        if (c == c0) firstSlot = (kw >> 7) & 0x7f;
         lastFlags = kw;
+        // the next corner's coordinates replace this corner's once the geometry is done
+        auto next_coords = [&]() {
+            if (c + 1 < c1) {
+                decode(rec, el, n1, n2, n3, e);
+                X1 = __ldg(A.coords + n1);
+                X2 = __ldg(A.coords + n2);
+                if (NN == 4) X3 = __ldg(A.coords + n3);
+            }
+        };
         double b0, b1, b2, b3;
         if constexpr (NN == 4) {
             const double ya = X1.y - X3.y, yb = X2.y - ownX.y, yc = X3.y - X2.y, yd = ownX.y - X1.y, ye = X2.y - X1.y, yf = ownX.y - X3.y;
@@ -173,48 +205,53 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             const double m0 = up + um, mx = G * (up - um), me = G * (vp + vm), mxe = THIRD * (vp - vm), m3 = THIRD * m0;
             const double P0 = fma(m0, ya, fma(mx, yc, me * ye)), Q0 = fma(mx, ya, fma(m3, yc, mxe * ye)), R0 = fma(me, ya, fma(mxe, yc, m3 * ye));
             const double P1 = fma(m0, xa, fma(mx, xc, me * xe)), Q1 = fma(mx, xa, fma(m3, xc, mxe * xe)), R1 = fma(me, xa, fma(mxe, xc, m3 * xe));
+            next_coords();
             // b:        0            1            2            3
             // C_Db:  ya | xa      yb | xb     -ya | -xa    -yb | -xb
             // X_Db:  yc | xc     -yc | -xc     yd | xd     -yd | -xd
             // E_Db:  ye | xe      yf | xf     -yf | -xf    -ye | -xe
-            finish(fma(P0, ya, fma(Q0, yc, R0 * ye)), fma(P0, xa, fma(Q0, xc, R0 * xe)), fma(P1, ya, fma(Q1, yc, R1 * ye)),
-                   fma(P1, xa, fma(Q1, xc, R1 * xe)), ownU, b0, b1, b2, b3);
+            apply_d(fma(P0, ya, fma(Q0, yc, R0 * ye)), fma(P0, xa, fma(Q0, xc, R0 * xe)), fma(P1, ya, fma(Q1, yc, R1 * ye)),
+                    fma(P1, xa, fma(Q1, xc, R1 * xe)), b0, b1, b2, b3);
             o0 += b0, o1 += b1, o2 += b2, o3 += b3;
-            finish(fma(P0, yb, fma(R0, yf, -(Q0 * yc))), fma(P0, xb, fma(R0, xf, -(Q0 * xc))), fma(P1, yb, fma(R1, yf, -(Q1 * yc))),
-                   fma(P1, xb, fma(R1, xf, -(Q1 * xc))), q1, b0, b1, b2, b3);
-            store((kw >> 7) & 0x7f, b0 + k0, b1 + k1, b2 + k2, b3 + k3);
-            finish(fma(Q0, yd, -fma(P0, ya, R0 * yf)), fma(Q0, xd, -fma(P0, xa, R0 * xf)), fma(Q1, yd, -fma(P1, ya, R1 * yf)),
-                   fma(Q1, xd, -fma(P1, xa, R1 * xf)), q2, b0, b1, b2, b3);
-            store((kw >> 14) & 0x7f, b0, b1, b2, b3);
-            finish(-fma(P0, yb, fma(Q0, yd, R0 * ye)), -fma(P0, xb, fma(Q0, xd, R0 * xe)), -fma(P1, yb, fma(Q1, yd, R1 * ye)),
-                   -fma(P1, xb, fma(Q1, xd, R1 * xe)), q3, k0, k1, k2, k3);
+            apply_d(fma(P0, yb, fma(R0, yf, -(Q0 * yc))), fma(P0, xb, fma(R0, xf, -(Q0 * xc))), fma(P1, yb, fma(R1, yf, -(Q1 * yc))),
+                    fma(P1, xb, fma(R1, xf, -(Q1 * xc))), b0, b1, b2, b3);
+            store((kw >> 7) & 0x7f, b0 + k0, b1 + k1, b2 + k2, b3 + k3, q1);
+            apply_d(fma(Q0, yd, -fma(P0, ya, R0 * yf)), fma(Q0, xd, -fma(P0, xa, R0 * xf)), fma(Q1, yd, -fma(P1, ya, R1 * yf)),
+                    fma(Q1, xd, -fma(P1, xa, R1 * xf)), b0, b1, b2, b3);
+            store((kw >> 14) & 0x7f, b0, b1, b2, b3, q2);
+            apply_d(-fma(P0, yb, fma(Q0, yd, R0 * ye)), -fma(P0, xb, fma(Q0, xd, R0 * xe)), -fma(P1, yb, fma(Q1, yd, R1 * ye)),
+                    -fma(P1, xb, fma(Q1, xd, R1 * xe)), k0, k1, k2, k3);
         } else {
             // Gh_0 = (y1 - y2, y2 - y0, y0 - y1), Gh_1 = (x2 - x1, x0 - x2, x1 - x0), 2 * area = det
             const double g00 = X1.y - X2.y, g01 = X2.y - ownX.y, g02 = ownX.y - X1.y;
             const double g10 = X2.x - X1.x, g11 = ownX.x - X2.x, g12 = X1.x - ownX.x;
+            next_coords();
             const double det = g12 * g01 - g11 * g02;  // (x1 - x0)(y2 - y0) - (x2 - x0)(y1 - y0)
             const double sc = 0.5 * theta * fast_rcp(det);
             const double A0 = sc * g00, A1 = sc * g10;
-            finish(A0 * g00, A0 * g10, A1 * g00, A1 * g10, ownU, b0, b1, b2, b3);
+            apply_d(A0 * g00, A0 * g10, A1 * g00, A1 * g10, b0, b1, b2, b3);
             o0 += b0, o1 += b1, o2 += b2, o3 += b3;
-            finish(A0 * g01, A0 * g11, A1 * g01, A1 * g11, q1, b0, b1, b2, b3);
-            store((kw >> 7) & 0x7f, b0 + k0, b1 + k1, b2 + k2, b3 + k3);
-            finish(A0 * g02, A0 * g12, A1 * g02, A1 * g12, q2, k0, k1, k2, k3);
+            apply_d(A0 * g01, A0 * g11, A1 * g01, A1 * g11, b0, b1, b2, b3);
+            store((kw >> 7) & 0x7f, b0 + k0, b1 + k1, b2 + k2, b3 + k3, q1);
+            apply_d(A0 * g02, A0 * g12, A1 * g02, A1 * g12, k0, k1, k2, k3);
         }
-        if (!(kw & (1u << 28)) && !(kw & (1u << 29))) {  // the fan ends here (open end or chain break): the carried block is final
-            store((kw >> (7 * (NN - 1))) & 0x7f, k0, k1, k2, k3);
+        if (!(kw & (3u << 28))) {  // the fan ends here (open end or chain break): the carried block is final
+            store((kw >> (7 * (NN - 1))) & 0x7f, k0, k1, k2, k3, WR ? __ldg(A.states + nLast) : make_double2(0.0, 0.0));
             k0 = k1 = k2 = k3 = 0.0;
         }
     }
-    if (WK && c0 < c1) {
+    if (c0 < c1) {
         if (lastFlags & (1u << 29)) {  // closed fan: the last corner continues into the first one's first neighbour
-            double2& s0 = slot(firstSlot);
-            double2& s1 = slot(deg + firstSlot);
-            const double2 p0 = s0, p1 = s1;
-            s0 = make_double2(p0.x + k0, p0.y + k1);
-            s1 = make_double2(p1.x + k2, p1.y + k3);
+            residual(k0, k1, k2, k3, WR ? __ldg(A.states + firstNode) : make_double2(0.0, 0.0));
+            if (WK) {
+                double2& s0 = slot(firstSlot);
+                double2& s1 = slot(deg + firstSlot);
+                const double2 p0 = s0, p1 = s1;
+                s0 = make_double2(p0.x + k0, p0.y + k1);
+                s1 = make_double2(p1.x + k2, p1.y + k3);
+            }
         }
-        store((int)(lastFlags & 0x7f), o0, o1, o2, o3);  // own block
+        store((int)(lastFlags & 0x7f), o0, o1, o2, o3, ownU);  // own block
     }
 
     // ---- BC rows, loads, residual: as in the row-owner kernel ------------------------------------------------------

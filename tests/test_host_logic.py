@@ -67,7 +67,7 @@ def test_model_mixed_types_and_errors():
         m.setDesignVariables({"Thickness": np.ones(3)})
     with pytest.raises(ValueError, match="2D constitutive"):
         FEMpyModel(make_cm(0), nodeCoords=np.array([[0.0, 0], [1, 0], [2, 0]]), connectivity={"quad": np.array([[0, 1, 2, 0]])})
-    with pytest.raises(Exception, match="Must supply"):
+    with pytest.raises(Exception, match="both needed"):
         FEMpyModel(make_cm(0))
 
 
