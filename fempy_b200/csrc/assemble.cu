@@ -149,12 +149,12 @@ bool rows_path_available(const femb_plan* p) {
 // write-once fan kernel (assemble_fan.cuh): single block of 3- / 4-node elements with the standard tables, small strain
 // =============================================================================================
 bool fan_path_available(const femb_plan* p) {
-    return rows_path_available(p) && p->useFan && p->blocks.size() == 1 && p->blocks[0].fanOK && p->blocks[0].closedForm;
+    return rows_path_available(p) && p->useFan && p->blocks.size() == 1 && p->blocks[0].fanOK && p->blocks[0].d_fanHdr && p->blocks[0].closedForm;
 }
 
 template <int NN, bool WK, bool WR, bool CMP>
 static int launch_fan(const femb_plan* p, const DMat& D, const fan::Args& A, cudaStream_t st) {
-    const size_t smem = (size_t)2 * p->maxDeg * fan::BLOCK * sizeof(double2);  // row staging
+    const size_t smem = FAN_DIRECT ? 0 : (size_t)2 * p->maxDeg * fan::BLOCK * sizeof(double2);  // row staging
     static size_t configured[64] = {};
     size_t& conf = configured[p->device & 63];
     if (smem > conf) {
@@ -302,15 +302,13 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
         if (fanPath) {
             fan::Args A;
             A.numNodes = p->numNodes;
-            A.nrowptr = p->d_nrowptr;
-            A.cPtr = p->d_adjPtr;
-            A.rec = b.d_fanRec;
-            A.elem = b.d_fanElem;
+            A.hdr = b.d_fanHdr;
+            A.rest = b.d_fanRest;
             A.coords = (const double2*)d_coords;
             A.states = (const double2*)d_states;
             A.thick = d_thick;
             A.loads = (const double2*)d_loads;
-            A.bcInfo = bcs ? p->d_bcInfo : nullptr;
+            A.useBC = bcs ? 1 : 0;
             A.bcNodeCnt = (const double2*)p->d_bcNodeCnt;
             A.bcNodeVal = (const double2*)p->d_bcNodeVal;
             A.maxDeg = p->maxDeg;

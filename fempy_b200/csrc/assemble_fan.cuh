@@ -27,17 +27,28 @@ namespace fan {
 
 static constexpr int BLOCK = 32;
 
+// Per-node input of the kernel (plan.cu: k_fan_headers).  Everything a thread needs before its first element arrives
+// with ONE level of loads: header {first row position, index of the node's further records, corners | degree << 8,
+// BC word (femb_plan_set_bcs)} and, behind it, the record of the node's first corner; the records of the further corners
+// sit in a second array.  (The first version read row pointer, corner pointer and BC word from three arrays and then
+// the first record: two dependent levels, 13 % of the stall samples at config 2, 15 % at config 4.)
+//   record, 3 nodes           {slots | flags, node 1, node 2, element}
+//   record, 4 nodes compact   {slots | flags, three node ids and the element id as signed 24-bit differences to the owner}
+//   record, 4 nodes wide      {slots | flags, node 1, node 2, node 3} {element, -, -, -}   (numberings without locality)
+template <int NN, bool CMP>
+__host__ __device__ constexpr int rec_words() {
+    return (NN == 4 && !CMP) ? 2 : 1;
+}
+
 struct Args {
     long long numNodes;
-    const int* nrowptr;
-    const int* cPtr;          // node -> first corner (numNodes + 1 entries: the node -> element adjacency pointers)
-    const int4* rec;          // fan-ordered corner records
-    const int* elem;          // 4 nodes: element id per corner (3 nodes: in the record)
+    const int4* hdr;          // (1 + rec_words) int4 per node, node count padded to a multiple of BLOCK
+    const int4* rest;         // records of the corners after the first, rec_words int4 each
     const double2* coords;
     const double2* states;
     const double* thick;
     const double2* loads;     // may be NULL
-    const int* bcInfo;        // NULL: no BCs (see rows::Args)
+    int useBC;                // 0: ignore the headers' BC words
     const double2* bcNodeCnt;
     const double2* bcNodeVal;
     int maxDeg;
@@ -56,19 +67,14 @@ __host__ __device__ constexpr int resident_warps() {
 #endif
     return NN == 4 ? FAN_WARPS4 : FAN_WARPS3;
 }
+#ifndef FAN_DIRECT
+#define FAN_DIRECT 0  // measurement builds: 1 stores every finished block straight to global memory (no row staging)
+#endif
 
-// streaming inputs (corner records, element ids): read once, kept out of L1 so that the node data the corners share stays there
+// streaming inputs (headers, corner records): read once, kept out of L1 so that the node data the corners share stays there
 __device__ __forceinline__ int4 ld_stream(const int4* p) {
     int4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-// neighbour states: volatile so that the compiler keeps the requests where they are written -- at the top of a corner,
-// ahead of the record prefetch -- instead of sinking them next to their use at the end of it (lower register pressure,
-// but the full memory latency in every corner)
-__device__ __forceinline__ double2 ld_early(const double2* p) {
-    double2 v;
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
 __device__ __forceinline__ int ld_stream(const int* p) {
@@ -76,39 +82,47 @@ __device__ __forceinline__ int ld_stream(const int* p) {
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+// volatile loads: the compiler keeps the request where it is written -- as early as the address is known -- instead of
+// sinking it next to its use (lower register pressure, but the full memory latency on the critical path)
+__device__ __forceinline__ double2 ld_early(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_early(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
 
-// CMP: 4-node records with node / element ids as 24-bit differences to the owner (plan.cu: k_fan_compact)
 template <int NN, bool WK, bool WR, bool CMP>
 __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(const __grid_constant__ femb::DMat D, const Args A) {
     using femb::fast_rcp;
     static_assert(NN == 3 || NN == 4, "fan kernel: 3- and 4-node elements");
+    constexpr int RW = rec_words<NN, CMP>();
+    constexpr bool DIRECT = FAN_DIRECT != 0;
     // Row staging in the layout of the output: the warp's 32 rows are one contiguous run of the CSR values (both DOF rows
     // of a node are adjacent, rows in node order), position p of the run sits at acc[swz(p)].  The swizzle (bit 3 of p
     // flips bit 0) spreads the lanes' block stores -- 2*deg positions apart -- over all 16-byte bank groups and leaves the
     // consecutive positions the write-out reads conflict-free.
     extern __shared__ double2 acc[];  // [<= 2*maxDeg*BLOCK]
-    const int tid = threadIdx.x, lane = tid;
-    const long long i = (long long)blockIdx.x * BLOCK + tid;
+    const int lane = threadIdx.x;
+    const long long i = (long long)blockIdx.x * BLOCK + lane;
     const bool valid = i < A.numNodes;
-    const int off = __ldg(A.nrowptr + (valid ? i : A.numNodes));
-    const int deg = valid ? __ldg(A.nrowptr + i + 1) - off : 0;
-    const int c0 = valid ? __ldg(A.cPtr + i) : 0;
-    const int c1 = valid ? __ldg(A.cPtr + i + 1) : 0;
-    const unsigned info = (valid && A.bcInfo) ? (unsigned)__ldg(A.bcInfo + i) : 0u;
+    // ---- level 1: header + first record (the header array is padded: tail lanes read {end of the values, 0, 0, 0}) --
+    const int4* hp = A.hdr + (1 + RW) * i;
+    const int4 h = ld_stream(hp);
+    int4 rec = ld_stream(hp + 1);
+    int el = 0;
+    if (RW == 2) el = ld_stream(reinterpret_cast<const int*>(hp + 2));
     double2 ownX = make_double2(0.0, 0.0), ownU = make_double2(0.0, 0.0);
     if (valid) {
         ownX = __ldg(A.coords + i);
         ownU = __ldg(A.states + i);
     }
-    // Software pipeline over the corners: a corner's record is requested one corner ahead, and the coordinates of its
-    // nodes as soon as the current corner has finished its geometry (its own coordinates are differences by then), so the
-    // dependent chain record -> coordinates -> geometry waits on memory for the first corner only.
-    int4 rec = make_int4(0, 0, 0, 0);
-    int el = 0;
-    if (c0 < c1) {
-        rec = ld_stream(A.rec + c0);
-        if (NN == 4 && !CMP) el = ld_stream(A.elem + c0);
-    }
+    const int off = h.x, nc = h.z & 0xff, deg = (h.z >> 8) & 0xff;
+    const unsigned info = A.useBC ? (unsigned)h.w : 0u;
+    const int4* rest = A.rest + (long long)RW * h.y;  // record of corner c >= 1 at rest[RW * (c - 1)]
     // node ids / element id of a record (CMP: four signed 24-bit differences to my node id)
     auto decode = [&](const int4 r, const int relem, int& n1, int& n2, int& n3, int& e) {
         n1 = r.y, n2 = r.z, n3 = r.w;  // 3 nodes: the fourth word is the element id
@@ -121,10 +135,37 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             n1 = me + ((r.y << 8) >> 8);
         }
     };
+    // ---- level 2: the first corner's nodes and thickness, the second corner's record -------------------------------
+    // Software pipeline over the corners: records run two corners ahead, coordinates and thickness one corner ahead
+    // (requested as soon as the current corner has turned its own coordinates into differences), so that the dependent
+    // chain record -> coordinates -> geometry waits on memory for the first corner only.
+    int n1 = 0, n2 = 0, n3 = 0, e = 0;
+    double2 X1 = make_double2(0.0, 0.0), X2 = X1, X3 = X1;
+    double theta = 0.0;
+    int4 rec1 = make_int4(0, 0, 0, 0);
+    int el1 = 0;
+    if (nc > 0) {
+        decode(rec, el, n1, n2, n3, e);
+        X1 = ld_early(A.coords + n1);
+        X2 = ld_early(A.coords + n2);
+        if (NN == 4) X3 = ld_early(A.coords + n3);
+        theta = ld_early(A.thick + e);
+        if (nc > 1) {
+            rec1 = ld_stream(rest);
+            if (RW == 2) el1 = ld_stream(reinterpret_cast<const int*>(rest + 1));
+        }
+    }
+    const int firstSlot = ((unsigned)rec.x >> 7) & 0x7f, firstNode = n1;  // closed fans wrap into the first corner's first neighbour
+    unsigned kw = (unsigned)rec.x, lastFlags = 0u;
+
     const int base = __shfl_sync(0xffffffffu, off, 0);
     const int ownStart = 2 * (off - base);  // my first position in the warp's run of values
     auto swz = [](int p) { return p ^ ((p >> 3) & 1); };
-    auto slot = [&](int m) -> double2& { return acc[swz(ownStart + m)]; };
+    double2* const Kown = reinterpret_cast<double2*>(A.K) + 2ll * off;
+    auto put = [&](int m, const double2 v) {
+        if (DIRECT) rows::st_stream(Kown + m, v);
+        else acc[swz(ownStart + m)] = v;
+    };
 
     // D through registers (an FP64 instruction with a constant-bank operand issues at half rate on sm_100)
     const double* Dv = &D.d00 + A.zero;
@@ -133,8 +174,6 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
     double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;  // own block, summed over the fan
     double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0;  // block carried from the previous corner into this one's first neighbour
     double ra0 = 0.0, ra1 = 0.0;                     // residual pair R_i = sum_j K_ij q_j, taken from the FINISHED row blocks
-    int firstSlot = 0, firstNode = 0;                // the first corner's first neighbour (closed fans wrap into its block)
-    unsigned lastFlags = 0u;
 
     // geometric sums -> 2x2 block: K = [[D00 S00 + D22 S11, D01 S01 + D22 S10], [D01 S10 + D22 S01, D11 S11 + D22 S00]]
     auto apply_d = [&](double s00, double s01, double s10, double s11, double& b0, double& b1, double& b2, double& b3) {
@@ -149,48 +188,44 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             ra1 = fma(b2, q.x, fma(b3, q.y, ra1));
         }
     };
-    // a finished row block: its share of the residual, then its place in the staged row
+    // a finished row block: its share of the residual, then its place in the row
     auto store = [&](int k, double b0, double b1, double b2, double b3, const double2 q) {
         residual(b0, b1, b2, b3, q);
         if (WK) {
-            slot(k) = make_double2(b0, b1);
-            slot(deg + k) = make_double2(b2, b3);
+            put(k, make_double2(b0, b1));
+            put(deg + k, make_double2(b2, b3));
         }
     };
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;  // DIRECT: the first corner's first block waits in registers for the closing wrap
 
-    int n1 = 0, n2 = 0, n3 = 0, e = 0;
-    double2 X1 = make_double2(0.0, 0.0), X2 = X1, X3 = X1;
-    if (c0 < c1) {
-        decode(rec, el, n1, n2, n3, e);
-        X1 = __ldg(A.coords + n1);
-        X2 = __ldg(A.coords + n2);
-        if (NN == 4) X3 = __ldg(A.coords + n3);
-        firstSlot = ((unsigned)rec.x >> 7) & 0x7f;
-        firstNode = n1;
-    }
-    for (int c = c0; c < c1; ++c) {
-        const unsigned kw = (unsigned)rec.x;
+    for (int c = 0; c < nc; ++c) {
         const int nLast = NN == 4 ? n3 : n2;
-        const double theta = __ldg(A.thick + e);
+        const double th = theta;
         double2 q1 = make_double2(0.0, 0.0), q2 = q1;
         if (WR) {
             q1 = ld_early(A.states + n1);
             if (NN == 4) q2 = ld_early(A.states + n2);
         }
-        if (c + 1 < c1) {
-            rec = ld_stream(A.rec + c + 1);
-            if (NN == 4 && !CMP) el = ld_stream(A.elem + c + 1);
+        int4 rec2 = make_int4(0, 0, 0, 0);
+        int el2 = 0;
+        if (c + 2 < nc) {
+            rec2 = ld_stream(rest + RW * (c + 1));
+            if (RW == 2) el2 = ld_stream(reinterpret_cast<const int*>(rest + RW * (c + 1) + 1));
         }
-        lastFlags = kw;
-        // the next corner's coordinates replace this corner's once the geometry is done
-        auto next_coords = [&]() {
-            if (c + 1 < c1) {
-                decode(rec, el, n1, n2, n3, e);
-                X1 = __ldg(A.coords + n1);
-                X2 = __ldg(A.coords + n2);
-                if (NN == 4) X3 = __ldg(A.coords + n3);
+        const unsigned kwc = kw;
+        lastFlags = kwc;
+        // the next corner's coordinates and thickness replace this corner's once the geometry has consumed them
+        auto next_corner = [&]() {
+            if (c + 1 < nc) {
+                decode(rec1, el1, n1, n2, n3, e);
+                X1 = ld_early(A.coords + n1);
+                X2 = ld_early(A.coords + n2);
+                if (NN == 4) X3 = ld_early(A.coords + n3);
+                theta = ld_early(A.thick + e);
+                kw = (unsigned)rec1.x;
             }
         };
+        const bool keepFirst = DIRECT && c == 0 && WK;
         double b0, b1, b2, b3;
         if constexpr (NN == 4) {
             const double ya = X1.y - X3.y, yb = X2.y - ownX.y, yc = X3.y - X2.y, yd = ownX.y - X1.y, ye = X2.y - X1.y, yf = ownX.y - X3.y;
@@ -198,14 +233,14 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             constexpr double G = 0.57735026918962576451, THIRD = 1.0 / 3.0;
             const double dd0 = xb * ya - xa * yb;
             const double gx = G * (xc * yd - xd * yc), ge = G * (xe * yf - xf * ye);
-            const double tp = dd0 + gx, tm = dd0 - gx, th8 = 0.125 * theta;
+            const double tp = dd0 + gx, tm = dd0 - gx, th8 = 0.125 * th;
             const double spp = th8 * fast_rcp(tp + ge), spm = th8 * fast_rcp(tp - ge);
             const double smp = th8 * fast_rcp(tm + ge), smm = th8 * fast_rcp(tm - ge);
             const double up = spp + spm, um = smp + smm, vp = spp - spm, vm = smp - smm;
             const double m0 = up + um, mx = G * (up - um), me = G * (vp + vm), mxe = THIRD * (vp - vm), m3 = THIRD * m0;
             const double P0 = fma(m0, ya, fma(mx, yc, me * ye)), Q0 = fma(mx, ya, fma(m3, yc, mxe * ye)), R0 = fma(me, ya, fma(mxe, yc, m3 * ye));
             const double P1 = fma(m0, xa, fma(mx, xc, me * xe)), Q1 = fma(mx, xa, fma(m3, xc, mxe * xe)), R1 = fma(me, xa, fma(mxe, xc, m3 * xe));
-            next_coords();
+            next_corner();
             // b:        0            1            2            3
             // C_Db:  ya | xa      yb | xb     -ya | -xa    -yb | -xb
             // X_Db:  yc | xc     -yc | -xc     yd | xd     -yd | -xd
@@ -215,41 +250,55 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             o0 += b0, o1 += b1, o2 += b2, o3 += b3;
             apply_d(fma(P0, yb, fma(R0, yf, -(Q0 * yc))), fma(P0, xb, fma(R0, xf, -(Q0 * xc))), fma(P1, yb, fma(R1, yf, -(Q1 * yc))),
                     fma(P1, xb, fma(R1, xf, -(Q1 * xc))), b0, b1, b2, b3);
-            store((kw >> 7) & 0x7f, b0 + k0, b1 + k1, b2 + k2, b3 + k3, q1);
+            b0 += k0, b1 += k1, b2 += k2, b3 += k3;
+            if (keepFirst) f0 = b0, f1 = b1, f2 = b2, f3 = b3, residual(b0, b1, b2, b3, q1);
+            else store((kwc >> 7) & 0x7f, b0, b1, b2, b3, q1);
             apply_d(fma(Q0, yd, -fma(P0, ya, R0 * yf)), fma(Q0, xd, -fma(P0, xa, R0 * xf)), fma(Q1, yd, -fma(P1, ya, R1 * yf)),
                     fma(Q1, xd, -fma(P1, xa, R1 * xf)), b0, b1, b2, b3);
-            store((kw >> 14) & 0x7f, b0, b1, b2, b3, q2);
+            store((kwc >> 14) & 0x7f, b0, b1, b2, b3, q2);
             apply_d(-fma(P0, yb, fma(Q0, yd, R0 * ye)), -fma(P0, xb, fma(Q0, xd, R0 * xe)), -fma(P1, yb, fma(Q1, yd, R1 * ye)),
                     -fma(P1, xb, fma(Q1, xd, R1 * xe)), k0, k1, k2, k3);
         } else {
             // Gh_0 = (y1 - y2, y2 - y0, y0 - y1), Gh_1 = (x2 - x1, x0 - x2, x1 - x0), 2 * area = det
             const double g00 = X1.y - X2.y, g01 = X2.y - ownX.y, g02 = ownX.y - X1.y;
             const double g10 = X2.x - X1.x, g11 = ownX.x - X2.x, g12 = X1.x - ownX.x;
-            next_coords();
+            next_corner();
             const double det = g12 * g01 - g11 * g02;  // (x1 - x0)(y2 - y0) - (x2 - x0)(y1 - y0)
-            const double sc = 0.5 * theta * fast_rcp(det);
+            const double sc = 0.5 * th * fast_rcp(det);
             const double A0 = sc * g00, A1 = sc * g10;
             apply_d(A0 * g00, A0 * g10, A1 * g00, A1 * g10, b0, b1, b2, b3);
             o0 += b0, o1 += b1, o2 += b2, o3 += b3;
             apply_d(A0 * g01, A0 * g11, A1 * g01, A1 * g11, b0, b1, b2, b3);
-            store((kw >> 7) & 0x7f, b0 + k0, b1 + k1, b2 + k2, b3 + k3, q1);
+            b0 += k0, b1 += k1, b2 += k2, b3 += k3;
+            if (keepFirst) f0 = b0, f1 = b1, f2 = b2, f3 = b3, residual(b0, b1, b2, b3, q1);
+            else store((kwc >> 7) & 0x7f, b0, b1, b2, b3, q1);
             apply_d(A0 * g02, A0 * g12, A1 * g02, A1 * g12, k0, k1, k2, k3);
         }
-        if (!(kw & (3u << 28))) {  // the fan ends here (open end or chain break): the carried block is final
-            store((kw >> (7 * (NN - 1))) & 0x7f, k0, k1, k2, k3, WR ? __ldg(A.states + nLast) : make_double2(0.0, 0.0));
+        if (!(kwc & (3u << 28))) {  // the fan ends here (open end or chain break): the carried block is final
+            store((kwc >> (7 * (NN - 1))) & 0x7f, k0, k1, k2, k3, WR ? __ldg(A.states + nLast) : make_double2(0.0, 0.0));
             k0 = k1 = k2 = k3 = 0.0;
         }
+        rec1 = rec2;
+        el1 = el2;
     }
-    if (c0 < c1) {
+    if (nc > 0) {
         if (lastFlags & (1u << 29)) {  // closed fan: the last corner continues into the first one's first neighbour
             residual(k0, k1, k2, k3, WR ? __ldg(A.states + firstNode) : make_double2(0.0, 0.0));
             if (WK) {
-                double2& s0 = slot(firstSlot);
-                double2& s1 = slot(deg + firstSlot);
-                const double2 p0 = s0, p1 = s1;
-                s0 = make_double2(p0.x + k0, p0.y + k1);
-                s1 = make_double2(p1.x + k2, p1.y + k3);
+                if (DIRECT) {
+                    f0 += k0, f1 += k1, f2 += k2, f3 += k3;
+                } else {
+                    double2& s0 = acc[swz(ownStart + firstSlot)];
+                    double2& s1 = acc[swz(ownStart + deg + firstSlot)];
+                    const double2 p0 = s0, p1 = s1;
+                    s0 = make_double2(p0.x + k0, p0.y + k1);
+                    s1 = make_double2(p1.x + k2, p1.y + k3);
+                }
             }
+        }
+        if (DIRECT && WK) {
+            put(firstSlot, make_double2(f0, f1));
+            put(deg + firstSlot, make_double2(f2, f3));
         }
         store((int)(lastFlags & 0x7f), o0, o1, o2, o3, ownU);  // own block
     }
@@ -261,8 +310,8 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
         const int diagK = (info >> 2) & 0x7f;
         for (int r = 0; r < 2; ++r) {
             if (m & (1u << r)) {
-                for (int k = 0; k < deg; ++k) slot(r * deg + k) = make_double2(0.0, 0.0);
-                slot(r * deg + diagK) = r ? make_double2(0.0, cnt.y) : make_double2(cnt.x, 0.0);
+                for (int k = 0; k < deg; ++k) put(r * deg + k, make_double2(0.0, 0.0));
+                put(r * deg + diagK, r ? make_double2(0.0, cnt.y) : make_double2(cnt.x, 0.0));
             }
         }
     }
@@ -272,9 +321,9 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
         if (m) valBC = __ldg(A.bcNodeVal + (info >> 9) - 1);
     }
     // ---- write-out: stream the warp's run of CSR values (both DOF rows of a node are adjacent, rows in node order) ---
-    if (WK) {
+    if (WK && !DIRECT) {
         double2* K2 = reinterpret_cast<double2*>(A.K) + 2ll * base;
-        const int total = __shfl_sync(0xffffffffu, ownStart + 2 * deg, 31);  // invalid tail lanes hold off = end, deg = 0
+        const int total = __shfl_sync(0xffffffffu, ownStart + 2 * deg, 31);  // padded tail lanes hold off = end, deg = 0
         __syncwarp();
 #pragma unroll 4
         for (int f = lane; f < total; f += 32) rows::st_stream(K2 + f, acc[swz(f)]);

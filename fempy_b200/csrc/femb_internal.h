@@ -55,8 +55,10 @@ struct BlockData {
     int4* d_connE = nullptr;   // element-major connectivity, ceil(nn/4) words per element (row-owner kernel)
     void* d_corners = nullptr; // corner records of this block, indexed by the global corner number (plan.cu: k_corners)
     int* d_cornerElem = nullptr;  // rotated 4-node records: element id of each corner
-    int4* d_fanRec = nullptr;     // fan-ordered corner records of the write-once kernel (plan.cu: k_fan_corners)
-    int* d_fanElem = nullptr;     // 4 nodes: element id of each fan-ordered corner
+    int4* d_fanRec = nullptr;     // plan-time: fan-ordered corner records of the write-once kernel (plan.cu: k_fan_corners)
+    int* d_fanElem = nullptr;     // plan-time, 4 nodes: element id of each fan-ordered corner
+    int4* d_fanHdr = nullptr;     // per node {row start, rest index, corners | degree << 8, BC word} + first corner record (plan.cu: k_fan_headers)
+    int4* d_fanRest = nullptr;    // records of every node's further corners
     bool fanCompact = false;      // 4 nodes: node / element ids as 24-bit differences to the owner, no element array
     bool fanOK = false;           // the corners of every node chain into fans: the write-once kernel applies
 };

@@ -495,6 +495,41 @@ __global__ void k_fan_compact(long long N, const int* __restrict__ cBegin, const
     }
 }
 
+// Kernel-side layout of the fan records (assemble_fan.cuh: Args): per node a header {first row position, index of its
+// further records, corners | degree << 8, BC word} followed by the record of its first corner (rw int4: 2 for wide 4-node
+// records, whose second word carries the element id), and the records of all further corners in `rest`.  The node count is
+// padded to a multiple of 32: the kernel's tail lanes read {end of the values, 0, 0, 0}.
+__global__ void k_fan_rest_count(long long N, const int* __restrict__ cBegin, const int* __restrict__ cEnd, int* __restrict__ cnt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) cnt[i] = max(cEnd[i] - cBegin[i] - 1, 0);
+}
+__global__ void k_fan_headers(long long N, long long Npad, int rw, const int* __restrict__ nrowptr, const int* __restrict__ cBegin,
+                              const int* __restrict__ cEnd, const int* __restrict__ restPtr, const int4* __restrict__ fanRec,
+                              const int* __restrict__ fanElem, int4* __restrict__ hdr, int4* __restrict__ rest) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Npad) return;
+    int4* h = hdr + (1 + rw) * i;
+    const int4 zero = make_int4(0, 0, 0, 0);
+    if (i >= N) {
+        h[0] = make_int4(nrowptr[N], 0, 0, 0);
+        h[1] = zero;
+        if (rw == 2) h[2] = zero;
+        return;
+    }
+    const int c0 = cBegin[i], nc = cEnd[i] - c0, off = nrowptr[i], deg = nrowptr[i + 1] - off, r0 = restPtr[i];
+    h[0] = make_int4(off, r0, nc | (deg << 8), 0);
+    h[1] = nc > 0 ? fanRec[c0] : zero;
+    if (rw == 2) h[2] = make_int4(nc > 0 ? fanElem[c0] : 0, 0, 0, 0);
+    for (int k = 1; k < nc; ++k) {
+        rest[(long long)rw * (r0 + k - 1)] = fanRec[c0 + k];
+        if (rw == 2) rest[(long long)rw * (r0 + k - 1) + 1] = make_int4(fanElem[c0 + k], 0, 0, 0);
+    }
+}
+__global__ void k_fan_header_bcs(long long N, int stride, const int* __restrict__ bcInfo, int4* __restrict__ hdr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) hdr[stride * i].w = bcInfo[i];
+}
+
 // standard linear triangle: N = (1 - xi - eta, xi, eta), centroid rule with weight 1/2 (TriElement2D order 1,
 // FEMpy/Elements/TriElement2D.py:69-169, Quadrature/TriQuad.py:78-86)
 static bool standard_t3(int nq, const double* dN, const double* w) {
@@ -706,6 +741,32 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
                         b.fanCompact = true;
                     }
                 }
+                if (b.fanOK) {  // kernel-side layout: per-node headers + first record, further records behind
+                    const int rw = (b.nn == 4 && !b.fanCompact) ? 2 : 1;
+                    const long long Npad = (N + 31) / 32 * 32;
+                    int *d_cnt = nullptr, *d_restPtr = nullptr;
+                    CUDA_TRY(cudaMalloc(&d_cnt, (N + 1) * sizeof(int)));
+                    CUDA_TRY(cudaMalloc(&d_restPtr, (N + 1) * sizeof(int)));
+                    k_fan_rest_count<<<grid_for(N, 256), 256, 0, st>>>(N, p->d_blockAdj, p->d_blockAdj + (size_t)N, d_cnt);
+                    launches++;
+                    int rc = exclusive_scan(d_cnt, d_restPtr, N, st, launches);
+                    int restTotal = 0;
+                    if (!rc && cudaMemcpyAsync(&restTotal, d_restPtr + N, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
+                    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
+                    if (!rc && cudaMalloc(&b.d_fanHdr, (size_t)Npad * (1 + rw) * sizeof(int4)) != cudaSuccess) rc = 1;
+                    if (!rc && cudaMalloc(&b.d_fanRest, std::max<size_t>((size_t)restTotal * rw, 1) * sizeof(int4)) != cudaSuccess) rc = 1;
+                    if (!rc) {
+                        k_fan_headers<<<grid_for(Npad, 128), 128, 0, st>>>(N, Npad, rw, p->d_nrowptr, p->d_blockAdj, p->d_blockAdj + (size_t)N,
+                                                                         d_restPtr, b.d_fanRec, b.d_fanElem, b.d_fanHdr, b.d_fanRest);
+                        launches++;
+                        if (cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
+                    }
+                    cudaFree(d_cnt);
+                    cudaFree(d_restPtr);
+                    dfree(b.d_fanRec);  // the kernel reads headers + rest only
+                    dfree(b.d_fanElem);
+                    if (rc) return fail("femb_plan_finalize: building the fan headers failed (%s)", cudaGetErrorString(cudaGetLastError()));
+                }
             }
             {  // balanced row schedule: kept only when it saves more than 8 % of the warps' corner iterations
                 const long long windows = (N + ROW_WINDOW - 1) / ROW_WINDOW;
@@ -780,6 +841,8 @@ extern "C" void femb_plan_destroy(femb_plan* p) {
         b.d_cornerElem = nullptr;
         dfree(b.d_fanRec);
         dfree(b.d_fanElem);
+        dfree(b.d_fanHdr);
+        dfree(b.d_fanRest);
     }
     dfree(p->d_bcMask);
     dfree(p->d_bcInfo);
@@ -993,6 +1056,10 @@ extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const doubl
         CUDA_TRY(cudaMemcpyAsync(p->d_bcNodeCnt, cnt2.data(), cnt2.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         CUDA_TRY(cudaMemcpyAsync(p->d_bcNodeVal, val2.data(), val2.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         k_bc_diag<<<grid_for(p->numNodes, 256), 256, 0, p->stream>>>(p->numNodes, p->d_nrowptr, p->d_ncols, p->d_bcInfo);
+        for (auto& b : p->blocks)  // the fan kernel reads the BC word from its per-node header
+            if (b.d_fanHdr)
+                k_fan_header_bcs<<<grid_for(p->numNodes, 256), 256, 0, p->stream>>>(p->numNodes, 1 + ((b.nn == 4 && !b.fanCompact) ? 2 : 1),
+                                                                                  p->d_bcInfo, b.d_fanHdr);
         CUDA_TRY(cudaStreamSynchronize(p->stream));  // the host vectors go out of scope
     }
     CUDA_TRY(cudaMalloc(&p->d_bcDof, n * sizeof(int)));
