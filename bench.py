@@ -326,6 +326,9 @@ def run_ours(args, rank, world, local_rank):
         plan.setOption("balance_rows", args.balance_rows)
     if args.no_fan:
         plan.setOption("fan_rows", 0)
+    for kv in args.plan_opt:
+        name, val = kv.split("=")
+        plan.setOption(name, int(val))
     plan.addBlock(N_, dN, w, wl["conn"][elType])
     plan.finalize()
     plan_wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -612,6 +615,7 @@ def main():
     ap.add_argument("--flush-write-only", action="store_true", help="L2 flush by the 512 MB write alone (leaves dirty lines for the timed kernel to evict)")
     ap.add_argument("--dist-mode", default="halo", choices=["halo", "exchange"], help="multi-GPU: redundant boundary elements (no exchange) or unique elements + NCCL interface exchange")
     ap.add_argument("--no-fan", action="store_true", help="accumulating row-owner kernel instead of the write-once fan kernel (exploration only)")
+    ap.add_argument("--plan-opt", action="append", default=[], metavar="NAME=INT", help="femb_plan_set_option before finalize (exploration only)")
     ap.add_argument("--no-bcs", action="store_true", help="device-timed steps without boundary conditions (exploration only)")
     ap.add_argument("--path", default="rows", choices=["rows", "scatter"],
                     help="assembly path: row-owner kernel (default) or slot-map scatter with FP64 atomics")

@@ -154,7 +154,7 @@ bool fan_path_available(const femb_plan* p) {
 
 template <int NN, bool WK, bool WR, bool CMP>
 static int launch_fan(const femb_plan* p, const DMat& D, const fan::Args& A, cudaStream_t st) {
-    const size_t smem = FAN_DIRECT ? 0 : (size_t)2 * p->maxDeg * fan::BLOCK * sizeof(double2);  // row staging
+    const size_t smem = (size_t)2 * p->maxDeg * fan::BLOCK * sizeof(double2);  // row staging
     static size_t configured[64] = {};
     size_t& conf = configured[p->device & 63];
     if (smem > conf) {
@@ -313,6 +313,19 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.bcNodeVal = (const double2*)p->d_bcNodeVal;
             A.maxDeg = p->maxDeg;
             A.zero = 0;
+            {   // L2 look-ahead distance: by default the warps one resident wave ahead (SMs x resident warps per SM)
+                int sms = 148;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+                const long long warps = p->fanPrefetch >= 0 ? p->fanPrefetch : (long long)sms * (b.nn == 3 ? fan::resident_warps<3>() : fan::resident_warps<4>());
+                const long long pfNodes = std::min<long long>(warps * fan::BLOCK, p->numNodes);
+                const double perNode = (double)pfNodes / (double)p->numNodes;
+                A.pfNodes = (int)pfNodes;
+                A.pfRest = (int)(perNode * (double)b.fanRestTotal);
+                A.pfElems = (int)(perNode * (double)p->numElems);
+                A.pfNodeLimit = pfNodes ? (int)(p->numNodes - pfNodes) : 0;
+                A.pfRestLimit = pfNodes ? (int)(b.fanRestTotal - A.pfRest) : 0;
+                A.pfElemLimit = pfNodes ? (int)(p->numElems - A.pfElems) : 0;
+            }
             A.K = d_K;
             A.R = d_R;
             if (b.nn == 3) TRY((launch_fan_variant<3>(p, D, A, wk, wr, st)));

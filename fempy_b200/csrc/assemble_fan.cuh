@@ -53,9 +53,15 @@ struct Args {
     const double2* bcNodeVal;
     int maxDeg;
     int zero;                 // always 0 (runtime-uniform index: keeps D out of the constant-bank operand slot)
+    // L2 look-ahead (0 = off): every thread asks L2 for the inputs of the node pfNodes ahead of its own -- about one wave
+    // of warps -- so that later warps find headers, records, node data and thickness in L2 instead of DRAM
+    // (limits = array length - distance, 0 when off: an index below its limit has a valid look-ahead target)
+    int pfNodes, pfNodeLimit, pfRest, pfRestLimit, pfElems, pfElemLimit;
     double* K;
     double* R;
 };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int NN>
 __host__ __device__ constexpr int resident_warps() {
@@ -67,8 +73,8 @@ __host__ __device__ constexpr int resident_warps() {
 #endif
     return NN == 4 ? FAN_WARPS4 : FAN_WARPS3;
 }
-#ifndef FAN_DIRECT
-#define FAN_DIRECT 0  // measurement builds: 1 stores every finished block straight to global memory (no row staging)
+#ifndef FAN_SWZ
+#define FAN_SWZ 1
 #endif
 
 // streaming inputs (headers, corner records): read once, kept out of L1 so that the node data the corners share stays there
@@ -100,7 +106,6 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
     using femb::fast_rcp;
     static_assert(NN == 3 || NN == 4, "fan kernel: 3- and 4-node elements");
     constexpr int RW = rec_words<NN, CMP>();
-    constexpr bool DIRECT = FAN_DIRECT != 0;
     // Row staging in the layout of the output: the warp's 32 rows are one contiguous run of the CSR values (both DOF rows
     // of a node are adjacent, rows in node order), position p of the run sits at acc[swz(p)].  The swizzle (bit 3 of p
     // flips bit 0) spreads the lanes' block stores -- 2*deg positions apart -- over all 16-byte bank groups and leaves the
@@ -123,6 +128,15 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
     const int off = h.x, nc = h.z & 0xff, deg = (h.z >> 8) & 0xff;
     const unsigned info = A.useBC ? (unsigned)h.w : 0u;
     const int4* rest = A.rest + (long long)RW * h.y;  // record of corner c >= 1 at rest[RW * (c - 1)]
+    if (i < A.pfNodeLimit) {  // L2 look-ahead for the warp that will own node i + pfNodes
+        const long long j = i + A.pfNodes;
+        prefetch_l2(A.hdr + (1 + RW) * j);
+        if (RW == 2) prefetch_l2(A.hdr + (1 + RW) * j + 2);
+        prefetch_l2(A.coords + j);
+        prefetch_l2(A.states + j);
+        if (WR && A.loads) prefetch_l2(A.loads + j);
+    }
+    if (h.y < A.pfRestLimit) prefetch_l2(rest + RW * A.pfRest);
     // node ids / element id of a record (CMP: four signed 24-bit differences to my node id)
     auto decode = [&](const int4 r, const int relem, int& n1, int& n2, int& n3, int& e) {
         n1 = r.y, n2 = r.z, n3 = r.w;  // 3 nodes: the fourth word is the element id
@@ -150,6 +164,7 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
         X2 = ld_early(A.coords + n2);
         if (NN == 4) X3 = ld_early(A.coords + n3);
         theta = ld_early(A.thick + e);
+        if (NN == 4 && e < A.pfElemLimit) prefetch_l2(A.thick + e + A.pfElems);
         if (nc > 1) {
             rec1 = ld_stream(rest);
             if (RW == 2) el1 = ld_stream(reinterpret_cast<const int*>(rest + 1));
@@ -160,12 +175,8 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
 
     const int base = __shfl_sync(0xffffffffu, off, 0);
     const int ownStart = 2 * (off - base);  // my first position in the warp's run of values
-    auto swz = [](int p) { return p ^ ((p >> 3) & 1); };
-    double2* const Kown = reinterpret_cast<double2*>(A.K) + 2ll * off;
-    auto put = [&](int m, const double2 v) {
-        if (DIRECT) rows::st_stream(Kown + m, v);
-        else acc[swz(ownStart + m)] = v;
-    };
+    auto swz = [](int p) { return FAN_SWZ ? p ^ ((p >> 3) & 1) : p; };
+    auto put = [&](int m, const double2 v) { acc[swz(ownStart + m)] = v; };
 
     // D through registers (an FP64 instruction with a constant-bank operand issues at half rate on sm_100)
     const double* Dv = &D.d00 + A.zero;
@@ -196,7 +207,6 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             put(deg + k, make_double2(b2, b3));
         }
     };
-    double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;  // DIRECT: the first corner's first block waits in registers for the closing wrap
 
     for (int c = 0; c < nc; ++c) {
         const int nLast = NN == 4 ? n3 : n2;
@@ -214,6 +224,7 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
         }
         const unsigned kwc = kw;
         lastFlags = kwc;
+        if (NN == 3 && e < A.pfElemLimit) prefetch_l2(A.thick + e + A.pfElems);
         // the next corner's coordinates and thickness replace this corner's once the geometry has consumed them
         auto next_corner = [&]() {
             if (c + 1 < nc) {
@@ -225,7 +236,6 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
                 kw = (unsigned)rec1.x;
             }
         };
-        const bool keepFirst = DIRECT && c == 0 && WK;
         double b0, b1, b2, b3;
         if constexpr (NN == 4) {
             const double ya = X1.y - X3.y, yb = X2.y - ownX.y, yc = X3.y - X2.y, yd = ownX.y - X1.y, ye = X2.y - X1.y, yf = ownX.y - X3.y;
@@ -251,8 +261,7 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             apply_d(fma(P0, yb, fma(R0, yf, -(Q0 * yc))), fma(P0, xb, fma(R0, xf, -(Q0 * xc))), fma(P1, yb, fma(R1, yf, -(Q1 * yc))),
                     fma(P1, xb, fma(R1, xf, -(Q1 * xc))), b0, b1, b2, b3);
             b0 += k0, b1 += k1, b2 += k2, b3 += k3;
-            if (keepFirst) f0 = b0, f1 = b1, f2 = b2, f3 = b3, residual(b0, b1, b2, b3, q1);
-            else store((kwc >> 7) & 0x7f, b0, b1, b2, b3, q1);
+            store((kwc >> 7) & 0x7f, b0, b1, b2, b3, q1);
             apply_d(fma(Q0, yd, -fma(P0, ya, R0 * yf)), fma(Q0, xd, -fma(P0, xa, R0 * xf)), fma(Q1, yd, -fma(P1, ya, R1 * yf)),
                     fma(Q1, xd, -fma(P1, xa, R1 * xf)), b0, b1, b2, b3);
             store((kwc >> 14) & 0x7f, b0, b1, b2, b3, q2);
@@ -270,8 +279,7 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             o0 += b0, o1 += b1, o2 += b2, o3 += b3;
             apply_d(A0 * g01, A0 * g11, A1 * g01, A1 * g11, b0, b1, b2, b3);
             b0 += k0, b1 += k1, b2 += k2, b3 += k3;
-            if (keepFirst) f0 = b0, f1 = b1, f2 = b2, f3 = b3, residual(b0, b1, b2, b3, q1);
-            else store((kwc >> 7) & 0x7f, b0, b1, b2, b3, q1);
+            store((kwc >> 7) & 0x7f, b0, b1, b2, b3, q1);
             apply_d(A0 * g02, A0 * g12, A1 * g02, A1 * g12, k0, k1, k2, k3);
         }
         if (!(kwc & (3u << 28))) {  // the fan ends here (open end or chain break): the carried block is final
@@ -285,20 +293,12 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
         if (lastFlags & (1u << 29)) {  // closed fan: the last corner continues into the first one's first neighbour
             residual(k0, k1, k2, k3, WR ? __ldg(A.states + firstNode) : make_double2(0.0, 0.0));
             if (WK) {
-                if (DIRECT) {
-                    f0 += k0, f1 += k1, f2 += k2, f3 += k3;
-                } else {
-                    double2& s0 = acc[swz(ownStart + firstSlot)];
-                    double2& s1 = acc[swz(ownStart + deg + firstSlot)];
-                    const double2 p0 = s0, p1 = s1;
-                    s0 = make_double2(p0.x + k0, p0.y + k1);
-                    s1 = make_double2(p1.x + k2, p1.y + k3);
-                }
+                double2& s0 = acc[swz(ownStart + firstSlot)];
+                double2& s1 = acc[swz(ownStart + deg + firstSlot)];
+                const double2 p0 = s0, p1 = s1;
+                s0 = make_double2(p0.x + k0, p0.y + k1);
+                s1 = make_double2(p1.x + k2, p1.y + k3);
             }
-        }
-        if (DIRECT && WK) {
-            put(firstSlot, make_double2(f0, f1));
-            put(deg + firstSlot, make_double2(f2, f3));
         }
         store((int)(lastFlags & 0x7f), o0, o1, o2, o3, ownU);  // own block
     }
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
         if (m) valBC = __ldg(A.bcNodeVal + (info >> 9) - 1);
     }
     // ---- write-out: stream the warp's run of CSR values (both DOF rows of a node are adjacent, rows in node order) ---
-    if (WK && !DIRECT) {
+    if (WK) {
         double2* K2 = reinterpret_cast<double2*>(A.K) + 2ll * base;
         const int total = __shfl_sync(0xffffffffu, ownStart + 2 * deg, 31);  // padded tail lanes hold off = end, deg = 0
         __syncwarp();

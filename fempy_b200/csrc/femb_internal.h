@@ -59,6 +59,7 @@ struct BlockData {
     int* d_fanElem = nullptr;     // plan-time, 4 nodes: element id of each fan-ordered corner
     int4* d_fanHdr = nullptr;     // per node {row start, rest index, corners | degree << 8, BC word} + first corner record (plan.cu: k_fan_headers)
     int4* d_fanRest = nullptr;    // records of every node's further corners
+    long long fanRestTotal = 0;   // records in d_fanRest
     bool fanCompact = false;      // 4 nodes: node / element ids as 24-bit differences to the owner, no element array
     bool fanOK = false;           // the corners of every node chain into fans: the write-once kernel applies
 };
@@ -89,6 +90,7 @@ struct femb_plan {
     long long* d_rowStats = nullptr;  // measurement builds only (ROWS_TRACE): warp lifetime statistics
     int assemblyPath = 2;        // 2 row-owner kernel, 0 slot-map scatter with FP64 atomics
     bool fanCompactAllowed = true;  // option "fan_compact" (tests): 0 keeps the wide fan records even when the differences fit
+    int fanPrefetch = -1;        // option "fan_prefetch": L2 look-ahead of the fan kernel in 32-node warps (-1: one resident wave, 0: off)
     bool useFan = true;          // option "fan_rows": write-once fan kernel where it applies (else the accumulating row-owner kernel)
     int* d_blockAdj = nullptr;   // (numBlocks+1) x numNodes: start of each block's corners in a node's adjacency list (row-owner kernel)
     int* d_rowOrder = nullptr;   // plan-time temporary: balanced row order (plan.cu: k_row_order), node of every thread slot, -1 = padding

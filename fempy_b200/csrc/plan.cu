@@ -753,6 +753,7 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
                     int restTotal = 0;
                     if (!rc && cudaMemcpyAsync(&restTotal, d_restPtr + N, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
                     if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
+                    b.fanRestTotal = restTotal;
                     if (!rc && cudaMalloc(&b.d_fanHdr, (size_t)Npad * (1 + rw) * sizeof(int4)) != cudaSuccess) rc = 1;
                     if (!rc && cudaMalloc(&b.d_fanRest, std::max<size_t>((size_t)restTotal * rw, 1) * sizeof(int4)) != cudaSuccess) rc = 1;
                     if (!rc) {
@@ -882,6 +883,9 @@ extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t valu
     } else if (!strcmp(name, "fan_compact")) {
         if (p->finalized) return fail("femb_plan_set_option: fan_compact must be set before finalize");
         p->fanCompactAllowed = value != 0;
+    } else if (!strcmp(name, "fan_prefetch")) {
+        if (value < -1) return fail("femb_plan_set_option: fan_prefetch must be -1 (default), 0 (off) or a distance in 32-node warps");
+        p->fanPrefetch = (int)value;
     } else if (!strcmp(name, "fan_rows")) {
         if (value != 0 && value != 1) return fail("femb_plan_set_option: fan_rows must be 0 or 1");
         p->useFan = value != 0;
