@@ -454,6 +454,26 @@ def run_ours(args, rank, world, local_rank):
 
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads to the CPUs NVML reports as closest to its GPU, so that the pinned staging buffers
+    (first touch) land on that NUMA node and the per-step H2D / D2H copies do not all cross one socket.  Returns the
+    resulting CPU set (or the reason nothing was done)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = sorted(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        if not after:
+            os.sched_setaffinity(0, before)
+            return "unchanged (empty NVML set)"
+        return f"{len(after)} cpus ({after[0]}-{after[-1]})"
+    except Exception as exc:  # containers often hide the topology: keep the inherited affinity
+        return f"unchanged ({type(exc).__name__})"
+
+
 def run_ours_multi(args, rank, world, local_rank, dev):
     """N > 1: the mesh is element-partitioned over the ranks (fempy_b200/dist.py): every rank assembles the CSR row
     block of the nodes it owns, interface partial sums travel over NCCL.  Weak scaling: config 2's per-GPU share
@@ -478,6 +498,7 @@ def run_ours_multi(args, rank, world, local_rank, dev):
         sys.stdout.flush()
         os.dup2(savedStdout, 1)
         os.close(savedStdout)
+    affinity = bind_to_gpu_numa_node(local_rank)
     strong = args.config == "c5"
     if strong:
         nx = ny = args.nx or 5000
@@ -512,12 +533,20 @@ def run_ours_multi(args, rank, world, local_rank, dev):
     h_thick, h_states, h_loads = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (thickLocal, states[part.localNodes], loadsLocal))
     d_thick, d_states, d_loads = (h.to(dev) for h in (h_thick, h_states, h_loads))
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    flushRead = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+
+    def flush_l2():
+        """same flush as the single-GPU arm: 512 MB write, then a 256 MB read so that the write's dirty lines are written
+        back before the timed region"""
+        flush.zero_()
+        if not args.flush_write_only:
+            flushRead.sum()
 
     def step():
         return da.assemble(d_thick, d_states, d_loads, True)
 
     for _ in range(args.warmup):
-        flush.zero_()
+        flush_l2()
         step()
     torch.cuda.synchronize()
     launches_per_step = asm.plan.lastLaunches
@@ -529,7 +558,7 @@ def run_ours_multi(args, rank, world, local_rank, dev):
     dist.barrier()
     sampler.start()
     for i in range(args.steps):
-        flush.zero_()
+        flush_l2()
         starts[i].record(stream)
         step()
         ends[i].record(stream)
@@ -538,12 +567,16 @@ def run_ours_multi(args, rank, world, local_rank, dev):
     clocks = sampler.stop()
     asm.plan.profile(True)  # roofline leg: in-library events, outside the timed steps
     for i in range(min(args.steps, 50)):
-        flush.zero_()
+        flush_l2()
         step()
     torch.cuda.synchronize()
     kernel_ms_sum, kernel_calls = asm.plan.profileRead()
     asm.plan.profile(False)
     total_ms = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, ends))], dtype=torch.float64, device=dev)
+    perRank = torch.zeros(world, 2, dtype=torch.float64, device=dev)  # every rank's own step / kernel time
+    perRank[rank, 0] = total_ms[0] / args.steps
+    perRank[rank, 1] = kernel_ms_sum / max(kernel_calls, 1)
+    dist.all_reduce(perRank, op=dist.ReduceOp.SUM)
     dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)  # the slowest rank sets the pace
     ms_per_step = float(total_ms.item()) / args.steps
     value = numEl / (ms_per_step * 1e-3)
@@ -583,12 +616,12 @@ def run_ours_multi(args, rank, world, local_rank, dev):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "elements": numEl, "dof": 2 * N, "nnz": int(counts[4].item()),
-                       "l2": "flushed between timed steps (512 MB write)", "partition": "contiguous node ranges; element -> owner of its lowest node",
+                       "l2": "flushed between timed steps (512 MB write" + ("" if args.flush_write_only else " + 256 MB read, as at N=1") + ")", "partition": "contiguous node ranges; element -> owner of its lowest node",
                        "collective": ("none: boundary elements are evaluated by every rank owning one of their nodes (owner-computes rows)" if args.dist_mode == "halo"
                                       else "NCCL batched send/recv of interface-row partial sums"), "interface_bytes_per_step": int(counts[2].item())},
             "nnz_per_s": counts[4].item() / (ms_per_step * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_assemble_rows on rank 0's local mesh", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": "k_assemble_fan on rank 0's local mesh", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": peak_src},
             "e2e": {"value": numEl / float(e2e_t.item()), "unit": "elements/s", "ms_per_step": 1e3 * float(e2e_t.item()),
                     "h2d_bytes_per_step": int(counts[0].item()), "d2h_bytes_per_step": int(counts[1].item()),
@@ -596,6 +629,8 @@ def run_ours_multi(args, rank, world, local_rank, dev):
             "gpu_launches": int(launches_per_step * args.steps * world), "launches_per_step": int(launches_per_step), "clocks": clocks,
             "plan_build": {"wall_ms": plan_wall_ms, "device_ms": asm.plan.buildMs},
             "elements_evaluated": int(counts[3].item()),
+            "per_rank": {"ms_per_step": [round(v, 5) for v in perRank[:, 0].tolist()], "kernel_ms": [round(v, 5) for v in perRank[:, 1].tolist()]},
+            "host_affinity": affinity,
         }  # fmt: skip
         print(json.dumps(line))
     dist.destroy_process_group()
