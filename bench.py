@@ -292,13 +292,49 @@ def run_reference_port(args, config):
     print(json.dumps(line))
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (None if absent)."""
+def ncu_traffic(config):
+    """DRAM bytes per launch of the dominant kernel of a configuration, from the committed ncu --set full capture
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep; None if absent)."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
-            return json.load(f).get(kernel)
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f).get(config, {}).get("dram_bytes")
     except OSError:
         return None
+
+
+def fp64_peak():
+    """FP64 peak measured on a B200 of this pool with tools/micro/fp64_peak.cu (profiles/r02_fp64_peak.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_fp64_peak.json")) as f:
+            return json.load(f)["fp64_tflops"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+# minimal FP64 operations per element (symmetric, B-sparse count of SURVEY.md section 8d)
+MIN_FLOPS = {"quad": 1170.0, "quad9": 9900.0, "triangle": 240.0}
+
+
+class _PluginProblem:
+    """What bench.py needs of a load case to drive B200AssemblyMixin the way FEMpyProblem.updateJacobian /
+    updateResidual do (FEMpy/Problem.py:239-264): the attributes SURVEY.md section 8b lists, nothing else."""
+
+    def __init__(self, wl, el, cm):
+        from types import SimpleNamespace
+
+        elType = wl["elType"]
+        self.constitutiveModel = cm
+        self.model = SimpleNamespace(
+            numNodes=wl["numNodes"], numDim=2, constitutiveModel=cm, nodeCoords=wl["coords"], dvs={"Thickness": wl["thick"]},
+            elements={elType: {"elementObject": el, "connectivity": wl["conn"][elType], "numElements": wl["numElems"]}})
+        self.numDOF = 2 * wl["numNodes"]
+        self.states = wl["states"]
+        loaded = np.flatnonzero(wl["loads"])
+        self.loads = {"Load": {"DOF": loaded.tolist(), "Value": wl["loads"][loaded].tolist()}}
+        self._bcs = {"Fixed": {"DOF": wl["bcDOF"].tolist(), "Value": wl["bcVal"].tolist()}}
+
+    def getBCs(self):
+        return self._bcs
 
 
 def run_ours(args, rank, world, local_rank):
@@ -393,13 +429,41 @@ def run_ours(args, rank, world, local_rank):
     alg_bytes = algorithmic_bytes(wl, nnz)
     kernel_ms = kernel_ms_sum / max(kernel_calls, 1)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    nn = wl["conn"][elType].shape[1]
+    if args.path == "scatter" or not plan.info("rows_path"):
+        kernel = f"k_assemble_sym<{nn}> (fused K_e / R_e evaluation + RED.F64 scatter through the slot map)"
+    elif plan.info("fan_path"):
+        kernel = (f"k_assemble_fan<{nn}> (one thread per node row pair: corners walked as a fan, closed-form element rows, every 2x2 block "
+                  "finished in registers and staged once, coalesced warp write-out; BCs, loads and residual fused)")
+    else:
+        kernel = f"k_assemble_rows<{nn}> (one thread per node row pair, accumulator rows in shared memory, coalesced warp write-out; BCs, loads, residual fused)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (ncu_traffic({"c2": "k_assemble_rows", "c3": "k_assemble_rows_config3", "c4": "k_assemble_rows_config4"}.get(args.config, ""))
-                            if (args.path == "rows" and args.nx is None) else None),
-                "kernel": {"rows": "k_assemble_rows (one thread per node row, redundant element geometry, private swizzled smem row, coalesced warp write-out; BCs and loads fused)",
-                           "scatter": "k_assemble_sym (fused K_e/R_e evaluation + RED.F64 scatter)"}[args.path], "kernel_ms": kernel_ms,
+                "traffic": ncu_traffic(args.config) if (args.path == "rows" and args.nx is None and not args.no_fan) else None,
+                "kernel": kernel, "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_element": alg_bytes / numEl,
                 "peak_source": peak_src, "step_frac_of_roofline": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
+    f64 = fp64_peak()
+    if f64:
+        minTf = MIN_FLOPS[elType] * numEl / (kernel_ms * 1e-3) / 1e12
+        roofline["fp64"] = {"peak_tflops": f64, "peak_source": "profiles/r02_fp64_peak.json (tools/micro/fp64_peak.cu on a B200 of this pool)",
+                            "min_flops_per_element": MIN_FLOPS[elType], "achieved_tflops_min_count": minTf, "frac": minTf / f64}
+
+    # --- stress recovery: von Mises, mean over the element's Gauss points, device-resident ---------
+    d_vm = torch.empty(numEl, dtype=torch.float64, device=dev)
+    for _ in range(3):
+        plan.functionDev(d_coords, d_states, mat, 1, 2, d_vm)
+    fs = [torch.cuda.Event(enable_timing=True) for _ in range(20)]
+    fe = [torch.cuda.Event(enable_timing=True) for _ in range(20)]
+    for i in range(20):
+        flush_l2()
+        fs[i].record(stream)
+        plan.functionDev(d_coords, d_states, mat, 1, 2, d_vm)
+        fe[i].record(stream)
+    torch.cuda.synchronize()
+    vm_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(fs, fe)]))
+    vm_bytes = 4 * nn * numEl + 32 * wl["numNodes"] + 8 * numEl  # connectivity + coords + states read, one value per element written
+    function = {"von_mises_mean": {"ms": vm_ms, "elements_per_s": numEl / (vm_ms * 1e-3), "algorithmic_bytes": vm_bytes,
+                                   "frac_of_hbm_roofline": vm_bytes / (vm_ms * 1e-3) / 1e9 / peak, "checksum": float(d_vm.sum().item())}}
 
     # --- end to end through the host-pointer C ABI (pinned host buffers) ---------------------------
     def pinned(a):
@@ -434,6 +498,26 @@ def run_ours(args, rank, world, local_rank):
     assert float(h_R.sum()) == checksum
     e2e["resident_geometry"] = {"value": numEl / res_s, "ms_per_step": 1e3 * res_s,
                                 "h2d_bytes_per_step": int(h_states.nbytes + h_loads.nbytes)}
+    e2e["K_abs_checksum"] = float(np.abs(h_K).sum())
+    e2e["residual_abs_checksum"] = float(np.abs(h_R).sum())
+    # the plugin seam itself: B200AssemblyMixin._assembleMatrix + _assembleResidual as FEMpyProblem.updateJacobian /
+    # updateResidual call them (FEMpy/Problem.py:239-264): pageable numpy arrays, a scipy csr_array built per call,
+    # two kernel passes (K, then R)
+    from fempy_b200.problem import B200AssemblyMixin
+
+    plug = type("BenchProblem", (B200AssemblyMixin, _PluginProblem), {})(wl, el, cm)
+    plug.model._b200_plan = plan
+    plan.setGeometry(None, None)
+    for _ in range(2):
+        Kp, Rp = plug._assembleMatrix(plug.states, applyBCs=True), plug._assembleResidual(plug.states, applyBCs=True)
+    t0 = time.perf_counter()
+    psteps = max(3, min(args.steps, 10))
+    for _ in range(psteps):
+        Kp, Rp = plug._assembleMatrix(plug.states, applyBCs=True), plug._assembleResidual(plug.states, applyBCs=True)
+    plug_s = (time.perf_counter() - t0) / psteps
+    assert Kp.nnz == nnz and float(Rp.sum()) == checksum, "plugin path and C-ABI path disagree"
+    e2e["plugin"] = {"value": numEl / plug_s, "ms_per_step": 1e3 * plug_s,
+                     "api": "B200AssemblyMixin._assembleMatrix + _assembleResidual (pageable numpy in, scipy csr_array + ndarray out)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -442,14 +526,20 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": wl["desc"], "elements": numEl, "dof": numDOF, "nnz": nnz, "l2": "flushed between timed steps (512 MB write" + ("" if args.flush_write_only else " + 256 MB read so its dirty lines are written back before the timed region") + ")",
                    "states": "1e-3*rng(0)", "bcs": int(wl["bcDOF"].size)},
         "nnz_per_s": nnz / (ms_per_step * 1e-3), "ms_per_step_min": float(times.min()), "ms_per_step_median": float(np.median(times)),
-        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": roofline, "e2e": e2e, "function": function, "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step), "clocks": clocks,
         "plan_build": {"device_ms": plan.buildMs, "wall_ms": plan_wall_ms},
         "path": {"assembly_path": args.path, "rows_path": plan.info("rows_path"), "max_degree": plan.info("max_degree"), "rows_balanced": plan.info("rows_balanced"),
                  "row_iters": [plan.info("row_iters_node_order"), plan.info("row_iters_balanced")], "closed_form_q4": plan.info("closed_form_q4"), "fan_path": plan.info("fan_path")},
     }  # fmt: skip
     if not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(wl, args.config, args.nx)
+        cb = line["cpu_baseline"] = cpu_baseline(wl, args.config, args.nx)
+        # the GPU result against the reference's own, where the reference assembled the same (whole) mesh in this run
+        if cb.get("kind") == "reference" and cb.get("sampled_rows") is None and args.nx is None:
+            dR = abs(cb["residual_checksum"] - checksum) / e2e["residual_abs_checksum"]
+            dK = abs(cb["K_abs_checksum"] - e2e["K_abs_checksum"]) / cb["K_abs_checksum"]
+            line["parity_vs_reference_in_this_run"] = {"residual_sum_rel_diff": dR, "K_abs_sum_rel_diff": dK, "tolerance": 1e-12}
+            assert dR < 1e-12 and dK < 1e-12, f"GPU result differs from the reference's: R {dR:.2e}, K {dK:.2e}"
     print(json.dumps(line))
 
 

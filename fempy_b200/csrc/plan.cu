@@ -1052,6 +1052,7 @@ extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const doubl
             cnt2[2 * j + (dofs[i] & 1)] = counts[i];
             val2[2 * j + (dofs[i] & 1)] = vals[i];
         }
+        if (cnt2.size() / 2 >= (1u << 22)) return fail("femb_plan_set_bcs: more than 2^22 constrained nodes do not fit the per-node BC word");
         dfree(p->d_bcInfo); dfree(p->d_bcNodeCnt); dfree(p->d_bcNodeVal);
         TRY(dalloc(&p->d_bcInfo, (size_t)p->numNodes));
         TRY(dalloc(&p->d_bcNodeCnt, cnt2.size()));

@@ -110,6 +110,7 @@ class DistributedAssembly:
         self.blockIndices = p.global_dofs(self.indices[self.k0 : self.k1])
         self._negotiate()
         self._bcFilter = None
+        self._ownedMask = None
 
     # -- plan time: who sends what where -------------------------------------------------------------------
     def _negotiate(self):
@@ -194,6 +195,19 @@ class DistributedAssembly:
         t = self.torch
         bcd = getattr(self, "bcLocal", None) if applyBCs else None
         bcv = getattr(self, "bcVal", None) if applyBCs else None
+        if loadsLocal is not None and self.part.mode == "exchange":
+            # loads are applied by the OWNER of a row only: the partial sums of ghost rows travel to their owner, which
+            # subtracts its own loads -- entries given for ghost rows are dropped here (halo mode never returns those rows)
+            if t.is_tensor(loadsLocal):
+                if self._ownedMask is None:
+                    m = np.zeros(2 * self.part.numLocalNodes)
+                    m[self.part.owned_dof_slice()] = 1.0
+                    self._ownedMask = t.from_numpy(m).to(loadsLocal.device)
+                loadsLocal = loadsLocal * self._ownedMask
+            else:
+                masked = np.zeros(2 * self.part.numLocalNodes)
+                masked[self.part.owned_dof_slice()] = np.asarray(loadsLocal, dtype=np.float64)[self.part.owned_dof_slice()]
+                loadsLocal = masked
         K, R = self.asm.assemble(thicknessLocal, statesLocal, loadsLocal, bcd, bcv, applyBCs)
         ops, recvBufs = [], {}
         for s in self._sendKd:
@@ -235,7 +249,6 @@ class GpuLocalAssembler:
         self.d_coords = torch.from_numpy(self.localCoords).to(self.device)
         self.d_K = torch.empty(self.plan.nnz, dtype=torch.float64, device=self.device)
         self.d_R = torch.empty(self.plan.numDOF, dtype=torch.float64, device=self.device)
-        self._bcKey = None
 
     def pattern(self):
         return self.plan.pattern()
@@ -249,10 +262,7 @@ class GpuLocalAssembler:
         st = states if t.is_tensor(states) else self.to_device(states)
         ld = None if loads is None else (loads if t.is_tensor(loads) else self.to_device(loads))
         if applyBCs and bcDOF is not None:
-            key = (id(bcDOF), len(bcDOF))
-            if key != self._bcKey:
-                self.plan.setBCs(bcDOF, bcVal)
-                self._bcKey = key
+            self.plan.setBCs(bcDOF, bcVal)  # femb_plan_set_bcs returns early when the lists are the ones it already holds
         self.plan.setStream(t.cuda.current_stream(self.device).cuda_stream)
         self.plan.assembleDev(self.d_coords, st, th, self.material, bool(applyBCs and bcDOF is not None and len(bcDOF)), ld, self.d_K, self.d_R)
         return self.d_K, self.d_R

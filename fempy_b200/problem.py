@@ -48,19 +48,24 @@ class B200AssemblyMixin:
     """The CUDA assembly path behind FEMpyProblem's private assembly drivers."""
 
     def _b200Inputs(self, states):
-        """Plan + inputs of one call.  A model that counts its geometry changes (`_b200_geomVersion`, bumped by this
-        package's FEMpyModel.setCoordinates / setDesignVariables) keeps node coordinates and thickness on the device:
-        they are uploaded when the count moves and the calls pass None (device-side model, femb_plan_set_geometry).
-        The reference's own FEMpyModel has no such counter: its arrays are uploaded on every call."""
+        """Plan + inputs of one call.  By default node coordinates and thickness are read from the model and uploaded on
+        EVERY call, exactly as the reference re-reads `model.nodeCoords` / `model.dvs` in every assembly
+        (FEMpy/Problem.py:590-595) -- in-place edits of those public arrays are always seen.
+        Opt-in residency (device-side model, femb_plan_set_geometry): a caller that sets `model._b200_residentGeometry =
+        True` promises to change the geometry only through calls that bump `model._b200_geomVersion` (or to bump it
+        itself); the arrays are then uploaded when the count moves and the calls pass None."""
         plan = planFor(self.model)
         coords = np.ascontiguousarray(self.model.nodeCoords, dtype=np.float64)
         thickness = np.ascontiguousarray(self.model.dvs["Thickness"], dtype=np.float64)
         version = getattr(self.model, "_b200_geomVersion", None)
-        if version is not None:
+        if version is not None and getattr(self.model, "_b200_residentGeometry", False):
             if getattr(plan, "_geomVersion", None) != version:
                 plan.setGeometry(coords, thickness)
                 plan._geomVersion = version
             coords = thickness = None
+        elif getattr(plan, "_geomVersion", None) is not None:  # residency was switched off again
+            plan.setGeometry(None, None)
+            plan._geomVersion = None
         return plan, coords, np.ascontiguousarray(states, dtype=np.float64), thickness, materialFor(self.constitutiveModel)
 
     def _assembleMatrix(self, states, applyBCs=True):
@@ -104,6 +109,9 @@ class B200AssemblyMixin:
         bcDOF, bcVal = AssemblyUtils.convertBCDictToLists(self.getBCs())
         loads = AssemblyUtils.convertLoadsDictToVector(self.loads, self.numDOF) if self.loads else None
         update, R, iters, res = plan.assembleSolve(coords, q, thickness, mat, bcDOF, bcVal, loads, relTol, maxIter)
+        if not (res <= relTol):  # also catches NaN (singular system); the states stay untouched
+            raise RuntimeError(f"solveOnDevice: PCG stopped after {iters} iterations at relative residual {res:.3e} > {relTol:.1e} "
+                               "(raise maxIter, or use solve() for the host direct solver)")
         self.Res = R
         self.incrementState(update)
         self.solveCounter += 1

@@ -90,9 +90,9 @@ def _worker(rank, world, port, kind, applyBCs, mode):
         da = DistributedAssembly(part, asm, torch.device("cpu"))
         if applyBCs:
             da.set_bcs(bcDOF, bcVal)
-        loadsLocal = np.zeros(2 * part.numLocalNodes)
-        own = part.owned_dof_slice()
-        loadsLocal[own] = loads[2 * part.n0 : 2 * part.n1]
+        # the loads of ALL local nodes, ghost rows included: a row's load is applied by its owner only (the exchange
+        # mode drops the ghost entries itself, the halo mode never returns those rows)
+        loadsLocal = loads[part.global_dofs(np.arange(2 * part.numLocalNodes))]
         Kb, Rb = da.assemble(part.local_thickness(thick, offsets), states[part.localNodes], loadsLocal, applyBCs)
 
         gathered = [None] * world
