@@ -138,6 +138,28 @@ static inline void dfree(T*& p) {
     p = nullptr;
 }
 
+// device scratch released when the scope ends: the C ABI's error paths return early (CUDA_TRY / TRY)
+template <typename T>
+struct Scratch {
+    T* p = nullptr;
+    Scratch() = default;
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    ~Scratch() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T)); }
+    operator T*() const { return p; }
+};
+struct ScopedEvent {
+    cudaEvent_t e = nullptr;
+    ~ScopedEvent() {
+        if (e) cudaEventDestroy(e);
+    }
+    cudaError_t create() { return cudaEventCreate(&e); }
+    operator cudaEvent_t() const { return e; }
+};
+
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 static inline int use_device(const femb_plan* p) {

@@ -186,9 +186,9 @@ extern "C" int femb_element_blocks(femb_plan* p, const double* coords, const dou
     TRY(stage(&p->s_coords, coords, (size_t)p->numNodes * 2, p->stream));
     TRY(stage(&p->s_states, states, (size_t)numDOF, p->stream));
     TRY(stage(&p->s_thick, thickness, (size_t)p->numElems, p->stream));
-    double *d_Ke = nullptr, *d_Re = nullptr;
-    if (Ke) CUDA_TRY(cudaMalloc(&d_Ke, p->keTotal * sizeof(double)));
-    if (Re) CUDA_TRY(cudaMalloc(&d_Re, p->reTotal * sizeof(double)));
+    Scratch<double> d_Ke, d_Re;
+    if (Ke) CUDA_TRY(d_Ke.alloc(p->keTotal));
+    if (Re) CUDA_TRY(d_Re.alloc(p->reTotal));
     const DMat D = make_dmat(*mat);
     int64_t launches = 0;
     for (auto& b : p->blocks) {
@@ -203,8 +203,8 @@ extern "C" int femb_element_blocks(femb_plan* p, const double* coords, const dou
         A.thick = p->s_thick;
         A.K = nullptr;
         A.R = nullptr;
-        FEMB_DISPATCH_FAMILY(b.nn, b.nq, (launch_blocks<NN, NQ>(b, D, A, mat->nonlinear != 0, d_Ke ? d_Ke + b.keOffset : nullptr,
-                                                               d_Re ? d_Re + b.reOffset : nullptr, p->stream)));
+        FEMB_DISPATCH_FAMILY(b.nn, b.nq, (launch_blocks<NN, NQ>(b, D, A, mat->nonlinear != 0, d_Ke.p ? d_Ke.p + b.keOffset : nullptr,
+                                                               d_Re.p ? d_Re.p + b.reOffset : nullptr, p->stream)));
         launches++;
     }
     p->launches = launches;
@@ -212,8 +212,6 @@ extern "C" int femb_element_blocks(femb_plan* p, const double* coords, const dou
     if (Ke && cudaMemcpyAsync(Ke, d_Ke, p->keTotal * sizeof(double), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess) rc = 1;
     if (Re && cudaMemcpyAsync(Re, d_Re, p->reTotal * sizeof(double), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess) rc = 1;
     if (cudaStreamSynchronize(p->stream) != cudaSuccess) rc = 1;
-    cudaFree(d_Ke);
-    cudaFree(d_Re);
     if (rc) return fail("femb_element_blocks: %s", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
@@ -249,16 +247,16 @@ extern "C" int femb_local_matrices_to_coo(const double* localMats, const int64_t
     *numOut = 0;
     if (n == 0) return 0;
     CUDA_TRY(cudaSetDevice(device));
-    double *d_vals = nullptr, *d_out = nullptr;
-    long long *d_dof = nullptr, *d_rows = nullptr, *d_cols = nullptr;
-    int *d_flags = nullptr, *d_pos = nullptr;
-    CUDA_TRY(cudaMalloc(&d_vals, n * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&d_out, n * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&d_dof, numElems * nd * sizeof(long long)));
-    CUDA_TRY(cudaMalloc(&d_rows, n * sizeof(long long)));
-    CUDA_TRY(cudaMalloc(&d_cols, n * sizeof(long long)));
-    CUDA_TRY(cudaMalloc(&d_flags, n * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d_pos, (n + 1) * sizeof(int)));
+    Scratch<double> d_vals, d_out;
+    Scratch<long long> d_dof, d_rows, d_cols;
+    Scratch<int> d_flags, d_pos;
+    CUDA_TRY(d_vals.alloc(n));
+    CUDA_TRY(d_out.alloc(n));
+    CUDA_TRY(d_dof.alloc(numElems * nd));
+    CUDA_TRY(d_rows.alloc(n));
+    CUDA_TRY(d_cols.alloc(n));
+    CUDA_TRY(d_flags.alloc(n));
+    CUDA_TRY(d_pos.alloc(n + 1));
     CUDA_TRY(cudaMemcpy(d_vals, localMats, n * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_dof, localDOF, numElems * nd * sizeof(long long), cudaMemcpyHostToDevice));
     int64_t launches = 0;
@@ -271,13 +269,6 @@ extern "C" int femb_local_matrices_to_coo(const double* localMats, const int64_t
     CUDA_TRY(cudaMemcpy(cols, d_cols, total * sizeof(long long), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(vals, d_out, total * sizeof(double), cudaMemcpyDeviceToHost));
     *numOut = total;
-    cudaFree(d_vals);
-    cudaFree(d_out);
-    cudaFree(d_dof);
-    cudaFree(d_rows);
-    cudaFree(d_cols);
-    cudaFree(d_flags);
-    cudaFree(d_pos);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -300,13 +291,13 @@ extern "C" int femb_scatter_local_residuals(const double* localRes, const int64_
     if (femb_device_count() == 0) return fail("femb_scatter_local_residuals: no CUDA device available");
     CUDA_TRY(cudaSetDevice(device));
     const int64_t n = numElems * nn, nd = numNodes * numStates;
-    double *d_res = nullptr, *d_R = nullptr;
-    long long* d_conn = nullptr;
-    int* d_flag = nullptr;
-    CUDA_TRY(cudaMalloc(&d_res, std::max<int64_t>(n * numStates, 1) * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&d_R, std::max<int64_t>(nd, 1) * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&d_conn, std::max<int64_t>(n, 1) * sizeof(long long)));
-    CUDA_TRY(cudaMalloc(&d_flag, sizeof(int)));
+    Scratch<double> d_res, d_R;
+    Scratch<long long> d_conn;
+    Scratch<int> d_flag;
+    CUDA_TRY(d_res.alloc(n * numStates));
+    CUDA_TRY(d_R.alloc(nd));
+    CUDA_TRY(d_conn.alloc(n));
+    CUDA_TRY(d_flag.alloc(1));
     CUDA_TRY(cudaMemset(d_flag, 0, sizeof(int)));
     CUDA_TRY(cudaMemcpy(d_res, localRes, n * numStates * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_R, globalResidual, nd * sizeof(double), cudaMemcpyHostToDevice));
@@ -315,10 +306,6 @@ extern "C" int femb_scatter_local_residuals(const double* localRes, const int64_
     int flag = 0;
     CUDA_TRY(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(globalResidual, d_R, nd * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(d_res);
-    cudaFree(d_R);
-    cudaFree(d_conn);
-    cudaFree(d_flag);
     if (flag) return fail("femb_scatter_local_residuals: connectivity out of range");
     return 0;
 }

@@ -595,9 +595,9 @@ extern "C" int femb_plan_add_block(femb_plan* p, int32_t nn, int32_t nq, const d
     b.w.assign(w, w + nq);
     if (nn <= 4) b.cyclic = tables_cyclic_invariant(nn, nq, dNdxi, w);
     b.closedForm = b.cyclic && ((nn == 4 && standard_q4(nq, dNdxi, w)) || (nn == 3 && standard_t3(nq, dNdxi, w)));
-    long long* d_conn64 = nullptr;
+    Scratch<long long> d_conn64;
     const size_t cnt = (size_t)numElems * nn;
-    CUDA_TRY(cudaMalloc(&d_conn64, cnt * sizeof(long long)));
+    CUDA_TRY(d_conn64.alloc(cnt));
     CUDA_TRY(cudaMalloc(&b.d_conn, cnt * sizeof(int)));
     CUDA_TRY(cudaMemcpyAsync(d_conn64, conn, cnt * sizeof(long long), cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
@@ -606,7 +606,6 @@ extern "C" int femb_plan_add_block(femb_plan* p, int32_t nn, int32_t nq, const d
     int flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
-    cudaFree(d_conn64);
     if (flag) {
         cudaFree(b.d_conn);
         return fail("femb_plan_add_block: connectivity refers to a node outside [0, %lld)", (long long)p->numNodes);
@@ -625,22 +624,21 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
     if (p->blocks.empty()) return fail("femb_plan_finalize: no element blocks");
     TRY(use_device(p));
     cudaStream_t st = p->stream;
-    cudaEvent_t ev0, ev1;
-    CUDA_TRY(cudaEventCreate(&ev0));
-    CUDA_TRY(cudaEventCreate(&ev1));
+    ScopedEvent ev0, ev1;
+    CUDA_TRY(ev0.create());
+    CUDA_TRY(ev1.create());
     CUDA_TRY(cudaEventRecord(ev0, st));
     const int64_t N = p->numNodes;
     int64_t launches = 0;
-    int *d_adjCount = nullptr, *d_candCount = nullptr, *d_candPtr = nullptr, *d_cursor = nullptr;
-    int *d_cand = nullptr, *d_deg = nullptr;
+    Scratch<int> d_adjCount, d_candCount, d_candPtr, d_cursor, d_cand, d_deg;  // plan-time temporaries (freed on every path)
     int*& d_adjPtr = p->d_adjPtr;
     int*& d_adj = p->d_adj;
-    CUDA_TRY(cudaMalloc(&d_adjCount, (N + 1) * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d_candCount, (N + 1) * sizeof(int)));
+    CUDA_TRY(d_adjCount.alloc(N + 1));
+    CUDA_TRY(d_candCount.alloc(N + 1));
     CUDA_TRY(cudaMalloc(&d_adjPtr, (N + 1) * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d_candPtr, (N + 1) * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d_cursor, (N + 1) * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d_deg, (N + 1) * sizeof(int)));
+    CUDA_TRY(d_candPtr.alloc(N + 1));
+    CUDA_TRY(d_cursor.alloc(N + 1));
+    CUDA_TRY(d_deg.alloc(N + 1));
     CUDA_TRY(cudaMemsetAsync(d_adjCount, 0, (N + 1) * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(d_candCount, 0, (N + 1) * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(d_cursor, 0, (N + 1) * sizeof(int), st));
@@ -655,7 +653,7 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
     TRY(exclusive_scan(d_adjCount, d_adjPtr, N, st, launches));
     TRY(exclusive_scan(d_candCount, d_candPtr, N, st, launches));
     CUDA_TRY(cudaMalloc(&d_adj, std::max<int64_t>(totalAdj, 1) * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d_cand, std::max<int64_t>(totalCand, 1) * sizeof(int)));
+    CUDA_TRY(d_cand.alloc((size_t)totalCand));
     BlockTable bt;
     bt.numBlocks = (int)p->blocks.size();
     for (int i = 0; i < bt.numBlocks; ++i) {
@@ -744,9 +742,9 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
                 if (b.fanOK) {  // kernel-side layout: per-node headers + first record, further records behind
                     const int rw = (b.nn == 4 && !b.fanCompact) ? 2 : 1;
                     const long long Npad = (N + 31) / 32 * 32;
-                    int *d_cnt = nullptr, *d_restPtr = nullptr;
-                    CUDA_TRY(cudaMalloc(&d_cnt, (N + 1) * sizeof(int)));
-                    CUDA_TRY(cudaMalloc(&d_restPtr, (N + 1) * sizeof(int)));
+                    Scratch<int> d_cnt, d_restPtr;
+                    CUDA_TRY(d_cnt.alloc(N + 1));
+                    CUDA_TRY(d_restPtr.alloc(N + 1));
                     k_fan_rest_count<<<grid_for(N, 256), 256, 0, st>>>(N, p->d_blockAdj, p->d_blockAdj + (size_t)N, d_cnt);
                     launches++;
                     int rc = exclusive_scan(d_cnt, d_restPtr, N, st, launches);
@@ -762,8 +760,6 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
                         launches++;
                         if (cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
                     }
-                    cudaFree(d_cnt);
-                    cudaFree(d_restPtr);
                     dfree(b.d_fanRec);  // the kernel reads headers + rest only
                     dfree(b.d_fanElem);
                     if (rc) return fail("femb_plan_finalize: building the fan headers failed (%s)", cudaGetErrorString(cudaGetLastError()));
@@ -771,16 +767,15 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
             }
             {  // balanced row schedule: kept only when it saves more than 8 % of the warps' corner iterations
                 const long long windows = (N + ROW_WINDOW - 1) / ROW_WINDOW;
-                unsigned long long* d_iters = nullptr;
+                Scratch<unsigned long long> d_iters;
                 unsigned long long iters[2] = {0, 0};
                 CUDA_TRY(cudaMalloc(&p->d_rowOrder, windows * ROW_WINDOW * sizeof(int)));
-                CUDA_TRY(cudaMalloc(&d_iters, sizeof(iters)));
+                CUDA_TRY(d_iters.alloc(2));
                 CUDA_TRY(cudaMemsetAsync(d_iters, 0, sizeof(iters), st));
                 k_row_order<<<(unsigned)windows, ROW_WINDOW, 0, st>>>(N, p->d_blockAdj, p->d_blockAdj + nb * (size_t)N, p->d_rowOrder, d_iters);
                 launches++;
                 CUDA_TRY(cudaMemcpyAsync(iters, d_iters, sizeof(iters), cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaStreamSynchronize(st));
-                cudaFree(d_iters);
                 p->rowSlots = windows * ROW_WINDOW;
                 p->rowIters[0] = (long long)iters[0];
                 p->rowIters[1] = (long long)iters[1];
@@ -803,14 +798,6 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     cudaEventElapsedTime(&p->buildMs, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    cudaFree(d_adjCount);
-    cudaFree(d_candCount);
-    cudaFree(d_candPtr);
-    cudaFree(d_cursor);
-    cudaFree(d_cand);
-    cudaFree(d_deg);
     p->launches = launches;
     p->finalized = true;
     return 0;
@@ -950,18 +937,16 @@ extern "C" int femb_plan_pattern(femb_plan* p, int64_t* indptr, int64_t* indices
     TRY(need_final(p, "femb_plan_pattern"));
     TRY(use_device(p));
     const int64_t nd = femb_plan_num_dof(p), nnz = femb_plan_nnz(p);
-    long long *d_ip = nullptr, *d_ix = nullptr;
-    CUDA_TRY(cudaMalloc(&d_ip, (nd + 1) * sizeof(long long)));
-    CUDA_TRY(cudaMalloc(&d_ix, std::max<int64_t>(nnz, 1) * sizeof(long long)));
-    int rc = femb_plan_pattern_dev(p, (int64_t*)d_ip, (int64_t*)d_ix);
+    Scratch<long long> d_ip, d_ix;
+    CUDA_TRY(d_ip.alloc(nd + 1));
+    CUDA_TRY(d_ix.alloc((size_t)nnz));
+    int rc = femb_plan_pattern_dev(p, (int64_t*)d_ip.p, (int64_t*)d_ix.p);
     if (!rc) {
         cudaError_t e1 = cudaMemcpyAsync(indptr, d_ip, (nd + 1) * sizeof(long long), cudaMemcpyDeviceToHost, p->stream);
         cudaError_t e2 = cudaMemcpyAsync(indices, d_ix, nnz * sizeof(long long), cudaMemcpyDeviceToHost, p->stream);
         cudaError_t e3 = cudaStreamSynchronize(p->stream);
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = fail("femb_plan_pattern: copy back failed");
     }
-    cudaFree(d_ip);
-    cudaFree(d_ix);
     return rc;
 }
 
