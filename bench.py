@@ -65,9 +65,9 @@ class ClockSampler(threading.Thread):
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.maxMhz = index, [], set(), None
+        self.index, self.samples, self.reasons, self.maxMhz, self.period = index, [], set(), None, period
         self._halt = threading.Event()
         try:
             import pynvml
@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def stop(self):
         self._halt.set()
@@ -526,6 +526,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": wl["desc"], "elements": numEl, "dof": numDOF, "nnz": nnz, "l2": "flushed between timed steps (512 MB write" + ("" if args.flush_write_only else " + 256 MB read so its dirty lines are written back before the timed region") + ")",
                    "states": "1e-3*rng(0)", "bcs": int(wl["bcDOF"].size)},
         "nnz_per_s": nnz / (ms_per_step * 1e-3), "ms_per_step_min": float(times.min()), "ms_per_step_median": float(np.median(times)),
+        "ms_per_step_p90": float(np.percentile(times, 90)), "ms_per_step_max": float(times.max()),
         "roofline": roofline, "e2e": e2e, "function": function, "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step), "clocks": clocks,
         "plan_build": {"device_ms": plan.buildMs, "wall_ms": plan_wall_ms},

@@ -314,8 +314,8 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.maxDeg = p->maxDeg;
             A.zero = 0;
             {   // L2 look-ahead distance: by default the warps one resident wave ahead (SMs x resident warps per SM)
-                int sms = 148;
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+                if (p->numSMs <= 0 && cudaDeviceGetAttribute(&p->numSMs, cudaDevAttrMultiProcessorCount, p->device) != cudaSuccess) p->numSMs = 148;
+                const int sms = p->numSMs;
                 const long long warps = p->fanPrefetch >= 0 ? p->fanPrefetch : (long long)sms * (b.nn == 3 ? fan::resident_warps<3>() : fan::resident_warps<4>());
                 const long long pfNodes = std::min<long long>(warps * fan::BLOCK, p->numNodes);
                 const double perNode = (double)pfNodes / (double)p->numNodes;

@@ -74,6 +74,7 @@ struct BlockTable {  // kernel-side view of all blocks (pattern build)
 
 struct femb_plan {
     int device = 0;
+    int numSMs = 0;  // cached on first use
     int64_t numNodes = 0;
     int numDim = 2, numStates = 2;
     std::vector<BlockData> blocks;

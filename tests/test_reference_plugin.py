@@ -41,7 +41,11 @@ def _case(elType="quad", n=24):
     rng = np.random.default_rng(11)
     thick = rng.random(conn[elType].shape[0]) * 1e-2 + 1e-3
     states = 1e-3 * rng.random(coords.shape)
-    return coords, conn, thick, states, meshes.edge_nodes(coords, x=0.0), meshes.edge_nodes(coords, x=2.0)
+    left, right = meshes.edge_nodes(coords, x=0.0), meshes.edge_nodes(coords, x=2.0)
+    # nodes nudged off the grid (as tests/testProblem.py:52-54 does): no element entry is an exact zero, so the reference's
+    # value-dependent pattern (AssemblyUtils.py:208-212 drops exact zeros) is the structural one
+    coords = coords + 2e-3 / n * rng.random(coords.shape)
+    return coords, conn, thick, states, left, right
 
 
 def test_install_swaps_only_the_problem_class():
@@ -61,7 +65,7 @@ def test_install_swaps_only_the_problem_class():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("elType,n", [("quad", 24), ("quad9", 9), ("triangle", 20)])
-def test_reference_problem_on_the_cuda_path(elType, n):
+def test_reference_problem_on_the_cuda_path(elType, n, tmp_path):
     """the reference's own drivers (updateJacobian / updateResidual / computeFunction / solve) on a B200Problem against
     the same calls on the stock FEMpyProblem: pattern bit-exact, values to 1e-12, the solved states to solver accuracy"""
     fp, ref, model, ours = _both(*_case(elType, n))
@@ -88,6 +92,28 @@ def test_reference_problem_on_the_cuda_path(elType, n):
     K1.sort_indices()
     assert np.abs(K2.data - 2.0 * K1.data).max() < 1e-12 * np.abs(K1.data).max() * 2
     model.dvs["Thickness"][:] /= 2.0
+    # the reference's writeSolution (Problem.py:506-559) consumes the stress recovery: three computeFunction passes per
+    # output function, written through meshio -- here the stub's Mesh, whose write() is captured
+    import meshio
+
+    captured = []
+    stockWrite = meshio.Mesh.write
+    meshio.Mesh.write = lambda self, name, *a, **k: captured.append((name, self))
+    try:
+        for prob in (ref, ours):
+            prob.setOption("outputFunctions", ["Von-Mises-Stress"])
+            prob.setOption("outputDir", str(tmp_path))
+            with contextlib.redirect_stdout(io.StringIO()):
+                prob.writeSolution(baseName="solution")
+    finally:
+        meshio.Mesh.write = stockWrite
+    (nameR, meshR), (nameO, meshO) = captured
+    assert nameR == nameO and set(meshR.cell_data) == set(meshO.cell_data) and "Von-Mises-Stress_max" in meshO.cell_data
+    for key in meshR.cell_data:
+        for a, b in zip(meshR.cell_data[key], meshO.cell_data[key]):
+            assert np.abs(np.asarray(a) - np.asarray(b)).max() <= 1e-12 * max(np.abs(np.asarray(a)).max(), 1e-300)
+    for key in meshR.point_data:
+        assert np.array_equal(meshR.point_data[key], meshO.point_data[key])
     # the reference's solve driver around the CUDA assembly
     with contextlib.redirect_stdout(io.StringIO()):
         ref.solve()
