@@ -597,132 +597,154 @@ def run_ours_multi(args, rank, world, local_rank, dev):
     else:
         nx, ny = args.nx or 512, (args.nx or 512) * world
         desc = f"config2 per GPU: structured Q4 {nx}x{ny} = {world} x ({nx}x{nx}), iso plane stress, element-partitioned (weak scaling)"
-    coords, conn = meshes.quad4_grid(nx, ny)
-    N = coords.shape[0]
-    numEl = conn["quad"].shape[0]
-    rng = np.random.default_rng(0)
-    states = 1e-3 * rng.random((N, 2))
-    left, right = meshes.edge_nodes(coords, x=0.0), meshes.edge_nodes(coords, x=2.0)
-    bcDOF = np.stack((2 * left, 2 * left + 1), axis=1).reshape(-1).astype(np.int64)
-    bcVal = np.zeros(bcDOF.size)
-    cm = Constitutive.IsoPlaneStress(MAT["E"], MAT["nu"], MAT["rho"], MAT["t"])
 
-    t0 = time.perf_counter()
-    part = Partition(N, conn, rank, world, mode=args.dist_mode)
-    asm = GpuLocalAssembler(part, {"quad": Elements.QuadElement2D(1).tables()}, coords, cm.material(), local_rank)
-    da = DistributedAssembly(part, asm, dev)
-    da.set_bcs(bcDOF, bcVal)
-    plan_wall_ms = 1e3 * (time.perf_counter() - t0)
+    def measure(nx, ny, desc, strong, steps, warmup):
+        """one partitioned workload: plan, device-timed steps (max over ranks), roofline leg, end-to-end leg; the JSON line
+        on rank 0 (None elsewhere)"""
+        coords, conn = meshes.quad4_grid(nx, ny)
+        N = coords.shape[0]
+        numEl = conn["quad"].shape[0]
+        rng = np.random.default_rng(0)
+        states = 1e-3 * rng.random((N, 2))
+        left, right = meshes.edge_nodes(coords, x=0.0), meshes.edge_nodes(coords, x=2.0)
+        bcDOF = np.stack((2 * left, 2 * left + 1), axis=1).reshape(-1).astype(np.int64)
+        bcVal = np.zeros(bcDOF.size)
+        cm = Constitutive.IsoPlaneStress(MAT["E"], MAT["nu"], MAT["rho"], MAT["t"])
 
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    own = part.owned_dof_slice()
-    loadsLocal = np.zeros(2 * part.numLocalNodes)
-    ownRight = right[(right >= part.n0) & (right < part.n1)]
-    loadsLocal[2 * np.searchsorted(part.localNodes, ownRight)] += 1e4
-    thickLocal = part.local_thickness(np.full(numEl, MAT["t"]), {"quad": 0})
-    h_thick, h_states, h_loads = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (thickLocal, states[part.localNodes], loadsLocal))
-    d_thick, d_states, d_loads = (h.to(dev) for h in (h_thick, h_states, h_loads))
-    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    flushRead = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+        t0 = time.perf_counter()
+        part = Partition(N, conn, rank, world, mode=args.dist_mode)
+        asm = GpuLocalAssembler(part, {"quad": Elements.QuadElement2D(1).tables()}, coords, cm.material(), local_rank)
+        da = DistributedAssembly(part, asm, dev)
+        da.set_bcs(bcDOF, bcVal)
+        plan_wall_ms = 1e3 * (time.perf_counter() - t0)
 
-    def flush_l2():
-        """same flush as the single-GPU arm: 512 MB write, then a 256 MB read so that the write's dirty lines are written
-        back before the timed region"""
-        flush.zero_()
-        if not args.flush_write_only:
-            flushRead.sum()
+        stream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(stream)
+        own = part.owned_dof_slice()
+        loadsLocal = np.zeros(2 * part.numLocalNodes)
+        ownRight = right[(right >= part.n0) & (right < part.n1)]
+        loadsLocal[2 * np.searchsorted(part.localNodes, ownRight)] += 1e4
+        thickLocal = part.local_thickness(np.full(numEl, MAT["t"]), {"quad": 0})
+        h_thick, h_states, h_loads = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (thickLocal, states[part.localNodes], loadsLocal))
+        d_thick, d_states, d_loads = (h.to(dev) for h in (h_thick, h_states, h_loads))
+        flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        flushRead = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
 
-    def step():
-        return da.assemble(d_thick, d_states, d_loads, True)
+        def flush_l2():
+            """same flush as the single-GPU arm: 512 MB write, then a 256 MB read so that the write's dirty lines are written
+            back before the timed region"""
+            flush.zero_()
+            if not args.flush_write_only:
+                flushRead.sum()
 
-    for _ in range(args.warmup):
-        flush_l2()
-        step()
-    torch.cuda.synchronize()
-    launches_per_step = asm.plan.lastLaunches
+        def step():
+            return da.assemble(d_thick, d_states, d_loads, True)
 
-    sampler = ClockSampler(local_rank)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    dist.barrier()
-    sampler.start()
-    for i in range(args.steps):
-        flush_l2()
-        starts[i].record(stream)
-        step()
-        ends[i].record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    clocks = sampler.stop()
-    asm.plan.profile(True)  # roofline leg: in-library events, outside the timed steps
-    for i in range(min(args.steps, 50)):
-        flush_l2()
-        step()
-    torch.cuda.synchronize()
-    kernel_ms_sum, kernel_calls = asm.plan.profileRead()
-    asm.plan.profile(False)
-    total_ms = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, ends))], dtype=torch.float64, device=dev)
-    perRank = torch.zeros(world, 2, dtype=torch.float64, device=dev)  # every rank's own step / kernel time
-    perRank[rank, 0] = total_ms[0] / args.steps
-    perRank[rank, 1] = kernel_ms_sum / max(kernel_calls, 1)
-    dist.all_reduce(perRank, op=dist.ReduceOp.SUM)
-    dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)  # the slowest rank sets the pace
-    ms_per_step = float(total_ms.item()) / args.steps
-    value = numEl / (ms_per_step * 1e-3)
-
-    # end to end: pinned host inputs -> device, assemble + exchange, owned row block -> pinned host, every step
-    Kb, Rb = step()
-    h_K = torch.empty(Kb.shape, dtype=torch.float64).pin_memory()
-    h_R = torch.empty(Rb.shape, dtype=torch.float64).pin_memory()
-    e2e_steps = max(3, min(args.steps, 20))
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        d_thick.copy_(h_thick, non_blocking=True)
-        d_states.copy_(h_states, non_blocking=True)
-        d_loads.copy_(h_loads, non_blocking=True)
-        Kb, Rb = step()
-        h_K.copy_(Kb, non_blocking=True)
-        h_R.copy_(Rb, non_blocking=True)
+        for _ in range(warmup):
+            flush_l2()
+            step()
         torch.cuda.synchronize()
-    dist.barrier()
-    e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    counts = torch.tensor([h_thick.nbytes + h_states.nbytes + h_loads.nbytes, h_K.nbytes + h_R.nbytes, da.interface_bytes(),
-                           int(part.numActiveElems), int(Kb.numel())], dtype=torch.float64, device=dev)
-    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        launches_per_step = asm.plan.lastLaunches
 
+        sampler = ClockSampler(local_rank)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        torch.cuda.synchronize()
+        dist.barrier()
+        sampler.start()
+        for i in range(steps):
+            flush_l2()
+            starts[i].record(stream)
+            step()
+            ends[i].record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        clocks = sampler.stop()
+        asm.plan.profile(True)  # roofline leg: in-library events, outside the timed steps
+        for i in range(min(steps, 50)):
+            flush_l2()
+            step()
+        torch.cuda.synchronize()
+        kernel_ms_sum, kernel_calls = asm.plan.profileRead()
+        asm.plan.profile(False)
+        total_ms = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, ends))], dtype=torch.float64, device=dev)
+        perRank = torch.zeros(world, 2, dtype=torch.float64, device=dev)  # every rank's own step / kernel time
+        perRank[rank, 0] = total_ms[0] / steps
+        perRank[rank, 1] = kernel_ms_sum / max(kernel_calls, 1)
+        dist.all_reduce(perRank, op=dist.ReduceOp.SUM)
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)  # the slowest rank sets the pace
+        ms_per_step = float(total_ms.item()) / steps
+        value = numEl / (ms_per_step * 1e-3)
+
+        # end to end: pinned host inputs -> device, assemble + exchange, owned row block -> pinned host, every step
+        Kb, Rb = step()
+        h_K = torch.empty(Kb.shape, dtype=torch.float64).pin_memory()
+        h_R = torch.empty(Rb.shape, dtype=torch.float64).pin_memory()
+        e2e_steps = max(3, min(steps, 20))
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            d_thick.copy_(h_thick, non_blocking=True)
+            d_states.copy_(h_states, non_blocking=True)
+            d_loads.copy_(h_loads, non_blocking=True)
+            Kb, Rb = step()
+            h_K.copy_(Kb, non_blocking=True)
+            h_R.copy_(Rb, non_blocking=True)
+            torch.cuda.synchronize()
+        dist.barrier()
+        e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        counts = torch.tensor([h_thick.nbytes + h_states.nbytes + h_loads.nbytes, h_K.nbytes + h_R.nbytes, da.interface_bytes(),
+                               int(part.numActiveElems), int(Kb.numel())], dtype=torch.float64, device=dev)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+
+        if rank == 0:
+            peak, peak_src = measured_peaks()
+            nnzLocal = asm.plan.nnz
+            localEl = asm.plan.numElements
+            alg_bytes = 4 * 4 * localEl + 16 * part.numLocalNodes * 2 + 8 * localEl + 8 * nnzLocal + 16 * part.numLocalNodes
+            kernel_ms = kernel_ms_sum / max(kernel_calls, 1)
+            achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+            line = {
+                "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "elements": numEl, "dof": 2 * N, "nnz": int(counts[4].item()),
+                           "l2": "flushed between timed steps (512 MB write" + ("" if args.flush_write_only else " + 256 MB read, as at N=1") + ")", "partition": "contiguous node ranges; element -> owner of its lowest node",
+                           "collective": ("none: boundary elements are evaluated by every rank owning one of their nodes (owner-computes rows)" if args.dist_mode == "halo"
+                                          else "NCCL batched send/recv of interface-row partial sums"), "interface_bytes_per_step": int(counts[2].item())},
+                "nnz_per_s": counts[4].item() / (ms_per_step * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "kernel": "k_assemble_fan on rank 0's local mesh", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                             "peak_source": peak_src},
+                "e2e": {"value": numEl / float(e2e_t.item()), "unit": "elements/s", "ms_per_step": 1e3 * float(e2e_t.item()),
+                        "h2d_bytes_per_step": int(counts[0].item()), "d2h_bytes_per_step": int(counts[1].item()),
+                        "api": "DistributedAssembly.assemble (pinned host inputs, owned row blocks back to pinned host)",
+                        "host_gbs_aggregate": (counts[0].item() + counts[1].item()) / float(e2e_t.item()) / 1e9},
+                "gpu_launches": int(launches_per_step * steps * world), "launches_per_step": int(launches_per_step), "clocks": clocks,
+                "plan_build": {"wall_ms": plan_wall_ms, "device_ms": asm.plan.buildMs},
+                "elements_evaluated": int(counts[3].item()),
+                "per_rank": {"ms_per_step": [round(v, 5) for v in perRank[:, 0].tolist()], "kernel_ms": [round(v, 5) for v in perRank[:, 1].tolist()]},
+                "host_affinity": affinity,
+            }  # fmt: skip
+            return line
+        return None
+
+    line = measure(nx, ny, desc, strong, args.steps, args.warmup)
+    if not strong and args.nx is None and not args.no_strong:
+        # the multi-GPU configuration BASELINE.json names (config 5, 50 M DOF) beside the weak-scaling line: same ranks,
+        # fixed mesh (strong scaling), fewer steps
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        c5 = measure(5000, 5000, f"config5: structured Q4 5000x5000, iso plane stress, element-partitioned over {world} GPUs (strong scaling)",
+                     True, max(3, min(args.steps, 20)), 3)
+        if rank == 0:
+            line["config5_strong"] = {k: c5[k] for k in ("value", "unit", "ms_per_step", "scaling", "config", "nnz_per_s", "roofline", "e2e", "per_rank",
+                                                       "elements_evaluated", "plan_build")}
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        nnzLocal = asm.plan.nnz
-        localEl = asm.plan.numElements
-        alg_bytes = 4 * 4 * localEl + 16 * part.numLocalNodes * 2 + 8 * localEl + 8 * nnzLocal + 16 * part.numLocalNodes
-        kernel_ms = kernel_ms_sum / max(kernel_calls, 1)
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "elements": numEl, "dof": 2 * N, "nnz": int(counts[4].item()),
-                       "l2": "flushed between timed steps (512 MB write" + ("" if args.flush_write_only else " + 256 MB read, as at N=1") + ")", "partition": "contiguous node ranges; element -> owner of its lowest node",
-                       "collective": ("none: boundary elements are evaluated by every rank owning one of their nodes (owner-computes rows)" if args.dist_mode == "halo"
-                                      else "NCCL batched send/recv of interface-row partial sums"), "interface_bytes_per_step": int(counts[2].item())},
-            "nnz_per_s": counts[4].item() / (ms_per_step * 1e-3),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_assemble_fan on rank 0's local mesh", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "peak_source": peak_src},
-            "e2e": {"value": numEl / float(e2e_t.item()), "unit": "elements/s", "ms_per_step": 1e3 * float(e2e_t.item()),
-                    "h2d_bytes_per_step": int(counts[0].item()), "d2h_bytes_per_step": int(counts[1].item()),
-                    "api": "DistributedAssembly.assemble (pinned host inputs, owned row blocks back to pinned host)"},
-            "gpu_launches": int(launches_per_step * args.steps * world), "launches_per_step": int(launches_per_step), "clocks": clocks,
-            "plan_build": {"wall_ms": plan_wall_ms, "device_ms": asm.plan.buildMs},
-            "elements_evaluated": int(counts[3].item()),
-            "per_rank": {"ms_per_step": [round(v, 5) for v in perRank[:, 0].tolist()], "kernel_ms": [round(v, 5) for v in perRank[:, 1].tolist()]},
-            "host_affinity": affinity,
-        }  # fmt: skip
         print(json.dumps(line))
     dist.destroy_process_group()
 
@@ -742,6 +764,7 @@ def main():
     ap.add_argument("--dist-mode", default="halo", choices=["halo", "exchange"], help="multi-GPU: redundant boundary elements (no exchange) or unique elements + NCCL interface exchange")
     ap.add_argument("--no-fan", action="store_true", help="accumulating row-owner kernel instead of the write-once fan kernel (exploration only)")
     ap.add_argument("--plan-opt", action="append", default=[], metavar="NAME=INT", help="femb_plan_set_option before finalize (exploration only)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the config-5 strong-scaling leg of the default line")
     ap.add_argument("--no-bcs", action="store_true", help="device-timed steps without boundary conditions (exploration only)")
     ap.add_argument("--path", default="rows", choices=["rows", "scatter"],
                     help="assembly path: row-owner kernel (default) or slot-map scatter with FP64 atomics")
