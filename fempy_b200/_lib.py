@@ -53,6 +53,8 @@ _SIGNATURES = {
     "femb_plan_profile_read": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),
     "femb_plan_row_stats": (C.c_int, [C.c_void_p, C.c_int32, c_int64_p, C.c_int64]),
     "femb_function": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.POINTER(Material), C.c_int32, C.c_int32, c_double_p]),
+    "femb_point_quantities": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                        c_double_p]),
     "femb_function_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Material), C.c_int32, C.c_int32, C.c_void_p]),
     "femb_solve_pcg": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int32, C.POINTER(C.c_int32), c_double_p]),
     "femb_solve_pcg_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.POINTER(C.c_int32),

@@ -139,8 +139,10 @@ bool rows_path_available(const femb_plan* p) {
     // every block needs corner records (<= 12 nodes per element: 16-node quads stay on the scatter kernels, their strip
     // alone is 64 doubles per thread)
     if (p->assemblyPath != 2 || !p->rowsBuilt || p->maxDeg > rows::MAXD) return false;
-    for (auto& b : p->blocks)
+    for (auto& b : p->blocks) {
         if (b.nn <= 4 && !b.cyclic) return false;  // rotated corner records need tables invariant under cyclic renumbering
+        if (!default_rule(b.nn, b.nq)) return false;  // non-default quadrature rules run on the scatter kernels
+    }
     const size_t smem = (size_t)2 * p->maxDeg * rows::BLOCK * (sizeof(double2) + 1) + rows::BLOCK * sizeof(double2);
     return smem <= 200 * 1024;
 }
@@ -370,7 +372,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.thick = d_thick;
             A.K = d_K;
             A.R = d_R;
-            FEMB_DISPATCH_FAMILY(b.nn, b.nq, (launch_assemble_variant<NN, NQ, ROW>(b, D, A, mat->nonlinear != 0, wk, wr, st)));
+            FEMB_DISPATCH_ANY(b.nn, b.nq, (launch_assemble_variant<NN, NQ, ROW>(b, D, A, mat->nonlinear != 0, wk, wr, st)));
         }
         launches++;
     }

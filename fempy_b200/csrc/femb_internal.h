@@ -92,6 +92,7 @@ struct femb_plan {
     int assemblyPath = 2;        // 2 row-owner kernel, 0 slot-map scatter with FP64 atomics
     bool fanCompactAllowed = true;  // option "fan_compact" (tests): 0 keeps the wide fan records even when the differences fit
     int fanPrefetch = -1;        // option "fan_prefetch": L2 look-ahead of the fan kernel in 32-node warps (-1: one resident wave, 0: off)
+    bool pointsOnly = false;     // option "points_only": blocks of any size, femb_point_quantities only
     bool useFan = true;          // option "fan_rows": write-once fan kernel where it applies (else the accumulating row-owner kernel)
     int* d_blockAdj = nullptr;   // (numBlocks+1) x numNodes: start of each block's corners in a node's adjacency list (row-owner kernel)
     int* d_rowOrder = nullptr;   // plan-time temporary: balanced row order (plan.cu: k_row_order), node of every thread slot, -1 = padding
@@ -263,10 +264,19 @@ static inline femb::DMat make_dmat(const femb_material& m) {
     return D;
 }
 
-static inline bool family_supported(int nn, int nq) {
+// the families' default rules (QuadElement2D.py:65-67, TriElement2D.py:92-94): the row-owner / fan kernels are built for these
+static inline bool default_rule(int nn, int nq) {
     return (nn == 3 && nq == 1) || (nn == 6 && nq == 3) || (nn == 10 && nq == 3) || (nn == 4 && nq == 4) ||
            (nn == 9 && nq == 9) || (nn == 16 && nq == 16);
 }
+// other quadrature rules (`intOrder=` of the element-level methods, Element.py:163,370,426; a model may also be built on
+// them): n x n Gauss rules with n = 1..4 for the quads, the 1- / 3- / 4-point rules for the triangles
+// (FEMpy/Quadrature/TriQuad.py:28-35).  These run on the scatter kernels, the element-block and the function kernels.
+static inline bool extra_rule(int nn, int nq) {
+    return (nn == 4 && (nq == 1 || nq == 9 || nq == 16)) || (nn == 9 && (nq == 4 || nq == 16)) || (nn == 16 && nq == 9) ||
+           (nn == 3 && (nq == 3 || nq == 4)) || (nn == 6 && (nq == 1 || nq == 4)) || (nn == 10 && (nq == 1 || nq == 4));
+}
+static inline bool family_supported(int nn, int nq) { return default_rule(nn, nq) || extra_rule(nn, nq); }
 
 // body sees constexpr NN, NQ and ROW (row-split kernels for the families that do not fit one thread)
 #define FEMB_DISPATCH_FAMILY(nn, nq, BODY)                                                                                 \
@@ -278,4 +288,18 @@ static inline bool family_supported(int nn, int nq) {
         else if ((nn) == 10 && (nq) == 3) { constexpr int NN = 10, NQ = 3; constexpr bool ROW = true; (void)ROW; BODY; }   \
         else if ((nn) == 16 && (nq) == 16) { constexpr int NN = 16, NQ = 16; constexpr bool ROW = true; (void)ROW; BODY; } \
         else return fail("unsupported element family: %d nodes, %d quadrature points", (nn), (nq));                        \
+    } while (0)
+
+// every supported (nodes, rule) pair: the default rules above + the extra rules (generic kernels only)
+#define FEMB_CASE(n_, q_, row_, BODY) if ((nn_) == n_ && (nq_) == q_) { constexpr int NN = n_, NQ = q_; constexpr bool ROW = row_; (void)ROW; BODY; }
+#define FEMB_DISPATCH_ANY(nnArg, nqArg, BODY)                                                                              \
+    do {                                                                                                                   \
+        const int nn_ = (nnArg), nq_ = (nqArg);                                                                            \
+        FEMB_CASE(3, 1, false, BODY) else FEMB_CASE(3, 3, false, BODY) else FEMB_CASE(3, 4, false, BODY)                   \
+        else FEMB_CASE(4, 4, false, BODY) else FEMB_CASE(4, 1, false, BODY) else FEMB_CASE(4, 9, false, BODY)              \
+        else FEMB_CASE(4, 16, false, BODY) else FEMB_CASE(6, 3, true, BODY) else FEMB_CASE(6, 1, true, BODY)               \
+        else FEMB_CASE(6, 4, true, BODY) else FEMB_CASE(9, 9, true, BODY) else FEMB_CASE(9, 4, true, BODY)                 \
+        else FEMB_CASE(9, 16, true, BODY) else FEMB_CASE(10, 3, true, BODY) else FEMB_CASE(10, 1, true, BODY)              \
+        else FEMB_CASE(10, 4, true, BODY) else FEMB_CASE(16, 16, true, BODY) else FEMB_CASE(16, 9, true, BODY)             \
+        else return fail("unsupported element family: %d nodes, %d quadrature points", nn_, nq_);                          \
     } while (0)

@@ -137,7 +137,7 @@ extern "C" int femb_function_dev(femb_plan* p, const double* d_coords, const dou
         F.coords = (const double2*)d_coords;
         F.states = (const double2*)d_states;
         F.out = d_out + (reduction == FEMB_REDUCE_NONE ? b.pointOffset : b.elemOffset);
-        FEMB_DISPATCH_FAMILY(b.nn, b.nq, (launch_function<NN, NQ>(b, D, F, mat->nonlinear != 0, func, reduction, p->stream)));
+        FEMB_DISPATCH_ANY(b.nn, b.nq, (launch_function<NN, NQ>(b, D, F, mat->nonlinear != 0, func, reduction, p->stream)));
         launches++;
     }
     p->launches = launches;
@@ -162,6 +162,127 @@ extern "C" int femb_function(femb_plan* p, const double* coords, const double* s
     TRY(femb_function_dev(p, p->s_coords, p->s_states, mat, func, reduction, p->s_out));
     CUDA_TRY(cudaMemcpyAsync(out, p->s_out, nout * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// =============================================================================================
+// point quantities: Element._computeFunctionEvaluationQuantities (FEMpy/Elements/Element.py:275-368) at the block's points
+//   Coord / State   sum_a N_a(p) X_a, sum_a N_a(p) q_a                (_interpolationProduct, Element.py:918-939)
+//   Jac             J[i][j] = sum_a dN_a/dxi_i X_a[j]                 (_computeNPrimeCoordProduct, :942-978)
+//   JacDet          signed determinant                                (LinAlg.py:70-90)
+//   StateGrad       u'[s][d] = sum_a (J^-1 dN_a)[d] q_a[s]            (_computeUPrimeProduct, :981-1018)
+//   StateGradSens   (J^-1 dN)[d][a]                                   (_computeDUPrimeDqProduct, :1021-1048)
+// One thread per (element, point); node count and point count are run-time values (tables in global memory), so any
+// family and any rule -- or any set of parametric points -- runs through this one kernel.
+// =============================================================================================
+struct PointArgs {
+    long long E;
+    int nn, nq;
+    const int* conn;         // node-major
+    const double* N;         // (nq, nn)
+    const double* dN;        // (nq, 2, nn)
+    const double2* coords;
+    const double2* states;
+    double *coord, *state, *grad, *jac, *det, *sens;  // (E*nq, ...) outputs of this block, any may be NULL
+};
+
+__global__ void __launch_bounds__(128) k_point_quantities(const PointArgs P) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.E * P.nq) return;
+    const long long e = t / P.nq;
+    const int p = (int)(t - e * P.nq);
+    const double* Np = P.N + (size_t)p * P.nn;
+    const double* d0 = P.dN + (size_t)p * 2 * P.nn;
+    const double* d1 = d0 + P.nn;
+    double cx = 0.0, cy = 0.0, sx = 0.0, sy = 0.0, J00 = 0.0, J01 = 0.0, J10 = 0.0, J11 = 0.0, H00 = 0.0, H01 = 0.0, H10 = 0.0, H11 = 0.0;
+    for (int a = 0; a < P.nn; ++a) {
+        const int node = __ldg(P.conn + (long long)a * P.E + e);
+        const double2 X = __ldg(P.coords + node), q = __ldg(P.states + node);
+        const double n = __ldg(Np + a), g0 = __ldg(d0 + a), g1 = __ldg(d1 + a);
+        cx = fma(n, X.x, cx), cy = fma(n, X.y, cy), sx = fma(n, q.x, sx), sy = fma(n, q.y, sy);
+        J00 = fma(g0, X.x, J00), J01 = fma(g0, X.y, J01), J10 = fma(g1, X.x, J10), J11 = fma(g1, X.y, J11);
+        H00 = fma(g0, q.x, H00), H01 = fma(g0, q.y, H01), H10 = fma(g1, q.x, H10), H11 = fma(g1, q.y, H11);
+    }
+    const double det = J00 * J11 - J01 * J10;
+    const double r = 1.0 / det;
+    const double i00 = J11 * r, i01 = -J01 * r, i10 = -J10 * r, i11 = J00 * r;  // J^-1
+    if (P.coord) P.coord[2 * t] = cx, P.coord[2 * t + 1] = cy;
+    if (P.state) P.state[2 * t] = sx, P.state[2 * t + 1] = sy;
+    if (P.jac) P.jac[4 * t] = J00, P.jac[4 * t + 1] = J01, P.jac[4 * t + 2] = J10, P.jac[4 * t + 3] = J11;
+    if (P.det) P.det[t] = det;
+    if (P.grad) {  // u'[s][d] = sum_k Jinv[d][k] H[k][s]
+        P.grad[4 * t] = i00 * H00 + i01 * H10;
+        P.grad[4 * t + 1] = i10 * H00 + i11 * H10;
+        P.grad[4 * t + 2] = i00 * H01 + i01 * H11;
+        P.grad[4 * t + 3] = i10 * H01 + i11 * H11;
+    }
+    if (P.sens) {
+        double* s = P.sens + (size_t)t * 2 * P.nn;
+        for (int a = 0; a < P.nn; ++a) {
+            const double g0 = __ldg(d0 + a), g1 = __ldg(d1 + a);
+            s[a] = i00 * g0 + i01 * g1;
+            s[P.nn + a] = i10 * g0 + i11 * g1;
+        }
+    }
+}
+
+extern "C" int femb_point_quantities(femb_plan* p, const double* coords, const double* states, double* coord, double* state,
+                                     double* stateGrad, double* jac, double* jacDet, double* stateGradSens) {
+    TRY(need_final(p, "femb_point_quantities"));
+    if (!states) return fail("femb_point_quantities: states is NULL");
+    if (!coord && !state && !stateGrad && !jac && !jacDet && !stateGradSens) return fail("femb_point_quantities: nothing requested");
+    TRY(use_device(p));
+    cudaStream_t st = p->stream;
+    TRY(stage_geometry(p, coords, nullptr, false, "femb_point_quantities"));
+    TRY(stage(&p->s_states, states, (size_t)femb_plan_num_dof(p), st));
+    const size_t np = (size_t)p->numPoints;
+    size_t sensTotal = 0;
+    for (auto& b : p->blocks) sensTotal += (size_t)b.numElems * b.nq * 2 * b.nn;
+    Scratch<double> d_coord, d_state, d_grad, d_jac, d_det, d_sens, d_tab;
+    if (coord) CUDA_TRY(d_coord.alloc(2 * np));
+    if (state) CUDA_TRY(d_state.alloc(2 * np));
+    if (stateGrad) CUDA_TRY(d_grad.alloc(4 * np));
+    if (jac) CUDA_TRY(d_jac.alloc(4 * np));
+    if (jacDet) CUDA_TRY(d_det.alloc(np));
+    if (stateGradSens) CUDA_TRY(d_sens.alloc(sensTotal));
+    size_t tabTotal = 0;
+    for (auto& b : p->blocks) tabTotal += b.N.size() + b.dN.size();
+    CUDA_TRY(d_tab.alloc(tabTotal));
+    size_t tabOff = 0, sensOff = 0;
+    int64_t launches = 0;
+    for (auto& b : p->blocks) {
+        CUDA_TRY(cudaMemcpyAsync(d_tab.p + tabOff, b.N.data(), b.N.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_tab.p + tabOff + b.N.size(), b.dN.data(), b.dN.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        PointArgs A;
+        A.E = b.numElems;
+        A.nn = b.nn;
+        A.nq = b.nq;
+        A.conn = b.d_conn;
+        A.N = d_tab.p + tabOff;
+        A.dN = d_tab.p + tabOff + b.N.size();
+        A.coords = (const double2*)p->s_coords;
+        A.states = (const double2*)p->s_states;
+        const size_t po = (size_t)b.pointOffset;
+        A.coord = coord ? d_coord.p + 2 * po : nullptr;
+        A.state = state ? d_state.p + 2 * po : nullptr;
+        A.grad = stateGrad ? d_grad.p + 4 * po : nullptr;
+        A.jac = jac ? d_jac.p + 4 * po : nullptr;
+        A.det = jacDet ? d_det.p + po : nullptr;
+        A.sens = stateGradSens ? d_sens.p + sensOff : nullptr;
+        k_point_quantities<<<grid_for(b.numElems * b.nq, 128), 128, 0, st>>>(A);
+        tabOff += b.N.size() + b.dN.size();
+        sensOff += (size_t)b.numElems * b.nq * 2 * b.nn;
+        launches++;
+    }
+    p->launches = launches;
+    if (coord) CUDA_TRY(cudaMemcpyAsync(coord, d_coord, 2 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (state) CUDA_TRY(cudaMemcpyAsync(state, d_state, 2 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (stateGrad) CUDA_TRY(cudaMemcpyAsync(stateGrad, d_grad, 4 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (jac) CUDA_TRY(cudaMemcpyAsync(jac, d_jac, 4 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (jacDet) CUDA_TRY(cudaMemcpyAsync(jacDet, d_det, np * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (stateGradSens) CUDA_TRY(cudaMemcpyAsync(stateGradSens, d_sens, sensTotal * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -203,7 +324,7 @@ extern "C" int femb_element_blocks(femb_plan* p, const double* coords, const dou
         A.thick = p->s_thick;
         A.K = nullptr;
         A.R = nullptr;
-        FEMB_DISPATCH_FAMILY(b.nn, b.nq, (launch_blocks<NN, NQ>(b, D, A, mat->nonlinear != 0, d_Ke.p ? d_Ke.p + b.keOffset : nullptr,
+        FEMB_DISPATCH_ANY(b.nn, b.nq, (launch_blocks<NN, NQ>(b, D, A, mat->nonlinear != 0, d_Ke.p ? d_Ke.p + b.keOffset : nullptr,
                                                                d_Re.p ? d_Re.p + b.reOffset : nullptr, p->stream)));
         launches++;
     }

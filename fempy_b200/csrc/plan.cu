@@ -577,7 +577,7 @@ extern "C" int femb_plan_add_block(femb_plan* p, int32_t nn, int32_t nq, const d
     if (!p) return fail("femb_plan_add_block: plan is NULL");
     if (p->finalized) return fail("femb_plan_add_block: plan already finalized");
     if ((int)p->blocks.size() >= MAX_BLOCKS) return fail("femb_plan_add_block: at most %d element types", MAX_BLOCKS);
-    if (!family_supported(nn, nq))
+    if (!family_supported(nn, nq) && !(p->pointsOnly && nn >= 1 && nn <= 64 && nq >= 1))
         return fail("femb_plan_add_block: unsupported element family (%d nodes, %d quadrature points)", nn, nq);
     if (numElems <= 0 || !conn || !N || !dNdxi || !w) return fail("femb_plan_add_block: bad arguments");
     if (numElems * (int64_t)nn * nn >= (1ll << 31)) return fail("femb_plan_add_block: block too large for int32 slot map");
@@ -685,7 +685,7 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
         CUDA_TRY(cudaMemcpyAsync(&p->maxDeg, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         launches++;
         bool rowsOk = true;
-        for (auto& b : p->blocks) rowsOk = rowsOk && b.nn <= 12 && b.numElems < (1ll << 28);
+        for (auto& b : p->blocks) rowsOk = rowsOk && b.nn <= 12 && b.numElems < (1ll << 28) && default_rule(b.nn, b.nq);
         if (rowsOk) {
             // row-owner kernel: per block element-major connectivity, corner records (indexed by the global corner
             // number) and, per node, where the block's corners start in the node's adjacency list (the list is sorted
@@ -870,6 +870,11 @@ extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t valu
     } else if (!strcmp(name, "fan_compact")) {
         if (p->finalized) return fail("femb_plan_set_option: fan_compact must be set before finalize");
         p->fanCompactAllowed = value != 0;
+    } else if (!strcmp(name, "points_only")) {
+        // blocks with any number of nodes / points: such a plan serves femb_point_quantities only (every other compute
+        // entry rejects a family it has no kernel for)
+        if (!p->blocks.empty()) return fail("femb_plan_set_option: points_only must be set before the first block");
+        p->pointsOnly = value != 0;
     } else if (!strcmp(name, "fan_prefetch")) {
         if (value < -1) return fail("femb_plan_set_option: fan_prefetch must be -1 (default), 0 (off) or a distance in 32-node warps");
         p->fanPrefetch = (int)value;

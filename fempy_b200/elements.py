@@ -84,16 +84,71 @@ class Element:
 
     def computeFunction(self, nodeCoords, nodeStates, elementDVs, function, elementReductionType, intOrder=None):
         """Element function values (Element.py:163-273); note the argument order differs from the two
-        methods above, as in the reference.  `function` is what `constitutiveModel.getFunction` returned."""
+        methods above, as in the reference.  `function` is what `constitutiveModel.getFunction` returned: the
+        functions of this package's models carry an id and are evaluated AND reduced in one fused kernel; any other
+        callable f(states, stateGradients, coords, dvs) -- e.g. the closures the reference's models return -- is evaluated
+        on the host from the point quantities the device computes (Coord, State, StateGrad, JacDet)."""
         if elementReductionType is not None:
             assert elementReductionType.lower() in ["sum", "mean", "integrate", "min", "max", "ksmax", "ksmin"], \
                 "elementReductionType not valid"
+        if not hasattr(function, "funcId"):
+            return self._computeCallable(nodeCoords, nodeStates, elementDVs, function, elementReductionType, intOrder)
         plan, X = self._flatPlan(nodeCoords, intOrder)
         q = np.ascontiguousarray(nodeStates, dtype=np.float64).reshape(-1, self.numStates)
         numElements = X.shape[0] // self.numNodes
         vals = plan.function(X, q, function.constitutiveModel.material(), function.funcId, elementReductionType)
         plan.close()
         return vals.reshape(numElements, -1) if elementReductionType is None else vals
+
+    def _computeCallable(self, nodeCoords, nodeStates, elementDVs, function, elementReductionType, intOrder):
+        order = self.quadratureOrder if intOrder is None else intOrder
+        w = self.getIntegrationPointWeights(order)
+        pts = np.atleast_2d(self.getIntegrationPointCoords(order))
+        numElements, numPoints = np.shape(nodeCoords)[0], len(w)
+        pq = self._computeFunctionEvaluationQuantities(pts, nodeStates, nodeCoords, elementDVs, ["Coord", "State", "StateGrad", "DVs", "JacDet"])
+        values = np.asarray(function(pq["State"], pq["StateGrad"], pq["Coord"], pq["DVs"]), dtype=np.float64).reshape(numElements, numPoints)
+        if elementReductionType is None:
+            return values
+        red = elementReductionType.lower()
+        if red in ("sum", "mean", "min", "max"):
+            return {"sum": np.sum, "mean": np.average, "min": np.min, "max": np.max}[red](values, axis=1)
+        if red == "integrate":
+            return np.einsum("ep,ep,p->e", values, pq["JacDet"].reshape(numElements, numPoints), w)
+        # "ksmax" and "ksmin" both take the reference's "ksmax" branch (Element.py:261-265): max + log(mean(exp(rho (v - max)))) / rho
+        rho = 100.0
+        m = values.max(axis=1)
+        return m + np.log(np.exp(rho * (values - m[:, None])).sum(axis=1) / numPoints) / rho
+
+    def _computeFunctionEvaluationQuantities(self, paramCoords, nodeStates, nodeCoords, designVars, quantities):
+        """Element._computeFunctionEvaluationQuantities (Element.py:275-368) with the per-element products on the device
+        (femb_point_quantities): N / NPrimeParam are host tables, Coord, State, StateGrad, Jac, JacDet, StateGradSens come
+        back as (numElements*numPoints, ...) arrays, DVs as a dict of per-point arrays.  (The reference never returns
+        "JacInv": its test for that key is case-mangled, Element.py:338.)"""
+        paramCoords = np.atleast_2d(np.asarray(paramCoords, dtype=np.float64))
+        nodeCoords = np.ascontiguousarray(nodeCoords, dtype=np.float64)
+        numElements, numPoints = nodeCoords.shape[0], paramCoords.shape[0]
+        if nodeCoords.shape[1:] != (self.numNodes, self.numDim):
+            raise ValueError("nodeCoords must be numElements x numNodes x numDim")
+        lower = [q.lower() for q in quantities]
+        out = {}
+        N = self.computeShapeFunctions(paramCoords)
+        dN = self.computeShapeFunctionGradients(paramCoords)
+        names = {"coord": "Coord", "state": "State", "stategrad": "StateGrad", "jac": "Jac", "jacdet": "JacDet", "stategradsens": "StateGradSens"}
+        want = tuple(names[q] for q in names if q in lower)
+        if want:
+            plan = AssemblyPlan(numElements * self.numNodes, self.numDim, self.numStates)
+            plan.setOption("points_only", 1)
+            conn = np.arange(numElements * self.numNodes, dtype=np.int64).reshape(numElements, self.numNodes)
+            plan.addBlock(N, dN, np.ones(numPoints), conn)
+            plan.finalize()
+            q = np.ascontiguousarray(nodeStates, dtype=np.float64).reshape(-1, self.numStates)
+            out.update(plan.pointQuantities(nodeCoords.reshape(-1, self.numDim), q, want))
+            plan.close()
+        if "nprimeparam" in lower:
+            out["NPrimeParam"] = dN
+        if "dvs" in lower:
+            out["DVs"] = {name: np.ascontiguousarray(np.repeat(vals, numPoints)) for name, vals in designVars.items()}
+        return out
 
 
 class QuadElement2D(Element):

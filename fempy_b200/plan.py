@@ -171,6 +171,22 @@ class AssemblyPlan:
                                       int(funcId), int(reduction), dptr(out)))
         return out
 
+    def pointQuantities(self, coords, states, want=("Coord", "State", "StateGrad", "JacDet")):
+        """Element._computeFunctionEvaluationQuantities on the device (femb_point_quantities) at the points the blocks were
+        added with: dict of (numPoints, ...) arrays for the names in `want` out of Coord, State, StateGrad, Jac, JacDet,
+        StateGradSens (single-block plans: (numPoints, numDim, nodesPerElement))."""
+        coords, states = (as_f64(coords) if coords is not None else None), as_f64(states)
+        P = self.numPoints
+        shapes = {"Coord": (P, 2), "State": (P, 2), "StateGrad": (P, 2, 2), "Jac": (P, 2, 2), "JacDet": (P,)}
+        if "StateGradSens" in want:
+            if len(self.blocks) != 1:
+                raise ValueError("StateGradSens needs a single-block plan")
+            shapes["StateGradSens"] = (P, 2, self.blocks[0][0])
+        out = {k: np.empty(shapes[k]) for k in want}
+        args = [dptr(out[k]) if k in out else None for k in ("Coord", "State", "StateGrad", "Jac", "JacDet", "StateGradSens")]
+        check(self._lib.femb_point_quantities(self._h, dptr(coords) if coords is not None else None, dptr(states), *args))
+        return out
+
     def elementBlocks(self, coords, states, thickness, material, wantK=True, wantR=True):
         coords, states, thickness = as_f64(coords), as_f64(states), as_f64(thickness)
         Ke = np.empty(sum(E * (2 * n) ** 2 for n, _, E in self.blocks)) if wantK else None

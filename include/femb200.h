@@ -159,6 +159,15 @@ int femb_function(femb_plan* plan, const double* coords, const double* states, c
 int femb_function_dev(femb_plan* plan, const double* d_coords, const double* d_states, const femb_material* mat,
                       int32_t func, int32_t reduction, double* d_out);
 
+/* ---- point quantities: Element._computeFunctionEvaluationQuantities (FEMpy/Elements/Element.py:275-368) with its helpers
+ * _interpolationProduct (:918-939), _computeNPrimeCoordProduct (:942-978), _computeUPrimeProduct (:981-1018),
+ * _computeDUPrimeDqProduct (:1021-1048) and det2 / inv2 (FEMpy/LinAlg/LinAlg.py:70-158), evaluated at the points the
+ * plan's blocks were added with (their N / dNdxi tables: the Gauss points of any rule, or any other parametric points).
+ * Outputs, (numPoints, ...) with the blocks concatenated in plan order, any may be NULL: coord (.,2), state (.,2),
+ * stateGrad (.,2,2) [state][dim], jac (.,2,2), jacDet (.), stateGradSens (.,2,nodesPerElem) per block. */
+int femb_point_quantities(femb_plan* plan, const double* coords, const double* states, double* coord, double* state,
+                          double* stateGrad, double* jac, double* jacDet, double* stateGradSens);
+
 /* ---- device-resident linear solve: the hand-off after assembly.
  * Replaces, on request, the host factorisation of FEMpyProblem.solveJacLinear (FEMpy/Problem.py:171-198).  K: the
  * plan's CSR values as femb_assemble[_dev] left them with applyBCs = 1 and the plan's current BC set (constrained rows =

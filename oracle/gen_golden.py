@@ -10,6 +10,7 @@ Fixtures
                   x {plane stress, plane strain} x {linear, Green strain}  (the "finer seams" of SURVEY 8b)
   meshes.npz      assembled K (CSR), R, element functions on small quad / quad9 / triangle / mixed meshes
   ks.npz          element-level KS reductions ("ksmax" / "ksmin", Element.py:261-265) of von Mises on the elements.npz inputs
+  points.npz      point quantities at arbitrary parametric points, non-default quadrature (intOrder), a caller-supplied function
   lbracket.npz    config 1: Examples/Meshes/LBracket.msh mesh arrays + assembled K, R, solution, functions
 """
 import os
@@ -90,6 +91,46 @@ def gen_ks(fp):
                 for red in ("ksmax", "ksmin"):
                     out[f"{key}_{red}"] = el.computeFunction(X, q, {"Thickness": thick}, cm.getFunction("Von-Mises-Stress"), red)
     np.savez_compressed(os.path.join(OUT, "ks.npz"), **out)
+
+
+EXTRA_RULES = {"quad1": (1, 3, 4), "quad2": (2, 4), "quad3": (3,), "tri1": (2, 3), "tri2": (1, 3), "tri3": (1, 3)}  # intOrder values
+
+
+def custom_function(states, stateGradients, coords, dvs):
+    """an element function that is NOT one of the constitutive models' own: it reads every argument the reference hands
+    to a point function (Element.py:203-214)"""
+    return states[:, 0] * coords[:, 1] + stateGradients[:, 0, 1] * dvs["Thickness"] - 3.0 * stateGradients[:, 1, 0] * coords[:, 0]
+
+
+def gen_points(fp):
+    """points.npz: Element._computeFunctionEvaluationQuantities (Element.py:275-368) at random parametric points, the
+    element-level methods with non-default quadrature (`intOrder=`, Element.py:163,370,426) and computeFunction with a
+    caller-supplied point function, all on the inputs of elements.npz."""
+    g = np.load(os.path.join(OUT, "elements.npz"))
+    out = {}
+    for name, el in families(fp).items():
+        X, q, thick = g[f"{name}_X"], g[f"{name}_q"], g[f"{name}_t"]
+        dvs = {"Thickness": thick}
+        rng = np.random.default_rng(7)
+        pts = rng.random((5, 2)) * (0.5 if name.startswith("tri") else 2.0) - (0.0 if name.startswith("tri") else 1.0)
+        out[f"{name}_pts"] = pts
+        pq = el._computeFunctionEvaluationQuantities(pts, q, X, dvs, ["Coord", "State", "StateGrad", "Jac", "JacDet", "StateGradSens", "DVs"])
+        for key in ("Coord", "State", "StateGrad", "Jac", "JacDet", "StateGradSens"):
+            out[f"{name}_{key}"] = pq[key]
+        out[f"{name}_DVs"] = pq["DVs"]["Thickness"]
+        for red in (None, "mean", "integrate", "max", "ksmax"):
+            out[f"{name}_custom_{red}"] = el.computeFunction(X, q, dvs, custom_function, red)
+        cm = rh.make_constitutive(fp, 0, MAT["E"], MAT["nu"], MAT["rho"], MAT["t"], True)
+        cmnl = rh.make_constitutive(fp, 1, MAT["E"], MAT["nu"], MAT["rho"], MAT["t"], False)
+        for order in EXTRA_RULES[name]:
+            key = f"{name}_int{order}"
+            out[key + "_Ke"] = el.computeResidualJacobians(q, X, dvs, cm, intOrder=order)
+            out[key + "_Re"] = el.computeResiduals(q, X, dvs, cm, intOrder=order)
+            out[key + "_Ke_nl"] = el.computeResidualJacobians(q, X, dvs, cmnl, intOrder=order)
+            out[key + "_vm"] = el.computeFunction(X, q, dvs, cm.getFunction("Von-Mises-Stress"), None, intOrder=order)
+            out[key + "_massint"] = el.computeFunction(X, q, dvs, cm.getFunction("Mass"), "integrate", intOrder=order)
+            out[key + "_custom_integrate"] = el.computeFunction(X, q, dvs, custom_function, "integrate", intOrder=order)
+    np.savez_compressed(os.path.join(OUT, "points.npz"), **out)
 
 
 def mixed_grid(nx, ny):
@@ -209,10 +250,14 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["ks"]:  # later addition: leaves the other fixtures untouched
         gen_ks(fp)
         sys.exit(0)
+    if sys.argv[1:] == ["points"]:  # round 2 addition
+        gen_points(fp)
+        sys.exit(0)
     gen_tables(fp)
     gen_elements(fp)
     gen_meshes(fp)
     gen_lbracket(fp)
     gen_ks(fp)
+    gen_points(fp)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

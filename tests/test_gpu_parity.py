@@ -79,6 +79,80 @@ def test_element_level_against_reference(family, model, linear):
     assert relerr(el.computeFunction(X, q, dvs, cm.getFunction("Mass"), "integrate"), g[key + "_massint"]) < TOL
 
 
+EXTRA_RULES = {"quad1": (1, 3, 4), "quad2": (2, 4), "quad3": (3,), "tri1": (2, 3), "tri2": (1, 3), "tri3": (1, 3)}
+
+
+def custom_function(states, stateGradients, coords, dvs):
+    """the caller-supplied point function of oracle/gen_golden.py: gen_points"""
+    return states[:, 0] * coords[:, 1] + stateGradients[:, 0, 1] * dvs["Thickness"] - 3.0 * stateGradients[:, 1, 0] * coords[:, 0]
+
+
+@pytest.mark.parametrize("family", sorted(FAMILY_ELEMENT))
+def test_point_quantities_against_reference(family):
+    """Element._computeFunctionEvaluationQuantities (Element.py:275-368: _interpolationProduct, Jacobians, state gradients
+    and their sensitivities) at arbitrary parametric points through femb_point_quantities, and Element.computeFunction
+    with a function that is not one of the models' own (evaluated on the host from the device's point quantities)"""
+    g, pg = golden("elements.npz"), golden("points.npz")
+    el = ELEMENT_FOR[FAMILY_ELEMENT[family]]()
+    X, q, t = g[family + "_X"], g[family + "_q"], g[family + "_t"]
+    names = ["Coord", "State", "StateGrad", "Jac", "JacDet", "StateGradSens", "DVs", "NPrimeParam"]
+    pq = el._computeFunctionEvaluationQuantities(pg[family + "_pts"], q, X, {"Thickness": t}, names)
+    for key in names[:6]:
+        want = pg[f"{family}_{key}"]
+        assert pq[key].shape == want.shape and relerr(pq[key], want) < TOL, key
+    np.testing.assert_array_equal(pq["DVs"]["Thickness"], pg[family + "_DVs"])
+    assert pq["NPrimeParam"].shape == (5, 2, el.numNodes)
+    for red in (None, "mean", "integrate", "max", "ksmax"):
+        v = el.computeFunction(X, q, {"Thickness": t}, custom_function, red)
+        want = pg[f"{family}_custom_{red}"]
+        assert v.shape == want.shape and relerr(v, want) < TOL, red
+
+
+@pytest.mark.parametrize("family", sorted(FAMILY_ELEMENT))
+def test_non_default_quadrature_against_reference(family):
+    """`intOrder=` of the element-level methods (Element.py:163,370,426): n x n Gauss rules for the quads, the 1- / 3- /
+    4-point rules for the triangles, on the scatter / element-block / function kernels"""
+    g, pg = golden("elements.npz"), golden("points.npz")
+    el = ELEMENT_FOR[FAMILY_ELEMENT[family]]()
+    X, q, t = g[family + "_X"], g[family + "_q"], g[family + "_t"]
+    dvs = {"Thickness": t}
+    cm, cmnl = make_cm(0, True), make_cm(1, False)
+    for order in EXTRA_RULES[family]:
+        key = f"{family}_int{order}"
+        assert relerr(el.computeResidualJacobians(q, X, dvs, cm, intOrder=order), pg[key + "_Ke"]) < TOL, key
+        assert relerr(el.computeResiduals(q, X, dvs, cm, intOrder=order), pg[key + "_Re"]) < TOL, key
+        assert relerr(el.computeResidualJacobians(q, X, dvs, cmnl, intOrder=order), pg[key + "_Ke_nl"]) < TOL, key
+        vm = el.computeFunction(X, q, dvs, cm.getFunction("Von-Mises-Stress"), None, intOrder=order)
+        assert vm.shape == pg[key + "_vm"].shape and relerr(vm, pg[key + "_vm"]) < TOL, key
+        assert relerr(el.computeFunction(X, q, dvs, cm.getFunction("Mass"), "integrate", intOrder=order), pg[key + "_massint"]) < TOL, key
+        assert relerr(el.computeFunction(X, q, dvs, custom_function, "integrate", intOrder=order), pg[key + "_custom_integrate"]) < TOL, key
+
+
+def test_model_on_a_non_default_rule_assembles_on_the_scatter_kernels():
+    """a plan whose block carries a non-default rule (Q4 with the 3 x 3 rule) leaves the row-owner path and still matches
+    the oracle evaluated with the same tables"""
+    coords, conn = meshes.quad4_grid(13, 9)
+    coords = coords + 0.01 * np.random.default_rng(4).random(coords.shape)
+    el = ELEMENT_FOR["quad"]()
+    N_, dN, w = el.tables(3)
+    N = coords.shape[0]
+    rng = np.random.default_rng(8)
+    states, thick, loads = 1e-3 * rng.random((N, 2)), rng.random(conn["quad"].shape[0]) + 0.5, rng.random(2 * N)
+    bcDOF, bcVal = np.array([0, 1, 7]), np.array([0.0, 1e-4, 0.0])
+    plan = AssemblyPlan(N)
+    plan.addBlock(N_, dN, w, conn["quad"])
+    plan.finalize()
+    assert plan.info("rows_path") == 0 and plan.info("fan_path") == 0
+    K, R = plan.assemble(coords, states, thick, make_cm(0).material(), bcDOF, bcVal, True, loads)
+    blocks = [fo.Block(N_, dN, w, conn["quad"])]
+    Ko = fo.assemble_matrix(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], bcDOF, dropZeros=False)
+    Ko.sort_indices()
+    Ro = fo.assemble_residual(blocks, coords, states, thick, 0, MAT["E"], MAT["nu"], loads, bcDOF, bcVal)
+    np.testing.assert_array_equal(plan.pattern()[1], Ko.indices)
+    assert relerr(K, Ko.data) < TOL and relerr(R, Ro) < TOL
+    plan.close()
+
+
 @pytest.mark.parametrize("family", sorted(FAMILY_ELEMENT))
 @pytest.mark.parametrize("model", [0, 1])
 def test_ks_element_reduction_against_reference(family, model):
@@ -782,7 +856,7 @@ def test_bad_inputs_raise():
     with pytest.raises(FembError, match="outside"):
         plan.addBlock(N, dN, w, np.array([[0, 1, 2, 7]]))
     with pytest.raises(FembError, match="unsupported element family"):
-        plan.addBlock(N[:1], dN[:1], w[:1], np.array([[0, 1, 2, 3]]))
+        plan.addBlock(N[:2], dN[:2], w[:2], np.array([[0, 1, 2, 3]]))  # 4 nodes with a 2-point rule: no such family
     with pytest.raises(FembError, match="not finalized"):
         plan.pattern()
     plan.addBlock(N, dN, w, np.array([[0, 1, 2, 3]]))

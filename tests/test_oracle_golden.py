@@ -177,6 +177,37 @@ def test_element_level_against_reference(family, model, linear):
     assert relerr(mi, g[key + "_massint"]) < TOL
 
 
+EXTRA_RULES = {"quad1": (1, 3, 4), "quad2": (2, 4), "quad3": (3,), "tri1": (2, 3), "tri2": (1, 3), "tri3": (1, 3)}
+
+
+@pytest.mark.parametrize("family", sorted(FAMILY_ELEMENT))
+def test_point_quantities_and_non_default_quadrature_against_reference(family):
+    """oracle vs the reference's _computeFunctionEvaluationQuantities at arbitrary points (Element.py:275-368) and its
+    element-level methods with `intOrder=` (points.npz, oracle/gen_golden.py: gen_points)"""
+    g, pg = golden("elements.npz"), golden("points.npz")
+    el = ELEMENT_FOR[FAMILY_ELEMENT[family]]()
+    X, q, t = g[family + "_X"], g[family + "_q"], g[family + "_t"]
+    pts = pg[family + "_pts"]
+    N, dN = el.computeShapeFunctions(pts), el.computeShapeFunctionGradients(pts)
+    detJ, G, up = fo.point_quantities(dN, X, q)
+    P = pts.shape[0]
+    assert relerr(detJ.reshape(-1), pg[family + "_JacDet"]) < TOL
+    assert relerr(G.reshape(-1, 2, el.numNodes), pg[family + "_StateGradSens"]) < TOL
+    assert relerr(up.reshape(-1, 2, 2), pg[family + "_StateGrad"]) < TOL
+    assert relerr(np.einsum("pn,end->epd", N, X).reshape(-1, 2), pg[family + "_Coord"]) < TOL
+    assert relerr(np.einsum("pn,ens->eps", N, q).reshape(-1, 2), pg[family + "_State"]) < TOL
+    assert relerr(np.einsum("pdn,enk->epdk", dN, X).reshape(-1, 2, 2), pg[family + "_Jac"]) < TOL
+    assert pg[family + "_DVs"].shape == (X.shape[0] * P,)
+    for order in EXTRA_RULES[family]:
+        _, dNo, w = el.tables(order)
+        key = f"{family}_int{order}"
+        assert relerr(fo.element_jacobians(dNo, w, X, q, t, 0, MAT["E"], MAT["nu"]), pg[key + "_Ke"]) < TOL, key
+        assert relerr(fo.element_residuals(dNo, w, X, q, t, 0, MAT["E"], MAT["nu"]), pg[key + "_Re"]) < TOL, key
+        assert relerr(fo.element_jacobians(dNo, w, X, q, t, 1, MAT["E"], MAT["nu"], nonlinear=True), pg[key + "_Ke_nl"]) < TOL, key
+        assert relerr(fo.element_function(dNo, w, X, q, fo.VON_MISES, None, 0, MAT["E"], MAT["nu"], MAT["rho"]), pg[key + "_vm"]) < TOL, key
+        assert relerr(fo.element_function(dNo, w, X, q, fo.MASS, "integrate", 0, MAT["E"], MAT["nu"], MAT["rho"]), pg[key + "_massint"]) < TOL, key
+
+
 @pytest.mark.parametrize("family", sorted(FAMILY_ELEMENT))
 @pytest.mark.parametrize("model", [0, 1])
 def test_ks_element_reduction_against_reference(family, model):
