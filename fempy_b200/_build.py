@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libfemb200.so")
-SOURCES = ["common.cu", "plan.cu", "assemble.cu", "functions.cu", "solve.cu"]
+SOURCES = ["common.cu", "plan.cu", "assemble.cu", "functions.cu", "solve.cu", "generic.cu"]
 HEADERS = ["elem_math.cuh", "femb_internal.h", "assemble_rows.cuh", "assemble_fan.cuh", os.path.join("..", "..", "include", "femb200.h")]
 
 NVCC_FLAGS = [

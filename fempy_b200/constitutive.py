@@ -8,8 +8,9 @@ names raise ValueError exactly as the reference does (IsoPlaneStress.py:206-209)
 """
 import numpy as np
 
-PLANE_STRESS, PLANE_STRAIN = 0, 1
-FUNC_MASS, FUNC_VON_MISES = 0, 1
+PLANE_STRESS, PLANE_STRAIN, ISO_3D, ISO_1D = 0, 1, 2, 3
+FUNC_MASS, FUNC_VON_MISES, FUNC_STRESS, FUNC_STRAIN = 0, 1, 2, 3
+FUNCTION_IDS = {"mass": FUNC_MASS, "von-mises-stress": FUNC_VON_MISES, "stress": FUNC_STRESS, "strain": FUNC_STRAIN}
 
 
 class PointFunction:
@@ -45,8 +46,7 @@ class ConstitutiveModel:
             raise ValueError(
                 f"{name} is not a valid function name for this constitutive model, valid choices are {self.functionNames}"
             )
-        funcId = {"mass": FUNC_MASS, "von-mises-stress": FUNC_VON_MISES}[name.lower()]
-        return PointFunction(name, funcId, self)
+        return PointFunction(name, FUNCTION_IDS[name.lower()], self)
 
 
 class _IsoPlane(ConstitutiveModel):
@@ -92,3 +92,46 @@ class IsoPlaneStrain(_IsoPlane):
             / ((1.0 + nu) * (1.0 - 2.0 * nu))
             * np.array([[1.0 - nu, nu, 0.0], [nu, 1.0 - nu, 0.0], [0.0, 0.0, (1.0 - 2.0 * nu) / 2.0]])
         )
+
+
+class Iso3D(ConstitutiveModel):
+    """3-D isotropic elasticity, no design variable (reference Iso3D.py:28-217)."""
+
+    modelId = ISO_3D
+
+    def __init__(self, E, nu, rho, linear=True):
+        self.E, self.nu, self.rho = E, nu, rho
+        super().__init__(3, ["X-Displacement", "Y-Displacement", "Z-Displacement"],
+                         ["e_xx", "e_yy", "e_zz", "gamma_xy", "gamma_xz", "gamma_yz"],
+                         ["sigma_xx", "sigma_yy", "sigma_zz", "tau_xy", "tau_xz", "tau_yz"], {}, ["Mass", "Von-Mises-Stress"], linear)
+
+    def material(self):
+        from ._lib import Material
+
+        return Material(float(self.E), float(self.nu), float(self.rho), ISO_3D, int(not self.isLinear))
+
+    def stressStrainMatrix(self):
+        E, nu = self.E, self.nu
+        D = np.zeros((6, 6))
+        D[:3, :3] = nu
+        D[[0, 1, 2], [0, 1, 2]] = 1.0 - nu
+        D[[3, 4, 5], [3, 4, 5]] = (1.0 - 2.0 * nu) / 2.0
+        return E / ((1.0 + nu) * (1.0 - 2.0 * nu)) * D
+
+
+class Iso1D(ConstitutiveModel):
+    """Axial bar; design variable "Area" (reference Iso1D.py:28-225)."""
+
+    modelId = ISO_1D
+
+    def __init__(self, E, rho, A, linear=True):
+        self.E, self.rho, self.nu = E, rho, 0.0
+        super().__init__(1, ["X-Displacement"], ["e_xx"], ["sigma_xx"], {"Area": {"defaultValue": A}}, ["Mass", "Stress", "Strain"], linear)
+
+    def material(self):
+        from ._lib import Material
+
+        return Material(float(self.E), 0.0, float(self.rho), ISO_1D, int(not self.isLinear))
+
+    def stressStrainMatrix(self):
+        return np.array([[self.E]])

@@ -268,12 +268,14 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
                                  double* d_K, double* d_R) {
     TRY(need_final(p, "femb_assemble_dev"));
     if (!mat) return fail("femb_assemble_dev: material is NULL");
-    if (mat->model != FEMB_PLANE_STRESS && mat->model != FEMB_PLANE_STRAIN)
-        return fail("femb_assemble_dev: unsupported constitutive model id %d", mat->model);
     const bool wk = (want & FEMB_WANT_K) != 0, wr = (want & FEMB_WANT_R) != 0;
     if (!wk && !wr) return fail("femb_assemble_dev: nothing requested");
     if ((wk && !d_K) || (wr && !d_R) || !d_coords || !d_states || !d_thick) return fail("femb_assemble_dev: NULL buffer");
     TRY(use_device(p));
+    if (p->numDim != 2)  // 1-D / 3-D families: generic.cu
+        return generic_assemble_dev(p, d_coords, d_states, d_thick, mat, applyBCs && p->nBC > 0, d_loads, wk, wr, d_K, d_R);
+    if (mat->model != FEMB_PLANE_STRESS && mat->model != FEMB_PLANE_STRAIN)
+        return fail("femb_assemble_dev: unsupported constitutive model id %d for a 2-D plan", mat->model);
     cudaStream_t st = p->stream;
     const DMat D = make_dmat(*mat);
     const int64_t numDOF = femb_plan_num_dof(p), nnz = femb_plan_nnz(p);

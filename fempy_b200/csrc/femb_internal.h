@@ -51,6 +51,7 @@ struct BlockData {
     bool closedForm = false;  // 4 nodes: standard bilinear tables + 2x2 Gauss rule -> closed-form row-owner kernel (plan.cu: standard_q4)
     bool cyclic = true;       // 3/4 nodes: tables invariant under cyclic renumbering -> corner records rotated to the owner
     int* d_conn = nullptr;  // node-major int32: conn[a * E + e]
+    double *d_tabN = nullptr, *d_tabdN = nullptr, *d_tabw = nullptr;  // 1-D / 3-D plans: the block's tables on the device (generic.cu)
     int* d_slot = nullptr;  // [(a*nn + b) * E + e] -> position of (node_a, node_b) in the node-level CSR
     int4* d_connE = nullptr;   // element-major connectivity, ceil(nn/4) words per element (row-owner kernel)
     void* d_corners = nullptr; // corner records of this block, indexed by the global corner number (plan.cu: k_corners)
@@ -173,8 +174,8 @@ static inline int use_device(const femb_plan* p) {
 // device.  An explicit pointer overwrites the scratch, so the resident promise ends there.
 static inline int stage_geometry(femb_plan* p, const double* coords, const double* thickness, bool needThickness, const char* who) {
     if (coords) {
-        if (!p->s_coords) CUDA_TRY(cudaMalloc((void**)&p->s_coords, std::max<size_t>((size_t)p->numNodes * 2, 1) * sizeof(double)));
-        CUDA_TRY(cudaMemcpyAsync(p->s_coords, coords, (size_t)p->numNodes * 2 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        if (!p->s_coords) CUDA_TRY(cudaMalloc((void**)&p->s_coords, std::max<size_t>((size_t)p->numNodes * p->numDim, 1) * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(p->s_coords, coords, (size_t)p->numNodes * p->numDim * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         p->coordsResident = false;
     } else if (!p->coordsResident) {
         return fail("%s: coords is NULL and no resident copy exists (femb_plan_set_geometry)", who);
@@ -201,6 +202,13 @@ int exclusive_scan(const int* d_in, int* d_out, int64_t n, cudaStream_t st, int6
 
 bool rows_path_available(const femb_plan* p);
 bool fan_path_available(const femb_plan* p);  // assemble.cu: the write-once fan kernel will run (small-strain model)
+// generic.cu: the 1-D / 3-D families (run-time node and point counts, FP64-atomic scatter)
+int generic_assemble_dev(femb_plan* p, const double* d_coords, const double* d_states, const double* d_scale, const femb_material* mat,
+                         bool bcs, const double* d_loads, bool wk, bool wr, double* d_K, double* d_R);
+int generic_function_dev(femb_plan* p, const double* d_coords, const double* d_states, const femb_material* mat, int func, int reduction,
+                         double* d_out);
+int generic_element_blocks_dev(femb_plan* p, const double* d_coords, const double* d_states, const double* d_scale, const femb_material* mat,
+                               double* d_Ke, double* d_Re);
 int ensure_slot_maps(femb_plan* p);  // plan.cu: builds the scatter kernels' slot maps on first use
 
 // ---------------------------------------------------------------------------------------------

@@ -124,10 +124,11 @@ extern "C" int femb_function_dev(femb_plan* p, const double* d_coords, const dou
                                  int32_t func, int32_t reduction, double* d_out) {
     TRY(need_final(p, "femb_function_dev"));
     if (!mat || !d_coords || !d_states || !d_out) return fail("femb_function_dev: NULL argument");
-    if (func != FEMB_FUNC_MASS && func != FEMB_FUNC_VON_MISES) return fail("femb_function_dev: unknown function id %d", func);
     if (reduction < FEMB_REDUCE_NONE || reduction > FEMB_REDUCE_KSMAX)
         return fail("femb_function_dev: unknown reduction id %d", reduction);
     TRY(use_device(p));
+    if (p->numDim != 2) return generic_function_dev(p, d_coords, d_states, mat, func, reduction, d_out);
+    if (func != FEMB_FUNC_MASS && func != FEMB_FUNC_VON_MISES) return fail("femb_function_dev: unknown function id %d", func);
     const DMat D = make_dmat(*mat);
     int64_t launches = 0;
     for (auto& b : p->blocks) {
@@ -231,6 +232,7 @@ extern "C" int femb_point_quantities(femb_plan* p, const double* coords, const d
     TRY(need_final(p, "femb_point_quantities"));
     if (!states) return fail("femb_point_quantities: states is NULL");
     if (!coord && !state && !stateGrad && !jac && !jacDet && !stateGradSens) return fail("femb_point_quantities: nothing requested");
+    if (p->numDim != 2) return fail("femb_point_quantities: 2-D plans only");
     TRY(use_device(p));
     cudaStream_t st = p->stream;
     TRY(stage_geometry(p, coords, nullptr, false, "femb_point_quantities"));
@@ -304,12 +306,19 @@ extern "C" int femb_element_blocks(femb_plan* p, const double* coords, const dou
     if (!coords || !states || !thickness || !mat) return fail("femb_element_blocks: NULL argument");
     TRY(use_device(p));
     const int64_t numDOF = femb_plan_num_dof(p);
-    TRY(stage(&p->s_coords, coords, (size_t)p->numNodes * 2, p->stream));
+    TRY(stage(&p->s_coords, coords, (size_t)p->numNodes * p->numDim, p->stream));
     TRY(stage(&p->s_states, states, (size_t)numDOF, p->stream));
     TRY(stage(&p->s_thick, thickness, (size_t)p->numElems, p->stream));
     Scratch<double> d_Ke, d_Re;
     if (Ke) CUDA_TRY(d_Ke.alloc(p->keTotal));
     if (Re) CUDA_TRY(d_Re.alloc(p->reTotal));
+    if (p->numDim != 2) {
+        TRY(generic_element_blocks_dev(p, p->s_coords, p->s_states, p->s_thick, mat, d_Ke.p, d_Re.p));
+        if (Ke) CUDA_TRY(cudaMemcpyAsync(Ke, d_Ke, p->keTotal * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (Re) CUDA_TRY(cudaMemcpyAsync(Re, d_Re, p->reTotal * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        return 0;
+    }
     const DMat D = make_dmat(*mat);
     int64_t launches = 0;
     for (auto& b : p->blocks) {

@@ -274,10 +274,10 @@ __global__ void k_bc_diag(long long N, const int* __restrict__ nrowptr, const in
     info[i] = ((v >> 2) << 9) | (diagK << 2) | (v & 3);
 }
 
-__global__ void k_check_bcs(long long nBC, const int* __restrict__ bcDof, const int* __restrict__ nrowptr, int* flag) {
+__global__ void k_check_bcs(long long nBC, int s, const int* __restrict__ bcDof, const int* __restrict__ nrowptr, int* flag) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nBC) return;
-    const int i = bcDof[t] >> 1;
+    const int i = bcDof[t] / s;
     if (nrowptr[i + 1] == nrowptr[i]) atomicExch(flag, 2);
 }
 
@@ -546,9 +546,9 @@ static bool standard_t3(int nq, const double* dN, const double* w) {
 extern "C" int femb_plan_create(int64_t numNodes, int32_t numDim, int32_t numStates, int32_t device, femb_plan** out) {
     if (!out) return fail("femb_plan_create: out is NULL");
     *out = nullptr;
-    if (numDim != 2 || numStates != 2)
-        return fail("femb_plan_create: only 2-D models with 2 states per node are supported (got numDim=%d, numStates=%d)",
-                    numDim, numStates);
+    if (numDim < 1 || numDim > 3 || numStates != numDim)
+        return fail("femb_plan_create: supported are 1-D, 2-D and 3-D models with one displacement state per dimension (got numDim=%d, "
+                    "numStates=%d)", numDim, numStates);
     if (numNodes <= 0 || numNodes >= (1ll << 30)) return fail("femb_plan_create: numNodes out of range");
     int ndev = femb_device_count();
     if (ndev == 0) return fail("femb_plan_create: no CUDA device available (this library has no CPU fallback)");
@@ -577,7 +577,8 @@ extern "C" int femb_plan_add_block(femb_plan* p, int32_t nn, int32_t nq, const d
     if (!p) return fail("femb_plan_add_block: plan is NULL");
     if (p->finalized) return fail("femb_plan_add_block: plan already finalized");
     if ((int)p->blocks.size() >= MAX_BLOCKS) return fail("femb_plan_add_block: at most %d element types", MAX_BLOCKS);
-    if (!family_supported(nn, nq) && !(p->pointsOnly && nn >= 1 && nn <= 64 && nq >= 1))
+    const bool generic = p->numDim != 2;  // 1-D / 3-D: any Lagrange family of up to 27 nodes (generic.cu)
+    if (generic ? !(nn >= 2 && nn <= 27 && nq >= 1 && nq <= 125) : (!family_supported(nn, nq) && !(p->pointsOnly && nn >= 1 && nn <= 64 && nq >= 1)))
         return fail("femb_plan_add_block: unsupported element family (%d nodes, %d quadrature points)", nn, nq);
     if (numElems <= 0 || !conn || !N || !dNdxi || !w) return fail("femb_plan_add_block: bad arguments");
     if (numElems * (int64_t)nn * nn >= (1ll << 31)) return fail("femb_plan_add_block: block too large for int32 slot map");
@@ -591,10 +592,19 @@ extern "C" int femb_plan_add_block(femb_plan* p, int32_t nn, int32_t nq, const d
     b.keOffset = p->keTotal;
     b.reOffset = p->reTotal;
     b.N.assign(N, N + (size_t)nq * nn);
-    b.dN.assign(dNdxi, dNdxi + (size_t)nq * 2 * nn);
+    b.dN.assign(dNdxi, dNdxi + (size_t)nq * p->numDim * nn);
     b.w.assign(w, w + nq);
-    if (nn <= 4) b.cyclic = tables_cyclic_invariant(nn, nq, dNdxi, w);
-    b.closedForm = b.cyclic && ((nn == 4 && standard_q4(nq, dNdxi, w)) || (nn == 3 && standard_t3(nq, dNdxi, w)));
+    if (!generic) {
+        if (nn <= 4) b.cyclic = tables_cyclic_invariant(nn, nq, dNdxi, w);
+        b.closedForm = b.cyclic && ((nn == 4 && standard_q4(nq, dNdxi, w)) || (nn == 3 && standard_t3(nq, dNdxi, w)));
+    } else {
+        CUDA_TRY(cudaMalloc(&b.d_tabN, b.N.size() * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&b.d_tabdN, b.dN.size() * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&b.d_tabw, b.w.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(b.d_tabN, b.N.data(), b.N.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        CUDA_TRY(cudaMemcpyAsync(b.d_tabdN, b.dN.data(), b.dN.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        CUDA_TRY(cudaMemcpyAsync(b.d_tabw, b.w.data(), b.w.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
     Scratch<long long> d_conn64;
     const size_t cnt = (size_t)numElems * nn;
     CUDA_TRY(d_conn64.alloc(cnt));
@@ -612,8 +622,8 @@ extern "C" int femb_plan_add_block(femb_plan* p, int32_t nn, int32_t nq, const d
     }
     p->numElems += numElems;
     p->numPoints += numElems * nq;
-    p->keTotal += numElems * (int64_t)(2 * nn) * (2 * nn);
-    p->reTotal += numElems * (int64_t)nn * 2;
+    p->keTotal += numElems * (int64_t)(p->numStates * nn) * (p->numStates * nn);
+    p->reTotal += numElems * (int64_t)nn * p->numStates;
     p->blocks.push_back(std::move(b));
     return 0;
 }
@@ -684,7 +694,7 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
         k_max_int<<<grid_for(N, 256), 256, 0, st>>>(d_deg, N, p->d_flag);
         CUDA_TRY(cudaMemcpyAsync(&p->maxDeg, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         launches++;
-        bool rowsOk = true;
+        bool rowsOk = p->numDim == 2;  // the row-owner / fan kernels are 2-D
         for (auto& b : p->blocks) rowsOk = rowsOk && b.nn <= 12 && b.numElems < (1ll << 28) && default_rule(b.nn, b.nq);
         if (rowsOk) {
             // row-owner kernel: per block element-major connectivity, corner records (indexed by the global corner
@@ -831,6 +841,9 @@ extern "C" void femb_plan_destroy(femb_plan* p) {
         dfree(b.d_fanElem);
         dfree(b.d_fanHdr);
         dfree(b.d_fanRest);
+        dfree(b.d_tabN);
+        dfree(b.d_tabdN);
+        dfree(b.d_tabw);
     }
     dfree(p->d_bcMask);
     dfree(p->d_bcInfo);
@@ -1024,10 +1037,12 @@ extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const doubl
         counts.swap(c2);
     }
     std::vector<unsigned char> mask((size_t)p->numNodes, 0);
-    for (size_t i = 0; i < n; ++i) mask[dofs[i] >> 1] |= (unsigned char)(1u << (dofs[i] & 1));
-    TRY(dalloc(&p->d_bcMask, (size_t)p->numNodes));
-    CUDA_TRY(cudaMemcpyAsync(p->d_bcMask, mask.data(), mask.size(), cudaMemcpyHostToDevice, p->stream));
-    {  // row-owner kernel: per node (index of the constrained node + 1) << 9 | diagK << 2 | DOF bits (0 = unconstrained) and, per
+    if (p->numStates == 2) {
+        for (size_t i = 0; i < n; ++i) mask[dofs[i] >> 1] |= (unsigned char)(1u << (dofs[i] & 1));
+        TRY(dalloc(&p->d_bcMask, (size_t)p->numNodes));
+        CUDA_TRY(cudaMemcpyAsync(p->d_bcMask, mask.data(), mask.size(), cudaMemcpyHostToDevice, p->stream));
+    }
+    if (p->numStates == 2) {  // row-owner kernel: per node (index of the constrained node + 1) << 9 | diagK << 2 | DOF bits (0 = unconstrained) and, per
        // constrained node, the diagonal values (occurrence counts) and the prescribed values of its two DOFs
         std::vector<int> info((size_t)p->numNodes, 0);
         std::vector<double> cnt2, val2;
@@ -1064,7 +1079,7 @@ extern "C" int femb_plan_set_bcs(femb_plan* p, const int64_t* bcDof, const doubl
     CUDA_TRY(cudaMemcpyAsync(p->d_bcVal, vals.data(), n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaMemcpyAsync(p->d_bcCount, counts.data(), n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
-    k_check_bcs<<<grid_for((int64_t)n, 256), 256, 0, p->stream>>>((long long)n, p->d_bcDof, p->d_nrowptr, p->d_flag);
+    k_check_bcs<<<grid_for((int64_t)n, 256), 256, 0, p->stream>>>((long long)n, p->numStates, p->d_bcDof, p->d_nrowptr, p->d_flag);
     int flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));

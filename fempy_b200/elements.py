@@ -1,5 +1,5 @@
-"""Host-side mirror of the reference's 2-D element families
-(reference FEMpy/Elements/Element.py:32-486, QuadElement2D.py:42-186, TriElement2D.py:69-169).
+"""Host-side mirror of the reference's element families
+(reference FEMpy/Elements/Element.py:32-486, QuadElement2D.py:42-186, TriElement2D.py:69-169, HexElement3D.py, LineElement1D.py).
 
 The table generators (shape functions, gradients, quadrature) are host code; the batched per-element
 methods -- `computeResidualJacobians`, `computeResiduals`, `computeFunction` -- keep the reference's
@@ -60,9 +60,12 @@ class Element:
         plan.finalize()
         return plan, nodeCoords.reshape(-1, self.numDim)
 
-    @staticmethod
-    def _thickness(designVars, numElements):
-        return np.ascontiguousarray(np.broadcast_to(np.asarray(designVars["Thickness"], dtype=np.float64), (numElements,)))
+    def _thickness(self, designVars, numElements):
+        """the per-element volume scaling (ConstitutiveModel.computeVolumeScaling): thickness in 2-D, cross-sectional area
+        in 1-D (Iso1D.py), 1 in 3-D (Iso3D.py has no design variable)"""
+        name = {1: "Area", 2: "Thickness"}.get(self.numDim)
+        vals = 1.0 if name is None else designVars[name]
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(vals, dtype=np.float64), (numElements,)))
 
     def computeResidualJacobians(self, nodeStates, nodeCoords, designVars, constitutiveModel, intOrder=None):
         """(E, n*s, n*s) element stiffness matrices (Element.py:426-486)."""
@@ -218,6 +221,74 @@ class TriElement2D(Element):
         return np.array([[0, 0], [1, 0], [0, 1], [t, 0], [2 * t, 0], [2 * t, t], [t, 2 * t], [0, 2 * t], [0, t], [t, t]], dtype=float)
 
 
+class HexElement3D(Element):
+    """Lagrange hexahedron of order 1-2 in meshio node order (HexElement3D.py:30-188)."""
+
+    def __init__(self, order=1, numStates=None, quadratureOrder=None):
+        if order not in [1, 2]:
+            raise ValueError("Hex elements only support orders 1 and 2")
+        self.order = order
+        if quadratureOrder is None:
+            quadratureOrder = int(np.ceil((2 * order + 1) / 2))
+        super().__init__((order + 1) ** 3, numDim=3, quadratureOrder=quadratureOrder, numStates=numStates)
+        self.name = f"Order{self.order}-LagrangeHex"
+        self.shapeFuncToNodeOrder = T._hex_node_order(order)
+
+    def computeShapeFunctions(self, paramCoords):
+        N = T.lagrange3d(paramCoords[:, 0], paramCoords[:, 1], paramCoords[:, 2], self.order + 1)
+        return np.ascontiguousarray(N[:, self.shapeFuncToNodeOrder])
+
+    def computeShapeFunctionGradients(self, paramCoords):
+        dN = T.lagrange3d_deriv(paramCoords[:, 0], paramCoords[:, 1], paramCoords[:, 2], self.order + 1)
+        return np.ascontiguousarray(dN[:, :, self.shapeFuncToNodeOrder])
+
+    def getIntegrationPointWeights(self, order=None):
+        return T.gauss_weights(self.numDim, self.quadratureOrder if order is None else order)
+
+    def getIntegrationPointCoords(self, order=None):
+        return T.gauss_points(self.numDim, self.quadratureOrder if order is None else order)
+
+    def getReferenceElementCoordinates(self):
+        n = self.order + 1
+        p = np.linspace(-1, 1, n)
+        x, y, z = np.tile(p, n * n), np.tile(np.repeat(p, n), n), np.repeat(p, n * n)
+        o = self.shapeFuncToNodeOrder
+        return np.vstack((x[o], y[o], z[o])).T
+
+
+class LineElement1D(Element):
+    """Lagrange line element of order 1-3 (LineElement1D.py:30-180)."""
+
+    def __init__(self, order=1, numStates=None, quadratureOrder=None):
+        if order not in [1, 2, 3]:
+            raise ValueError("Line elements only support orders 1, 2 and 3")
+        self.order = order
+        if quadratureOrder is None:
+            quadratureOrder = int(np.ceil((order + 1) / 2))
+        super().__init__(order + 1, numDim=1, quadratureOrder=quadratureOrder, numStates=numStates)
+        self.name = f"Order{self.order}-LagrangeLine"
+        # LineElement1D._getNodeReordering (LineElement1D.py:158-180): [0, 1], [0, 2, 1], [0, 2, 3, 1] -- for order 3 this is
+        # not meshio's "ends first" order; connectivity must follow the element's own order (meshes.line_grid does)
+        self.shapeFuncToNodeOrder = np.array([0] + list(range(2, order + 1)) + [1]) if order > 1 else np.array([0, 1])
+
+    def computeShapeFunctions(self, paramCoords):
+        N = T.lagrange1d(np.asarray(paramCoords).reshape(-1), self.order + 1)
+        return np.ascontiguousarray(N[:, self.shapeFuncToNodeOrder])
+
+    def computeShapeFunctionGradients(self, paramCoords):
+        dN = T.lagrange1d_deriv(np.asarray(paramCoords).reshape(-1), self.order + 1)
+        return np.ascontiguousarray(dN[:, None, self.shapeFuncToNodeOrder])
+
+    def getIntegrationPointWeights(self, order=None):
+        return T.gauss_weights(self.numDim, self.quadratureOrder if order is None else order)
+
+    def getIntegrationPointCoords(self, order=None):
+        return np.asarray(T.gauss_points(self.numDim, self.quadratureOrder if order is None else order)).reshape(-1, 1)
+
+    def getReferenceElementCoordinates(self):
+        return np.linspace(-1, 1, self.numNodes).reshape(-1, 1)[self.shapeFuncToNodeOrder]
+
+
 def elementFromMeshioName(meshioName, numStates):
     """meshio cell-type name -> element object, or None if unsupported (Model.py:429-488)."""
     name = meshioName.lower()
@@ -236,4 +307,9 @@ def elementFromMeshioName(meshioName, numStates):
         return TriElement2D(order=2, numStates=numStates)
     if name == "triangle10":
         return TriElement2D(order=3, numStates=numStates)
+    if name == "hexahedron":  # 27-node hexahedra: element level only, as in the reference (Model.py:470-476 fails for them)
+        return HexElement3D(order=1, numStates=numStates)
+    if name[:4] == "line":
+        order = 1 if name == "line" else int(name[4:]) - 1
+        return LineElement1D(order=order, numStates=numStates) if order in (1, 2, 3) else None
     return None

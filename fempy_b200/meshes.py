@@ -72,3 +72,30 @@ def edge_nodes(coords, x=None, y=None):
 
 
 GENERATORS = {"quad": quad4_grid, "quad9": quad9_grid, "triangle": tri3_grid, "triangle6": tri6_grid}
+
+
+def hex8_grid(nx, ny, nz):
+    """nodeCoords (N,3) on the unit cube and {"hexahedron": (nx*ny*nz, 8) int64}: nodes numbered x fastest, then y, then z;
+    meshio hexahedron order (bottom face counter-clockwise seen from above, then the top face)."""
+    x, y, z = np.linspace(0.0, 1.0, nx + 1), np.linspace(0.0, 1.0, ny + 1), np.linspace(0.0, 1.0, nz + 1)
+    coords = np.stack((np.tile(x, (ny + 1) * (nz + 1)), np.tile(np.repeat(y, nx + 1), nz + 1), np.repeat(z, (nx + 1) * (ny + 1))), axis=1)
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    ll = (i + (nx + 1) * (j + (ny + 1) * k)).transpose(2, 1, 0).reshape(-1)
+    dy, dz = nx + 1, (nx + 1) * (ny + 1)
+    conn = np.stack((ll, ll + 1, ll + 1 + dy, ll + dy, ll + dz, ll + 1 + dz, ll + 1 + dy + dz, ll + dy + dz), axis=1).astype(np.int64)
+    return coords, {"hexahedron": conn}
+
+
+def line_grid(n, order=1):
+    """nodeCoords (N,1) on [0, 1] and {"line" | "line3" | "line4": (n, order+1) int64} with the element nodes in the order
+    the reference's LineElement1D places them along the element (LineElement1D.py:158-180): [0, 1], [0, 2, 1], [0, 2, 3, 1]
+    as positions on the equispaced reference grid."""
+    N = n * order + 1
+    coords = np.linspace(0.0, 1.0, N).reshape(-1, 1)
+    first = order * np.arange(n)
+    position = [0] + list(range(2, order + 1)) + [1] if order > 1 else [0, 1]
+    conn = np.stack([first + k for k in position], axis=1).astype(np.int64)
+    return coords, {"line" if order == 1 else f"line{order + 1}": conn}
+
+
+GENERATORS.update({"hexahedron": hex8_grid})

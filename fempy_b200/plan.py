@@ -189,8 +189,9 @@ class AssemblyPlan:
 
     def elementBlocks(self, coords, states, thickness, material, wantK=True, wantR=True):
         coords, states, thickness = as_f64(coords), as_f64(states), as_f64(thickness)
-        Ke = np.empty(sum(E * (2 * n) ** 2 for n, _, E in self.blocks)) if wantK else None
-        Re = np.empty(sum(E * n * 2 for n, _, E in self.blocks)) if wantR else None
+        s = self.numStates
+        Ke = np.empty(sum(E * (s * n) ** 2 for n, _, E in self.blocks)) if wantK else None
+        Re = np.empty(sum(E * n * s for n, _, E in self.blocks)) if wantR else None
         check(
             self._lib.femb_element_blocks(
                 self._h, dptr(coords), dptr(states), dptr(thickness), C.byref(material),

@@ -12,7 +12,7 @@ import numpy as np
 from scipy.sparse import csr_array
 
 from . import assembly_utils as AssemblyUtils
-from .constitutive import FUNC_MASS, FUNC_VON_MISES, PLANE_STRAIN, PLANE_STRESS
+from .constitutive import FUNCTION_IDS, ISO_1D, ISO_3D, PLANE_STRAIN, PLANE_STRESS
 from .plan import AssemblyPlan
 
 
@@ -21,11 +21,11 @@ def materialFor(constitutiveModel):
     from ._lib import Material
 
     name = type(constitutiveModel).__name__
-    modelId = {"IsoPlaneStress": PLANE_STRESS, "IsoPlaneStrain": PLANE_STRAIN}.get(name)
+    modelId = {"IsoPlaneStress": PLANE_STRESS, "IsoPlaneStrain": PLANE_STRAIN, "Iso3D": ISO_3D, "Iso1D": ISO_1D}.get(name)
     if modelId is None:
         raise NotImplementedError(f"constitutive model {name} has no CUDA implementation (and there is no CPU fallback)")
     cm = constitutiveModel
-    return Material(float(cm.E), float(cm.nu), float(cm.rho), modelId, int(not cm.isLinear))
+    return Material(float(cm.E), float(getattr(cm, "nu", 0.0)), float(cm.rho), modelId, int(not cm.isLinear))
 
 
 def planFor(model, device=0):
@@ -56,7 +56,9 @@ class B200AssemblyMixin:
         itself); the arrays are then uploaded when the count moves and the calls pass None."""
         plan = planFor(self.model)
         coords = np.ascontiguousarray(self.model.nodeCoords, dtype=np.float64)
-        thickness = np.ascontiguousarray(self.model.dvs["Thickness"], dtype=np.float64)
+        # the per-element volume scaling (computeVolumeScaling): thickness in 2-D, area in 1-D, none (= 1) in 3-D
+        dvName = {1: "Area", 2: "Thickness"}.get(plan.numDim)
+        thickness = np.ascontiguousarray(self.model.dvs[dvName], dtype=np.float64) if dvName else np.ones(plan.numElements)
         version = getattr(self.model, "_b200_geomVersion", None)
         if version is not None and getattr(self.model, "_b200_residentGeometry", False):
             if getattr(plan, "_geomVersion", None) != version:
@@ -120,7 +122,7 @@ class B200AssemblyMixin:
     def computeFunction(self, name, elementReductionType, globalReductionType=None):
         """Element function over the whole model (Problem.py:282-355)."""
         func = self.model.constitutiveModel.getFunction(name)  # raises ValueError for unknown names
-        funcId = {"mass": FUNC_MASS, "von-mises-stress": FUNC_VON_MISES}[name.lower()]
+        funcId = FUNCTION_IDS[name.lower()]
         if elementReductionType is not None:
             assert elementReductionType.lower() in ["sum", "mean", "integrate", "min", "max", "ksmax", "ksmin"], \
                 "elementReductionType not valid"

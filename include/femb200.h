@@ -27,10 +27,14 @@ typedef struct femb_plan femb_plan;
 /* constitutive model ids (FEMpy/Constitutive/IsoPlaneStress.py, IsoPlaneStrain.py) */
 #define FEMB_PLANE_STRESS 0
 #define FEMB_PLANE_STRAIN 1
+#define FEMB_ISO_3D 2 /* FEMpy/Constitutive/Iso3D.py: 3-D plans (numDim = numStates = 3), no design variable */
+#define FEMB_ISO_1D 3 /* FEMpy/Constitutive/Iso1D.py: 1-D plans, the per-element scaling array is the cross-sectional area */
 
 /* element functions (ConstitutiveModel.getFunction names: "Mass", "Von-Mises-Stress") */
 #define FEMB_FUNC_MASS 0
-#define FEMB_FUNC_VON_MISES 1
+#define FEMB_FUNC_VON_MISES 1 /* 2-D and 3-D models (StressModels/VonMises.py:26-89) */
+#define FEMB_FUNC_STRESS 2    /* Iso1D "Stress" (Iso1D.py:217-225) */
+#define FEMB_FUNC_STRAIN 3    /* Iso1D "Strain" (Iso1D.py:210-215) */
 
 /* element reductions (FEMpy/Elements/Element.py:221-259) */
 #define FEMB_REDUCE_NONE 0 /* (E, P) point values */

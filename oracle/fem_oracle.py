@@ -246,7 +246,7 @@ def element_residuals(dNdxi, w, X, q, theta, model, E, nu, nonlinear=False):
     return out
 
 
-MASS, VON_MISES = 0, 1
+MASS, VON_MISES, STRESS, STRAIN = 0, 1, 2, 3  # STRESS / STRAIN: the bar model's functions (Iso1D.py:203-225)
 REDUCTIONS = ("sum", "mean", "integrate", "min", "max", "ksmax", "ksmin")
 KS_RHO = 100.0  # FEMpy/Utils/KSAgg.py:26
 
@@ -269,6 +269,9 @@ def element_function(dNdxi, w, X, q, func, reduction, model, E, nu, rho, nonline
             eps = strains(up.reshape(-1, *up.shape[2:]), nonlinear)
             sig = np.einsum("as,pa->ps", D, eps)
             vals = von_mises(sig, model, nu).reshape(hi - lo, P)
+        elif func in (STRESS, STRAIN) and model == BAR_1D:
+            eps = strains(up.reshape(-1, *up.shape[2:]), nonlinear)
+            vals = (eps if func == STRAIN else np.einsum("as,pa->ps", D, eps)).reshape(hi - lo, P)
         else:
             raise ValueError("unknown function id")
         if reduction is None:

@@ -11,8 +11,11 @@ Fixtures
   meshes.npz      assembled K (CSR), R, element functions on small quad / quad9 / triangle / mixed meshes
   ks.npz          element-level KS reductions ("ksmax" / "ksmin", Element.py:261-265) of von Mises on the elements.npz inputs
   points.npz      point quantities at arbitrary parametric points, non-default quadrature (intOrder), a caller-supplied function
+  solid_bar.npz   HexElement3D / Iso3D and LineElement1D / Iso1D: element level + assembled hexahedron and line meshes
   lbracket.npz    config 1: Examples/Meshes/LBracket.msh mesh arrays + assembled K, R, solution, functions
 """
+import contextlib
+import io
 import os
 import sys
 
@@ -131,6 +134,67 @@ def gen_points(fp):
             out[key + "_massint"] = el.computeFunction(X, q, dvs, cm.getFunction("Mass"), "integrate", intOrder=order)
             out[key + "_custom_integrate"] = el.computeFunction(X, q, dvs, custom_function, "integrate", intOrder=order)
     np.savez_compressed(os.path.join(OUT, "points.npz"), **out)
+
+
+def gen_solid_bar(fp):
+    """solid_bar.npz: the 3-D and 1-D families: HexElement3D order 1-2 with Iso3D, LineElement1D order 1-3
+    with Iso1D -- element-level K_e / R_e / functions for linear and Green strain, and assembled systems on a hexahedron
+    grid and on line meshes (the reference's model registry builds 27-node hexahedra only at element level:
+    FEMpy/Model.py:470-476 reads an undefined name for them)."""
+    out = {}
+    numEl = 5
+    fams = {"hex1": fp.Elements.HexElement3D(order=1), "hex2": fp.Elements.HexElement3D(order=2)}
+    fams.update({f"line{o}": fp.Elements.LineElement1D(order=o) for o in (1, 2, 3)})
+    for name, el in fams.items():
+        rng = np.random.default_rng(43)
+        X = np.zeros((numEl, el.numNodes, el.numDim))
+        for i in range(numEl):
+            X[i] = el.getRandomElementCoordinates(rng=rng)
+        q = 0.05 * rng.random((numEl, el.numNodes, el.numStates))
+        scale = rng.random(numEl) + 0.5
+        out[f"{name}_X"], out[f"{name}_q"], out[f"{name}_t"] = X, q, scale
+        model = 2 if name.startswith("hex") else 3
+        dvs = {} if model == 2 else {"Area": scale}
+        for linear in (True, False):
+            cm = rh.make_constitutive(fp, model, MAT["E"], MAT["nu"], MAT["rho"], MAT["t"], linear)
+            key = f"{name}_{'lin' if linear else 'nl'}"
+            out[key + "_Ke"] = el.computeResidualJacobians(q, X, dvs, cm)
+            out[key + "_Re"] = el.computeResiduals(q, X, dvs, cm)
+            out[key + "_massint"] = el.computeFunction(X, q, dvs, cm.getFunction("Mass"), "integrate")
+            for fname in (("Von-Mises-Stress",) if model == 2 else ("Stress", "Strain")):
+                out[f"{key}_{fname}"] = el.computeFunction(X, q, dvs, cm.getFunction(fname), None)
+                out[f"{key}_{fname}_mean"] = el.computeFunction(X, q, dvs, cm.getFunction(fname), "mean")
+                out[f"{key}_{fname}_max"] = el.computeFunction(X, q, dvs, cm.getFunction(fname), "max")
+    # assembled systems
+    cases = {"mesh_hex": (meshes.hex8_grid(4, 3, 2), 2, True), "mesh_hex_nl": (meshes.hex8_grid(3, 2, 2), 2, False),
+             "mesh_line": (meshes.line_grid(12, 1), 3, True), "mesh_line3": (meshes.line_grid(7, 2), 3, True), "mesh_line4_nl": (meshes.line_grid(5, 3), 3, False)}
+    for ci, (name, ((coords, conn), model, linear)) in enumerate(cases.items()):
+        rng = np.random.default_rng(300 + ci)
+        if model == 2:
+            coords = coords + 1e-2 * rng.random(coords.shape)
+        else:
+            coords = coords + np.concatenate(([0.0], 2e-2 * rng.random(coords.shape[0] - 2), [0.0])).reshape(-1, 1)
+        elType = next(iter(conn))
+        N, numEl = coords.shape[0], conn[elType].shape[0]
+        states = 1e-3 * rng.random((N, coords.shape[1]))
+        scale = rng.random(numEl) + 0.5
+        left = np.flatnonzero(coords[:, 0] == coords[:, 0].min()) if model == 3 else np.flatnonzero(np.arange(N) % (conn[elType][0, 1] - conn[elType][0, 0] + (4 if name == "mesh_hex" else 3)) == 0)
+        right = np.array([N - 1]) if model == 3 else np.flatnonzero(coords[:, 0] > 0.99)
+        dofs = list(range(coords.shape[1]))
+        _, prob = rh.build_problem(fp, coords, conn, model, MAT["E"], MAT["nu"], MAT["rho"], MAT["t"], linear, thickness=None if model == 2 else scale,
+                                   bcs=[("Fixed", left, dofs, 0.0)], loads=[("Load", right, [0], 1e4, False)], states=states)
+        K, R = rh.assemble(prob)
+        bcDOF, bcVal = fp.Utils.AssemblyUtils.convertBCDictToLists(prob.getBCs())
+        fname = "Von-Mises-Stress" if model == 2 else "Stress"
+        with contextlib.redirect_stdout(io.StringIO()):
+            f = prob.computeFunction(fname, "mean")[elType]
+            mass = prob.computeFunction("Mass", "integrate", "sum")
+        out.update({f"{name}_coords": coords, f"{name}_conn": conn[elType], f"{name}_eltype": np.array([elType]), f"{name}_states": states,
+                    f"{name}_scale": scale, f"{name}_bcDOF": np.array(bcDOF), f"{name}_bcVal": np.array(bcVal, dtype=float),
+                    f"{name}_loads": fp.Utils.AssemblyUtils.convertLoadsDictToVector(prob.loads, K.shape[0]),
+                    f"{name}_meta": np.array([model, int(linear)]), f"{name}_indptr": K.indptr, f"{name}_indices": K.indices,
+                    f"{name}_data": K.data, f"{name}_R": R, f"{name}_func_mean": f, f"{name}_mass": np.array(mass)})
+    np.savez_compressed(os.path.join(OUT, "solid_bar.npz"), **out)
 
 
 def mixed_grid(nx, ny):
@@ -253,11 +317,15 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["points"]:  # round 2 addition
         gen_points(fp)
         sys.exit(0)
+    if sys.argv[1:] == ["solid"]:  # round 2 addition
+        gen_solid_bar(fp)
+        sys.exit(0)
     gen_tables(fp)
     gen_elements(fp)
     gen_meshes(fp)
     gen_lbracket(fp)
     gen_ks(fp)
     gen_points(fp)
+    gen_solid_bar(fp)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -49,6 +49,11 @@ def import_reference():
 
 
 def make_constitutive(fp, model, E, nu, rho, t, linear=True):
+    """model 0 plane stress, 1 plane strain (t = thickness), 2 Iso3D, 3 Iso1D (t = cross-sectional area)"""
+    if model == 2:
+        return fp.Constitutive.Iso3D(E, nu, rho, linear=linear)
+    if model == 3:
+        return fp.Constitutive.Iso1D(E, rho, t, linear=linear)
     cls = {0: fp.Constitutive.IsoPlaneStress, 1: fp.Constitutive.IsoPlaneStrain}[model]
     return cls(E, nu, rho, t, linear=linear)
 
@@ -65,7 +70,7 @@ def build_problem(fp, coords, connectivity, model, E, nu, rho, t, linear=True, t
     con = make_constitutive(fp, model, E, nu, rho, t, linear)
     femModel = fp.FEMpyModel(con, nodeCoords=np.array(coords), connectivity={k: np.array(v) for k, v in connectivity.items()})
     if thickness is not None:
-        femModel.setDesignVariables({"Thickness": np.array(thickness)})
+        femModel.setDesignVariables({("Area" if model == 3 else "Thickness"): np.array(thickness)})
     prob = femModel.addProblem("oracle")
     for name, nodes, dof, value in bcs or []:
         prob.addFixedBCToNodes(name, [int(n) for n in nodes], dof, value)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 from scipy.sparse import csr_array
 
-from fempy_b200 import AssemblyPlan, AssemblyUtils, meshes
+from fempy_b200 import Constitutive, AssemblyPlan, AssemblyUtils, meshes
 from hostmirror import FEMpyModel
 from oracle import fem_oracle as fo
 from test_oracle_golden import COO_COLS, COO_DOF, COO_MATS, COO_ROWS, COO_VALS, KNOWN_QUAD_K, KNOWN_QUAD_X, two_quad_problem
@@ -863,8 +863,10 @@ def test_bad_inputs_raise():
     plan.finalize()
     with pytest.raises(ValueError):
         plan.assemble(np.zeros((3, 2)), np.zeros((4, 2)), np.ones(1), make_cm(0).material())
-    with pytest.raises(FembError, match="2-D"):
-        AssemblyPlan(4, numDim=3, numStates=3)
+    with pytest.raises(FembError, match="one displacement state per dimension"):
+        AssemblyPlan(4, numDim=3, numStates=2)
+    with pytest.raises(FembError, match="constitutive model"):  # a 2-D plan with a 3-D material
+        plan.assemble(np.zeros((4, 2)), np.zeros((4, 2)), np.ones(1), Constitutive.Iso3D(1.0, 0.3, 1.0).material())
     plan.close()
 
 

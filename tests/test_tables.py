@@ -47,4 +47,4 @@ def test_element_sizes_and_errors():
         Elements.TriElement2D(0)
     assert Elements.elementFromMeshioName("quad8", 2) is None
     assert Elements.elementFromMeshioName("quad9", 2).order == 2
-    assert Elements.elementFromMeshioName("hexahedron", 3) is None
+    assert Elements.elementFromMeshioName("hexahedron", 3).numNodes == 8 and Elements.elementFromMeshioName("tetra", 3) is None

@@ -8,5 +8,5 @@ name=$1; shift
 python -m fempy_b200._build > /dev/null 2>&1
 mkdir -p tools/micro
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c -o /tmp/assemble_$name.o fempy_b200/csrc/assemble.cu
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tools/micro/lib_$name.so /tmp/assemble_$name.o fempy_b200/csrc/build/common.o fempy_b200/csrc/build/plan.o fempy_b200/csrc/build/functions.o fempy_b200/csrc/build/solve.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tools/micro/lib_$name.so /tmp/assemble_$name.o fempy_b200/csrc/build/common.o fempy_b200/csrc/build/plan.o fempy_b200/csrc/build/functions.o fempy_b200/csrc/build/solve.o fempy_b200/csrc/build/generic.o
 echo tools/micro/lib_$name.so

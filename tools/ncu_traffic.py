@@ -15,5 +15,6 @@ for arg in sys.argv[1:]:
         return float(m[key]) * scale
 
     out[cfg] = {"kernel": m.get("Kernel Name", "?"), "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
-                "dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"), "gpu_time_us": float(m["gpu__time_duration.sum"])}
+                "dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+                "gpu_time_us": float(m["gpu__time_duration.sum"]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}[u["gpu__time_duration.sum"]]}
 print(json.dumps(out, indent=1))
