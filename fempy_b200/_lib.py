@@ -28,6 +28,8 @@ _SIGNATURES = {
     "femb_last_error": (C.c_char_p, []),
     "femb_version": (C.c_char_p, []),
     "femb_device_count": (C.c_int, []),
+    "femb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "femb_host_free": (C.c_int, [C.c_void_p]),
     "femb_plan_create": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "femb_plan_add_block": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, c_double_p, C.c_int64, c_int64_p]),
     "femb_plan_finalize": (C.c_int, [C.c_void_p]),

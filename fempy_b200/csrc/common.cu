@@ -110,3 +110,18 @@ int exclusive_scan(const int* d_in, int* d_out, int64_t n, cudaStream_t st, int6
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+// Page-locked host buffers for the Python layer's output pool (fempy_b200/_pinned.py): a D2H copy into pinned memory runs
+// at PCIe speed, into fresh pageable memory at a quarter of it (page faults + the driver's staged copy).
+extern "C" int femb_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail("femb_host_alloc: out is NULL");
+    *out = nullptr;
+    if (femb_device_count() == 0) return fail("femb_host_alloc: no CUDA device available");
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return 0;
+}
+
+extern "C" int femb_host_free(void* ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return 0;
+}

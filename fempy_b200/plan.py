@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
+from . import _lib, _pinned
 from ._lib import as_f64, as_i64, check, dptr, iptr
 
 WANT_K, WANT_R = 1, 2
@@ -143,8 +143,10 @@ class AssemblyPlan:
             lv = as_f64(loads)
             if lv.shape != (self.numDOF,):
                 raise ValueError("loads must have numDOF entries")
-        K = (Kout if Kout is not None else np.empty(self.nnz)) if wantK else None
-        R = (Rout if Rout is not None else np.empty(self.numDOF)) if wantR else None
+        # fresh result arrays come from the page-locked pool (_pinned.py): same value semantics, PCIe-speed copy back
+        pinned = _pinned.pool(self._lib)
+        K = (Kout if Kout is not None else pinned.empty(self.nnz)) if wantK else None
+        R = (Rout if Rout is not None else pinned.empty(self.numDOF)) if wantR else None
         for out, n in ((K, self.nnz), (R, self.numDOF)):
             if out is not None and (out.dtype != np.float64 or out.shape != (n,) or not out.flags.c_contiguous):
                 raise ValueError("output buffers must be contiguous float64 arrays of length nnz / numDOF")

@@ -36,8 +36,9 @@ def planFor(model, device=0):
     plan = AssemblyPlan(model.numNodes, model.numDim, model.constitutiveModel.numStates, device=device)
     for elType, elData in model.elements.items():
         el = elData["elementObject"]
-        pts = np.atleast_2d(el.getIntegrationPointCoords())
-        plan.addBlock(el.computeShapeFunctions(pts), el.computeShapeFunctionGradients(pts), el.getIntegrationPointWeights(),
+        pts = el.getIntegrationPointCoords()  # (P, numDim); the reference's 1-D element hands out and expects a flat (P,) array
+        dN = np.asarray(el.computeShapeFunctionGradients(pts))
+        plan.addBlock(el.computeShapeFunctions(pts), dN.reshape(dN.shape[0], model.numDim, -1), el.getIntegrationPointWeights(),
                       elData["connectivity"])
     plan.finalize()
     model._b200_plan = plan

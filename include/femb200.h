@@ -16,6 +16,7 @@
 #ifndef FEMB200_H
 #define FEMB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -64,6 +65,9 @@ typedef struct femb_material {
 } femb_material;
 
 const char* femb_last_error(void);
+/* page-locked host memory for result buffers (the Python layer keeps a pool of them: fempy_b200/_pinned.py) */
+int femb_host_alloc(size_t bytes, void** out);
+int femb_host_free(void* ptr);
 int femb_device_count(void);
 const char* femb_version(void);
 

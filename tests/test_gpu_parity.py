@@ -848,6 +848,38 @@ def test_inverted_element_signed_determinant():
     assert p.computeFunction("Mass", "integrate", "sum") < 0
 
 
+def test_result_arrays_come_from_the_pinned_pool_with_value_semantics():
+    """every assemble call returns its own arrays (as the reference does); they live in page-locked memory that goes back
+    to the pool when the last reference -- including views such as a scipy matrix's data -- is dropped"""
+    import gc
+
+    from fempy_b200 import _pinned
+
+    coords, conn, states, thick, loads, bcDOF, bcVal = _path_case("quad", 21)
+    plan = _raw_plan("quad", coords, conn)
+    mat = make_cm(0).material()
+    K1, R1 = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
+    K2, R2 = plan.assemble(coords, 2.0 * states, thick, mat, bcDOF, bcVal, True, loads)
+    assert not np.shares_memory(K1, K2) and not np.shares_memory(R1, R2)
+    np.testing.assert_array_equal(K1, K2)          # linear model: K does not depend on the state ...
+    assert np.abs(R1 - R2).max() > 0               # ... R does, and the first result is still intact
+    Ko = fo.assemble_residual(oracle_blocks(conn), coords, states, thick, 0, MAT["E"], MAT["nu"], loads, bcDOF, bcVal)
+    assert relerr(R1, Ko) < TOL
+    pool = _pinned.pool(None)
+    M = csr_array((K1, plan.pattern()[1], plan.pattern()[0]), shape=(plan.numDOF, plan.numDOF))
+    addr = K1.ctypes.data
+    del K1
+    gc.collect()
+    assert not pool._free.get(M.data.nbytes)       # the matrix still holds the buffer
+    del M
+    gc.collect()
+    assert addr in pool._free.get(8 * plan.nnz, [])
+    K3, _ = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
+    assert K3.ctypes.data == addr                  # recycled, not re-allocated
+    np.testing.assert_array_equal(K3, K2)
+    plan.close()
+
+
 def test_bad_inputs_raise():
     from fempy_b200._lib import FembError
 
