@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             store((kwc >> 14) & 0x7f, b0, b1, b2, b3, q2);
             apply_d(-fma(P0, yb, fma(Q0, yd, R0 * ye)), -fma(P0, xb, fma(Q0, xd, R0 * xe)), -fma(P1, yb, fma(Q1, yd, R1 * ye)),
                     -fma(P1, xb, fma(Q1, xd, R1 * xe)), k0, k1, k2, k3);
+
         } else {
             // Gh_0 = (y1 - y2, y2 - y0, y0 - y1), Gh_1 = (x2 - x1, x0 - x2, x1 - x0), 2 * area = det
             const double g00 = X1.y - X2.y, g01 = X2.y - ownX.y, g02 = ownX.y - X1.y;
