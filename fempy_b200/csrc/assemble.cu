@@ -169,7 +169,7 @@ static int launch_fan(const femb_plan* p, const DMat& D, const fan::Args& A, cud
 
 template <int NN>
 static int launch_fan_variant(const femb_plan* p, const DMat& D, const fan::Args& A, bool wk, bool wr, cudaStream_t st) {
-    if constexpr (NN == 4) {
+    {
         if (p->blocks[0].fanCompact) {
             if (wk && wr) return launch_fan<NN, true, true, true>(p, D, A, st);
             if (wk) return launch_fan<NN, true, false, true>(p, D, A, st);
@@ -324,7 +324,7 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
                 const long long pfNodes = std::min<long long>(warps * fan::BLOCK, p->numNodes);
                 const double perNode = (double)pfNodes / (double)p->numNodes;
                 A.pfNodes = (int)pfNodes;
-                A.pfRest = (int)(perNode * (double)b.fanRestTotal);
+                A.pfRest = (int)(perNode * (double)b.fanRestTotal);  // in records (16 / 32 bytes, 8 for compact 3-node records)
                 A.pfElems = (int)(perNode * (double)p->numElems);
                 A.pfNodeLimit = pfNodes ? (int)(p->numNodes - pfNodes) : 0;
                 A.pfRestLimit = pfNodes ? (int)(b.fanRestTotal - A.pfRest) : 0;

@@ -33,6 +33,7 @@ static constexpr int BLOCK = 32;
 // sit in a second array.  (The first version read row pointer, corner pointer and BC word from three arrays and then
 // the first record: two dependent levels, 13 % of the stall samples at config 2, 15 % at config 4.)
 //   record, 3 nodes           {slots | flags, node 1, node 2, element}
+//   record, 3 nodes compact   further corners only, 8 bytes: the first node is the previous corner's last (plan.cu: k_fan_rest3)
 //   record, 4 nodes compact   {slots | flags, three node ids and the element id as signed 24-bit differences to the owner}
 //   record, 4 nodes wide      {slots | flags, node 1, node 2, node 3} {element, -, -, -}   (numberings without locality)
 template <int NN, bool CMP>
@@ -85,6 +86,11 @@ __device__ __forceinline__ int4 ld_stream(const int4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ int2 ld_stream(const int2* p) {
+    int2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ int ld_stream(const int* p) {
     int v;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -129,7 +135,19 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
     }
     const int off = h.x, nc = h.z & 0xff, deg = (h.z >> 8) & 0xff;
     const unsigned info = A.useBC ? (unsigned)h.w : 0u;
+    constexpr bool T3C = NN == 3 && CMP;              // 8-byte records for the further corners of 3-node fans
     const int4* rest = A.rest + (long long)RW * h.y;  // record of corner c >= 1 at rest[RW * (c - 1)]
+    const int2* rest2 = reinterpret_cast<const int2*>(A.rest) + h.y;  // T3C
+    // record (and element id) of corner c >= 1
+    auto load_rec = [&](int c, int4& r, int& relem) {
+        if constexpr (T3C) {
+            const int2 v = ld_stream(rest2 + (c - 1));
+            r = make_int4(v.x, v.y, 0, 0);
+        } else {
+            r = ld_stream(rest + RW * (c - 1));
+            if (RW == 2) relem = ld_stream(reinterpret_cast<const int*>(rest + RW * (c - 1) + 1));
+        }
+    };
     if (i < A.pfNodeLimit) {  // L2 look-ahead for the warp that will own node i + pfNodes
         const long long j = i + A.pfNodes;
         prefetch_l2(A.hdr + (1 + RW) * j);
@@ -138,12 +156,15 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
         prefetch_l2(A.states + j);
         if (WR && A.loads) prefetch_l2(A.loads + j);
     }
-    if (h.y < A.pfRestLimit) prefetch_l2(rest + RW * A.pfRest);
+    if (h.y < A.pfRestLimit) {
+        if (T3C) prefetch_l2(rest2 + A.pfRest);
+        else prefetch_l2(rest + RW * A.pfRest);
+    }
     // node ids / element id of a record (CMP: four signed 24-bit differences to my node id)
     auto decode = [&](const int4 r, const int relem, int& n1, int& n2, int& n3, int& e) {
         n1 = r.y, n2 = r.z, n3 = r.w;  // 3 nodes: the fourth word is the element id
         e = NN == 4 ? relem : r.w;
-        if constexpr (CMP) {
+        if constexpr (CMP && NN == 4) {
             const int me = (int)i;
             e = me + (r.w >> 8);
             n3 = me + ((int)(__funnelshift_r((unsigned)r.z, (unsigned)r.w, 16) << 8) >> 8);
@@ -167,10 +188,7 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
         if (NN == 4) X3 = ld_early(A.coords + n3);
         theta = ld_early(A.thick + e);
         if (NN == 4 && e < A.pfElemLimit) prefetch_l2(A.thick + e + A.pfElems);
-        if (nc > 1) {
-            rec1 = ld_stream(rest);
-            if (RW == 2) el1 = ld_stream(reinterpret_cast<const int*>(rest + 1));
-        }
+        if (nc > 1) load_rec(1, rec1, el1);
     }
     const int firstSlot = ((unsigned)rec.x >> 7) & 0x7f, firstNode = n1;  // closed fans wrap into the first corner's first neighbour
     unsigned kw = (unsigned)rec.x, lastFlags = 0u;
@@ -221,18 +239,22 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
         }
         int4 rec2 = make_int4(0, 0, 0, 0);
         int el2 = 0;
-        if (c + 2 < nc) {
-            rec2 = ld_stream(rest + RW * (c + 1));
-            if (RW == 2) el2 = ld_stream(reinterpret_cast<const int*>(rest + RW * (c + 1) + 1));
-        }
+        if (c + 2 < nc) load_rec(c + 2, rec2, el2);
         const unsigned kwc = kw;
         lastFlags = kwc;
         if (NN == 3 && e < A.pfElemLimit) prefetch_l2(A.thick + e + A.pfElems);
         // the next corner's coordinates and thickness replace this corner's once the geometry has consumed them
         auto next_corner = [&]() {
             if (c + 1 < nc) {
-                decode(rec1, el1, n1, n2, n3, e);
-                X1 = ld_early(A.coords + n1);
+                if constexpr (T3C) {  // one chain: this corner's last node is the next one's first (coordinates are at hand)
+                    n1 = n2;
+                    X1 = X2;
+                    n2 = (int)i + (int)(short)(((unsigned)rec1.y & 0x1ffu) | ((((unsigned)rec1.x >> 21) & 0x7fu) << 9));
+                    e = (int)i + (rec1.y >> 9);
+                } else {
+                    decode(rec1, el1, n1, n2, n3, e);
+                    X1 = ld_early(A.coords + n1);
+                }
                 X2 = ld_early(A.coords + n2);
                 if (NN == 4) X3 = ld_early(A.coords + n3);
                 theta = ld_early(A.thick + e);

@@ -525,6 +525,37 @@ __global__ void k_fan_headers(long long N, long long Npad, int rw, const int* __
         if (rw == 2) rest[(long long)rw * (r0 + k - 1) + 1] = make_int4(fanElem[c0 + k], 0, 0, 0);
     }
 }
+// Compact 3-node fan records (8 bytes): in a single chain the first node of a corner is the last node of the one before it,
+// so a further corner only names its second node and its element -- as signed differences to the owner's id:
+//   x = slots (21 bits) | (node 2 - i) bits 9..15 << 21 | flags (bits 28, 29)       y = (node 2 - i) bits 0..8 | (element - i) << 9
+// Fits when every node's corners form ONE chain and |node 2 - i| < 2^15, |element - i| < 2^22 (checked here); else the
+// plan keeps the 16-byte records.
+__global__ void k_fan_fits3(long long N, const int* __restrict__ cBegin, const int* __restrict__ cEnd, const int4* __restrict__ fanRec,
+                            int* __restrict__ bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int c0 = cBegin[i], c1 = cEnd[i];
+    for (int c = c0; c < c1; ++c) {
+        const int4 r = fanRec[c];  // {slots | flags, node 1, node 2, element}
+        if (c + 1 < c1 && !((unsigned)r.x & (1u << 28))) atomicExch(bad, 1);  // chain break: the next corner starts a new fan
+        if (c > c0) {
+            const long long d2 = r.z - i, de = r.w - i;
+            if (d2 < -(1 << 15) || d2 >= (1 << 15) || de < -(1 << 22) || de >= (1 << 22)) atomicExch(bad, 1);
+        }
+    }
+}
+__global__ void k_fan_rest3(long long N, const int* __restrict__ cBegin, const int* __restrict__ cEnd, const int* __restrict__ restPtr,
+                            const int4* __restrict__ fanRec, int2* __restrict__ rest) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int c0 = cBegin[i], nc = cEnd[i] - c0, r0 = restPtr[i];
+    for (int k = 1; k < nc; ++k) {
+        const int4 r = fanRec[c0 + k];
+        const unsigned d2 = (unsigned)(r.z - (int)i) & 0xffffu, de = (unsigned)(r.w - (int)i) & 0x7fffffu;
+        rest[r0 + k - 1] = make_int2((int)(((unsigned)r.x & 0x301fffffu) | ((d2 >> 9) << 21)), (int)((d2 & 0x1ffu) | (de << 9)));
+    }
+}
+
 __global__ void k_fan_header_bcs(long long N, int stride, const int* __restrict__ bcInfo, int4* __restrict__ hdr) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N) hdr[stride * i].w = bcInfo[i];
@@ -735,6 +766,13 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
                 if (!b.fanOK) {
                     dfree(b.d_fanRec);
                     dfree(b.d_fanElem);
+                } else if (b.nn == 3 && p->fanCompactAllowed) {  // 8-byte records where every node has one chain and the numbering is local
+                    CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
+                    k_fan_fits3<<<grid_for(N, 128), 128, 0, st>>>(N, p->d_blockAdj, p->d_blockAdj + (size_t)N, b.d_fanRec, p->d_flag);
+                    CUDA_TRY(cudaMemcpyAsync(&bad, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    launches++;
+                    b.fanCompact = !bad;
                 } else if (b.nn == 4 && p->fanCompactAllowed) {  // element id into the record when the numbering has the locality for it
                     CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
                     k_fan_fits<<<grid_for(N, 128), 128, 0, st>>>(N, p->d_blockAdj, p->d_blockAdj + (size_t)N, b.d_fanRec, b.d_fanElem, p->d_flag);
@@ -768,6 +806,11 @@ extern "C" int femb_plan_finalize(femb_plan* p) {
                         k_fan_headers<<<grid_for(Npad, 128), 128, 0, st>>>(N, Npad, rw, p->d_nrowptr, p->d_blockAdj, p->d_blockAdj + (size_t)N,
                                                                          d_restPtr, b.d_fanRec, b.d_fanElem, b.d_fanHdr, b.d_fanRest);
                         launches++;
+                        if (b.nn == 3 && b.fanCompact) {  // the further corners again, as 8-byte records over the same allocation
+                            k_fan_rest3<<<grid_for(N, 128), 128, 0, st>>>(N, p->d_blockAdj, p->d_blockAdj + (size_t)N, d_restPtr, b.d_fanRec,
+                                                                          (int2*)b.d_fanRest);
+                            launches++;
+                        }
                         if (cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
                     }
                     dfree(b.d_fanRec);  // the kernel reads headers + rest only

@@ -619,7 +619,7 @@ def test_fan_kernel_matches_oracle(elType, n, renumber, fan, compact):
         case = _renumbered(case)
     plan = _raw_plan(elType, case[0], case[1], fan=fan, fanCompact=compact)
     assert plan.info("rows_path") == 1 and plan.info("fan_path") == fan
-    assert plan.info("fan_compact") == (1 if (compact and elType == "quad") else 0)
+    assert plan.info("fan_compact") == (1 if compact else 0)  # quads: 24-bit differences; triangles: 8-byte chained records
     K1, R1 = _check_against_oracle(plan, elType, case, launchesExpected=1)
     plan.setOption("fan_rows", 1 - fan)  # the other kernel on the same plan: same values to rounding
     mat = make_cm(0).material()
@@ -668,6 +668,13 @@ def test_fan_kernel_open_fans_bow_ties_and_fallbacks():
     tri2 = tri.copy()
     tri2[2] = tri2[2][[0, 2, 1]]
     _check_small(coords, {"triangle": tri2}, "triangle", expectFan=0)
+    # triangle bow tie: two fans at node 2 -- the chained 8-byte records do not apply, the plan keeps the 16-byte ones
+    coords = np.array([[0.0, 0.0], [1.0, 0.1], [1.1, 1.0], [2.2, 1.1], [2.3, 2.0], [0.1, 1.1]])
+    tri = np.array([[0, 1, 2], [2, 3, 4], [0, 2, 5]])
+    plan = _raw_plan("triangle", coords, {"triangle": tri})
+    assert plan.info("fan_path") == 1 and plan.info("fan_compact") == 0
+    plan.close()
+    _check_small(coords, {"triangle": tri}, "triangle", expectFan=1)
 
 
 def test_tables_without_cyclic_symmetry_leave_the_row_owner_path():
