@@ -41,12 +41,15 @@ class PinnedPool:
         return np.frombuffer(buf, dtype=dtype)
 
     def _release(self, ptr, nbytes):
-        parked = self._free.setdefault(nbytes, [])
-        if len(parked) < self.maxFreePerSize:
-            parked.append(ptr)
-        else:
-            self._lib.femb_host_free(ptr)
-            self.bytesLive -= nbytes
+        try:
+            parked = self._free.setdefault(nbytes, [])
+            if len(parked) < self.maxFreePerSize:
+                parked.append(ptr)
+            else:
+                self._lib.femb_host_free(ptr)
+                self.bytesLive -= nbytes
+        except Exception:  # interpreter shutdown: the library may already be gone; the OS reclaims the memory
+            pass
 
     def trim(self):
         """give every parked buffer back to the OS"""
