@@ -633,6 +633,35 @@ def test_fan_kernel_matches_oracle(elType, n, renumber, fan, compact):
     plan.close()
 
 
+def test_chained_triangle_records_fall_back_without_locality_and_look_ahead_is_only_a_hint():
+    """8-byte chained 3-node records need |node - owner| < 2^15: a 70 k-node mesh with random numbering keeps the 16-byte
+    records (same values as the scatter kernels); the L2 look-ahead distance never changes a bit of the result"""
+    case = _renumbered(_path_case("triangle", 268))
+    coords, conn, states, thick, loads, bcDOF, bcVal = case
+    assert coords.shape[0] > 65536
+    plan = _raw_plan("triangle", coords, conn)
+    assert plan.info("fan_path") == 1 and plan.info("fan_compact") == 0
+    mat = make_cm(0).material()
+    K, R = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
+    ref = _raw_plan("triangle", coords, conn, path="scatter")
+    K0, R0 = ref.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
+    np.testing.assert_array_equal(plan.pattern()[1], ref.pattern()[1])
+    assert relerr(K, K0) < 1e-13 and relerr(R, R0) < 1e-13
+    ref.close()
+    plan.close()
+    ordered = _path_case("triangle", 268)
+    plan = _raw_plan("triangle", ordered[0], ordered[1])
+    assert plan.info("fan_compact") == 1
+    results = []
+    for pf in (-1, 0, 7, 100000):
+        plan.setOption("fan_prefetch", pf)
+        results.append(plan.assemble(ordered[0], ordered[2], ordered[3], mat, ordered[5], ordered[6], True, ordered[4]))
+    for Kp, Rp in results[1:]:
+        np.testing.assert_array_equal(Kp, results[0][0])
+        np.testing.assert_array_equal(Rp, results[0][1])
+    plan.close()
+
+
 def _check_small(coords, conn, elType, expectFan, expectRows=1):
     N = coords.shape[0]
     numEl = conn[elType].shape[0]
