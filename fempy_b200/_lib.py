@@ -32,6 +32,7 @@ _SIGNATURES = {
     "femb_host_free": (C.c_int, [C.c_void_p]),
     "femb_plan_create": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "femb_plan_add_block": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, c_double_p, C.c_int64, c_int64_p]),
+    "femb_plan_add_block_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_void_p]),
     "femb_plan_finalize": (C.c_int, [C.c_void_p]),
     "femb_plan_destroy": (None, [C.c_void_p]),
     "femb_plan_set_stream": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),

@@ -603,8 +603,22 @@ extern "C" int femb_plan_create(int64_t numNodes, int32_t numDim, int32_t numSta
     return 0;
 }
 
+static int add_block(femb_plan* p, int32_t nn, int32_t nq, const double* N, const double* dNdxi, const double* w, int64_t numElems,
+                     const int64_t* conn, bool connOnDevice);
+
 extern "C" int femb_plan_add_block(femb_plan* p, int32_t nn, int32_t nq, const double* N, const double* dNdxi,
                                    const double* w, int64_t numElems, const int64_t* conn) {
+    return add_block(p, nn, nq, N, dNdxi, w, numElems, conn, false);
+}
+
+// the same with the connectivity already on the plan's device (mesh generated or ingested there): no host copy of the mesh
+extern "C" int femb_plan_add_block_dev(femb_plan* p, int32_t nn, int32_t nq, const double* N, const double* dNdxi,
+                                       const double* w, int64_t numElems, const int64_t* d_conn) {
+    return add_block(p, nn, nq, N, dNdxi, w, numElems, d_conn, true);
+}
+
+static int add_block(femb_plan* p, int32_t nn, int32_t nq, const double* N, const double* dNdxi, const double* w, int64_t numElems,
+                     const int64_t* conn, bool connOnDevice) {
     if (!p) return fail("femb_plan_add_block: plan is NULL");
     if (p->finalized) return fail("femb_plan_add_block: plan already finalized");
     if ((int)p->blocks.size() >= MAX_BLOCKS) return fail("femb_plan_add_block: at most %d element types", MAX_BLOCKS);
@@ -640,7 +654,7 @@ extern "C" int femb_plan_add_block(femb_plan* p, int32_t nn, int32_t nq, const d
     const size_t cnt = (size_t)numElems * nn;
     CUDA_TRY(d_conn64.alloc(cnt));
     CUDA_TRY(cudaMalloc(&b.d_conn, cnt * sizeof(int)));
-    CUDA_TRY(cudaMemcpyAsync(d_conn64, conn, cnt * sizeof(long long), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_conn64, conn, cnt * sizeof(long long), connOnDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
     k_convert_conn<<<grid_for((int64_t)cnt, 256), 256, 0, p->stream>>>(d_conn64, b.d_conn, numElems, nn, p->numNodes,
                                                                         p->d_flag);

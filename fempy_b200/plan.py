@@ -38,6 +38,16 @@ class AssemblyPlan:
         check(self._lib.femb_plan_add_block(self._h, n, P, dptr(N), dptr(dNdxi), dptr(w), conn.shape[0], iptr(conn)))
         self.blocks.append((n, P, conn.shape[0]))
 
+    def addBlockDev(self, N, dNdxi, w, d_conn, numElems):
+        """addBlock with the (numElems, n) int64 connectivity already on the plan's device (pointer or object with
+        .data_ptr()): device-side mesh ingest."""
+        N, dNdxi, w = as_f64(N), as_f64(dNdxi), as_f64(w)
+        P, n = N.shape
+        if dNdxi.shape != (P, self.numDim, n) or w.shape != (P,):
+            raise ValueError("inconsistent element table shapes")
+        check(self._lib.femb_plan_add_block_dev(self._h, n, P, dptr(N), dptr(dNdxi), dptr(w), int(numElems), _p(d_conn)))
+        self.blocks.append((n, P, int(numElems)))
+
     def finalize(self):
         check(self._lib.femb_plan_finalize(self._h))
         self.finalized = True

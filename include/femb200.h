@@ -83,6 +83,10 @@ int femb_plan_create(int64_t numNodes, int32_t numDim, int32_t numStates, int32_
  * computeShapeFunctionGradients / getIntegrationPointWeights).  conn: (numElems, n) node ids. */
 int femb_plan_add_block(femb_plan* plan, int32_t nodesPerElem, int32_t numQuad, const double* N, const double* dNdxi,
                         const double* w, int64_t numElems, const int64_t* conn);
+/* the same with the connectivity already in device memory (device-side mesh ingest): the element registry,
+ * DOF map (FEMpy/Model.py:123-142,387-414), pattern and kernel records are then built without the mesh touching the host */
+int femb_plan_add_block_dev(femb_plan* plan, int32_t nodesPerElem, int32_t numQuad, const double* N, const double* dNdxi,
+                        const double* w, int64_t numElems, const int64_t* d_conn);
 
 /* builds the node->element adjacency, the sorted structural CSR pattern and the corner records of the row-owner
  * kernel (the element scatter map of the fallback kernels is built on their first use) */

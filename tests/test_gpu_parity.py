@@ -916,6 +916,30 @@ def test_result_arrays_come_from_the_pinned_pool_with_value_semantics():
     plan.close()
 
 
+def test_connectivity_from_device_memory():
+    """femb_plan_add_block_dev: the mesh connectivity is taken from device memory; same plan, same values"""
+    import torch
+
+    coords, conn, states, thick, loads, bcDOF, bcVal = _path_case("quad", 25)
+    el = ELEMENT_FOR["quad"]()
+    d_conn = torch.from_numpy(conn["quad"]).cuda()
+    plan = AssemblyPlan(coords.shape[0])
+    plan.addBlockDev(*el.tables(), d_conn, conn["quad"].shape[0])
+    plan.finalize()
+    ref = _raw_plan("quad", coords, conn)
+    np.testing.assert_array_equal(plan.pattern()[1], ref.pattern()[1])
+    mat = make_cm(0).material()
+    K, R = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
+    K0, R0 = ref.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
+    np.testing.assert_array_equal(K, K0)
+    np.testing.assert_array_equal(R, R0)
+    bad = torch.full((3, 4), 10**6, dtype=torch.int64).cuda()
+    with pytest.raises(Exception, match="outside"):
+        AssemblyPlan(16).addBlockDev(*el.tables(), bad, 3)
+    plan.close()
+    ref.close()
+
+
 def test_bad_inputs_raise():
     from fempy_b200._lib import FembError
 
