@@ -12,7 +12,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -59,16 +58,17 @@ def algorithmic_bytes(wl, nnz):
     return 4 * nn * wl["numElems"] + 16 * wl["numNodes"] * 2 + 8 * wl["numElems"] + 8 * nnz + 16 * wl["numNodes"]
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+class ClockSampler:
+    """SM clock and throttle reasons of one GPU through NVML, sampled DURING the timed region: `sample()` is called from
+    the timing loop every few steps, right after the L2 flush has been queued and before the step's start event -- the GPU
+    is under load, but no NVML query lands inside a timed interval (a sampling thread did: at 2 GPUs it inflated single
+    steps of one rank by milliseconds)."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index, period=0.01):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.maxMhz, self.period = index, [], set(), None, period
-        self._halt = threading.Event()
+    def __init__(self, index, every=8):
+        self.index, self.samples, self.reasons, self.maxMhz, self.every, self.calls = index, [], set(), None, every, 0
         try:
             import pynvml
 
@@ -79,21 +79,24 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.nv = None
 
-    def run(self):
-        while not self._halt.is_set() and self.nv is not None:
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(self.period)
+    def start(self):
+        self.sample(force=True)
+
+    def sample(self, force=False):
+        self.calls += 1
+        if self.nv is None or not (force or self.calls % self.every == 0):
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=2)
+        self.sample(force=True)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.maxMhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
@@ -406,6 +409,7 @@ def run_ours(args, rank, world, local_rank):
     sampler.start()
     for i in range(args.steps):
         flush_l2()  # evict the previous step's working set from L2 (untimed)
+        sampler.sample()
         starts[i].record(stream)
         step()
         ends[i].record(stream)
@@ -654,6 +658,7 @@ def run_ours_multi(args, rank, world, local_rank, dev):
         sampler.start()
         for i in range(steps):
             flush_l2()
+            sampler.sample()
             starts[i].record(stream)
             step()
             ends[i].record(stream)
