@@ -20,6 +20,10 @@
 //            theta / (8 det J) over the Gauss points;
 //   3 nodes  constant gradients: S[d][D]_0b = theta / (2 det J) * Gh_d0 Gh_Db, Gh = adj(J) dN.
 // D is applied per block: K = [[D00 S00 + D22 S11, D01 S01 + D22 S10], [D01 S10 + D22 S01, D11 S11 + D22 S00]].
+//
+// Memory side: per-node headers with the first corner record inline (one load level before the first
+// element), records two corners ahead / node data one corner ahead in registers, an L2 look-ahead for the warps of the next
+// resident wave, and -- 4-node elements -- the finished run written out by ONE cp.async.bulk per warp.
 #pragma once
 #include "assemble_rows.cuh"
 

@@ -41,11 +41,6 @@ struct Args {
     double* out;           // function values
 };
 
-template <int DIM>
-__device__ __forceinline__ constexpr int num_strains() {
-    return DIM * (DIM + 1) / 2;
-}
-
 // signed determinant and inverse (LinAlg.py:54-189)
 template <int DIM>
 __device__ __forceinline__ double inverse(const double (&J)[DIM][DIM], double (&I)[DIM][DIM]) {
