@@ -706,6 +706,76 @@ def test_fan_kernel_open_fans_bow_ties_and_fallbacks():
     _check_small(coords, {"triangle": tri}, "triangle", expectFan=1)
 
 
+@pytest.mark.parametrize("oriented", [True, False])
+def test_unstructured_delaunay_triangulation(oriented):
+    """an unstructured triangle mesh (Delaunay triangulation of random points: node valences 3..10+, no numbering
+    locality): consistently oriented it takes the fan kernel (wide or chained records, whatever fits); with the
+    triangulation's own mixed orientations the corners do not chain and the plan takes the accumulating kernel"""
+    from scipy.spatial import Delaunay
+
+    rng = np.random.default_rng(21)
+    coords = rng.random((4000, 2)) * np.array([2.0, 1.0])
+    tri = Delaunay(coords).simplices.astype(np.int64)
+    a, b, c = coords[tri[:, 0]], coords[tri[:, 1]], coords[tri[:, 2]]
+    area2 = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1])
+    tri = tri[np.abs(area2) > 1e-9]  # drop slivers on the hull
+    area2 = area2[np.abs(area2) > 1e-9]
+    if oriented:
+        tri[area2 < 0] = tri[area2 < 0][:, [0, 2, 1]]
+    else:
+        flip = rng.random(tri.shape[0]) < 0.5
+        tri[flip] = tri[flip][:, [0, 2, 1]]
+    used = np.unique(tri)
+    assert used.size == coords.shape[0]
+    N, numEl = coords.shape[0], tri.shape[0]
+    conn = {"triangle": tri}
+    case = (coords, conn, 1e-3 * rng.random((N, 2)), rng.random(numEl) + 0.5, rng.random(2 * N), np.array([0, 1, 9, 2 * N - 1]),
+            np.array([1e-4, 0.0, 2e-4, -1e-4]))
+    plan = _raw_plan("triangle", coords, conn)
+    assert plan.info("rows_path") == 1 and plan.info("fan_path") == (1 if oriented else 0)
+    assert plan.info("max_degree") >= 9
+    _check_against_oracle(plan, "triangle", case, launchesExpected=1)
+    plan.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_meshes_numberings_and_boundary_conditions(seed):
+    """randomised sweep: element type, mesh size, node renumbering, constitutive model, BC / load sets (duplicates, negative
+    indices) drawn from the seed -- K pattern bit-exact, K / R / von Mises to 1e-12 against the oracle"""
+    rng = np.random.default_rng(1000 + seed)
+    elType = ["quad", "triangle", "quad9", "triangle6"][seed % 4]
+    nx, ny = int(rng.integers(2, 40)), int(rng.integers(2, 40))
+    if elType in ("quad9", "triangle6"):
+        nx, ny = max(2, nx // 3), max(2, ny // 3)
+    coords, conn = meshes.GENERATORS[elType](nx, ny)
+    coords = coords + 0.2 / max(nx, ny) / 3 * rng.random(coords.shape)
+    N, numEl = coords.shape[0], conn[elType].shape[0]
+    states, thick, loads = 1e-3 * rng.random((N, 2)), rng.random(numEl) + 0.5, rng.random(2 * N)
+    nbc = int(rng.integers(1, 12))
+    bcDOF = rng.integers(-2 * N, 2 * N, nbc)
+    bcDOF = np.concatenate((bcDOF, bcDOF[: nbc // 2]))  # duplicates: the occurrence count lands on the diagonal
+    bcVal = rng.random(bcDOF.size) * 1e-4
+    case = (coords, conn, states, thick, loads, bcDOF, bcVal)
+    if rng.random() < 0.5:
+        case = _renumbered((coords, conn, states, thick, loads, np.where(bcDOF < 0, bcDOF + 2 * N, bcDOF), bcVal), seed=seed)
+    coords, conn, states, thick, loads, bcDOF, bcVal = case
+    model = int(rng.integers(0, 2))
+    plan = _raw_plan(elType, coords, conn)
+    mat = make_cm(model).material()
+    K, R = plan.assemble(coords, states, thick, mat, bcDOF, bcVal, True, loads)
+    blocks = oracle_blocks(conn)
+    bcPos = np.where(np.asarray(bcDOF) < 0, np.asarray(bcDOF) + 2 * N, bcDOF)
+    Ko = fo.assemble_matrix(blocks, coords, states, thick, model, MAT["E"], MAT["nu"], bcPos, dropZeros=False)
+    Ko.sort_indices()
+    Ro = fo.assemble_residual(blocks, coords, states, thick, model, MAT["E"], MAT["nu"], loads, bcPos, bcVal)
+    np.testing.assert_array_equal(plan.pattern()[0], Ko.indptr)
+    np.testing.assert_array_equal(plan.pattern()[1], Ko.indices)
+    assert relerr(K, Ko.data) < TOL and relerr(R, Ro) < TOL, (elType, nx, ny)
+    vm = plan.function(coords, states, mat, 1, "max")
+    assert relerr(vm, fo.compute_function(blocks, coords, states, fo.VON_MISES, "max", model, MAT["E"], MAT["nu"], MAT["rho"])[0]) < TOL
+    plan.close()
+
+
 def test_tables_without_cyclic_symmetry_leave_the_row_owner_path():
     """the rotated corner records need basis + rule invariant under cyclic renumbering; a 4-node block whose tables are
     in tensor order (0,1,2,3 = BL,BR,TL,TR) is not: the plan runs the scatter kernels for it and stays exact"""
