@@ -5,17 +5,20 @@ fresh pageable array costs more than the assembly: 18 ms for the 75 MB of config
 staged copy) against 2 ms into page-locked memory (tools/time_plugin.py).  The pool hands out numpy arrays that live in
 page-locked memory obtained from the library (femb_host_alloc); when the last reference to such an array -- or to any view
 of it, e.g. the `data` of a scipy matrix -- is dropped, its buffer goes back to the pool instead of to the OS.  A caller
-that keeps results alive simply makes the pool allocate new buffers; beyond `maxBytes` of pinned memory it returns ordinary
-pageable arrays.
+that keeps results alive simply makes the pool allocate new buffers; beyond `maxBytes` of pinned memory (16 GB unless
+FEMB200_PINNED_POOL_BYTES says otherwise) it returns ordinary pageable arrays.
 """
 import ctypes as C
+import os
 import weakref
 
 import numpy as np
 
 
 class PinnedPool:
-    def __init__(self, lib, maxBytes=4 << 30, maxFreePerSize=3):
+    def __init__(self, lib, maxBytes=None, maxFreePerSize=3):
+        if maxBytes is None:  # default 16 GB of page-locked memory at most (FEMB200_PINNED_POOL_BYTES overrides; 0 switches the pool off)
+            maxBytes = int(os.environ.get("FEMB200_PINNED_POOL_BYTES", 16 << 30))
         self._lib = lib
         self.maxBytes, self.maxFreePerSize = maxBytes, maxFreePerSize
         self._free = {}   # nbytes -> [pointers]
