@@ -80,7 +80,15 @@ int femb_plan_create(int64_t numNodes, int32_t numDim, int32_t numStates, int32_
 /* one element type ("block"); element ids run across blocks in the order they are added
  * (FEMpy/Model.py:137-142).  N: (P, n) shape functions, dNdxi: (P, numDim, n) parametric gradients,
  * w: (P) weights at the element's own Gauss points (Element.computeShapeFunctions /
- * computeShapeFunctionGradients / getIntegrationPointWeights).  conn: (numElems, n) node ids. */
+ * computeShapeFunctionGradients / getIntegrationPointWeights).  conn: (numElems, n) node ids.
+ * Supported: 2-D plans -- 3/6/10-node triangles and 4/9/16-node quads with the families' default rules (1/3/3 and 4/9/16
+ * points) or the other rules `intOrder=` can select (triangles 1/3/4 points, quads n x n with n = 1..4); 1-D / 3-D plans --
+ * any Lagrange family of up to 27 nodes.  Which kernel a 2-D block gets is decided from its TABLES, checked here on the
+ * host: the row-owner / fan kernels evaluate a 3- or 4-node element renumbered so that the row's node comes first, which is
+ * exact only for tables invariant under cyclic renumbering of the nodes (counter-clockwise order + a rotation-symmetric
+ * rule, as QuadElement2D / TriElement2D order 1); the closed-form fan kernel additionally needs the standard bilinear /
+ * linear tables.  Blocks whose tables fail a check (e.g. a 4-node block in tensor order BL, BR, TL, TR) run on the scatter
+ * kernels -- same result, FP64 atomics (femb_plan_get_info "rows_path" / "fan_path" / "closed_form_q4" tell). */
 int femb_plan_add_block(femb_plan* plan, int32_t nodesPerElem, int32_t numQuad, const double* N, const double* dNdxi,
                         const double* w, int64_t numElems, const int64_t* conn);
 /* the same with the connectivity already in device memory (device-side mesh ingest): the element registry,
@@ -100,7 +108,10 @@ void femb_plan_destroy(femb_plan* plan);
  *   "fan_rows": 1 (default) single-block plans of 3- / 4-node elements with the reference's order-1 tables run the
  *       write-once fan kernel for the small-strain model (corners of a node chained into fans, every row block finished
  *       in registers and stored once); 0: the accumulating row-owner kernel.  "fan_compact" (before finalize): 0 keeps the
- *       wide fan records even when node / element ids fit 24-bit differences (tests);
+ *       wide fan records even when node / element ids fit the compact forms (4 nodes: 24-bit differences to the owner;
+ *       3 nodes: 8-byte chained records) (tests); "fan_prefetch": L2 look-ahead distance of the fan kernel in 32-node
+ *       warps (-1 default: one resident wave, 0 off; a hint only, results do not depend on it);
+ *   "points_only" (before the first block): blocks of any node / point count, for femb_point_quantities only;
  *   "balance_rows" (before finalize): row schedule of the row-owner kernel -- 0 threads take nodes in node order,
  *       1 (default) nodes of every 256-node window are ordered by their number of adjacent elements when that saves
  *       more than 8 % of the warps' element iterations (9-node quads, mixed meshes), 2 always; results do not depend on it */
