@@ -317,10 +317,12 @@ extern "C" int femb_assemble_dev(femb_plan* p, const double* d_coords, const dou
             A.bcNodeVal = (const double2*)p->d_bcNodeVal;
             A.maxDeg = p->maxDeg;
             A.zero = 0;
-            {   // L2 look-ahead distance: by default the warps one resident wave ahead (SMs x resident warps per SM)
+            {   // L2 look-ahead distance: by default a sixth of the resident wave (SMs x resident warps per SM / 6) -- far enough
+                // for the prefetch to land, near enough that the lines are still in L2 when their warp starts (measured:
+                // 200..600 warps at configs 2 / 5, 600..900 at config 4; a whole wave ahead loses 2..5 %)
                 if (p->numSMs <= 0 && cudaDeviceGetAttribute(&p->numSMs, cudaDevAttrMultiProcessorCount, p->device) != cudaSuccess) p->numSMs = 148;
                 const int sms = p->numSMs;
-                const long long warps = p->fanPrefetch >= 0 ? p->fanPrefetch : (long long)sms * (b.nn == 3 ? fan::resident_warps<3>() : fan::resident_warps<4>());
+                const long long warps = p->fanPrefetch >= 0 ? p->fanPrefetch : (long long)sms * (b.nn == 3 ? fan::resident_warps<3>() : fan::resident_warps<4>()) / 6;
                 const long long pfNodes = std::min<long long>(warps * fan::BLOCK, p->numNodes);
                 const double perNode = (double)pfNodes / (double)p->numNodes;
                 A.pfNodes = (int)pfNodes;

@@ -22,8 +22,8 @@
 // D is applied per block: K = [[D00 S00 + D22 S11, D01 S01 + D22 S10], [D01 S10 + D22 S01, D11 S11 + D22 S00]].
 //
 // Memory side: per-node headers with the first corner record inline (one load level before the first
-// element), records two corners ahead / node data one corner ahead in registers, an L2 look-ahead for the warps of the next
-// resident wave, and -- 4-node elements -- the finished run written out by ONE cp.async.bulk per warp.
+// element), records two corners ahead / node data one corner ahead in registers, an L2 look-ahead for the warps a
+// sixth of a resident wave ahead, and -- 4-node elements -- the finished run written out by ONE cp.async.bulk per warp.
 #pragma once
 #include "assemble_rows.cuh"
 
@@ -58,8 +58,8 @@ struct Args {
     const double2* bcNodeVal;
     int maxDeg;
     int zero;                 // always 0 (runtime-uniform index: keeps D out of the constant-bank operand slot)
-    // L2 look-ahead (0 = off): every thread asks L2 for the inputs of the node pfNodes ahead of its own -- about one wave
-    // of warps -- so that later warps find headers, records, node data and thickness in L2 instead of DRAM
+    // L2 look-ahead (0 = off): every thread asks L2 for the inputs of the node pfNodes ahead of its own -- a fraction of
+    // a resident wave of warps -- so that later warps find headers, records, node data and thickness in L2 instead of DRAM
     // (limits = array length - distance, 0 when off: an index below its limit has a valid look-ahead target)
     int pfNodes, pfNodeLimit, pfRest, pfRestLimit, pfElems, pfElemLimit;
     double* K;

@@ -92,7 +92,7 @@ struct femb_plan {
     long long* d_rowStats = nullptr;  // measurement builds only (ROWS_TRACE): warp lifetime statistics
     int assemblyPath = 2;        // 2 row-owner kernel, 0 slot-map scatter with FP64 atomics
     bool fanCompactAllowed = true;  // option "fan_compact" (tests): 0 keeps the wide fan records even when the differences fit
-    int fanPrefetch = -1;        // option "fan_prefetch": L2 look-ahead of the fan kernel in 32-node warps (-1: one resident wave, 0: off)
+    int fanPrefetch = -1;        // option "fan_prefetch": L2 look-ahead of the fan kernel in 32-node warps (-1: a sixth of the resident wave, 0: off)
     bool pointsOnly = false;     // option "points_only": blocks of any size, femb_point_quantities only
     bool useFan = true;          // option "fan_rows": write-once fan kernel where it applies (else the accumulating row-owner kernel)
     int* d_blockAdj = nullptr;   // (numBlocks+1) x numNodes: start of each block's corners in a node's adjacency list (row-owner kernel)

@@ -110,7 +110,7 @@ void femb_plan_destroy(femb_plan* plan);
  *       in registers and stored once); 0: the accumulating row-owner kernel.  "fan_compact" (before finalize): 0 keeps the
  *       wide fan records even when node / element ids fit the compact forms (4 nodes: 24-bit differences to the owner;
  *       3 nodes: 8-byte chained records) (tests); "fan_prefetch": L2 look-ahead distance of the fan kernel in 32-node
- *       warps (-1 default: one resident wave, 0 off; a hint only, results do not depend on it);
+ *       warps (-1 default: a sixth of the resident wave, 0 off; a hint only, results do not depend on it);
  *   "points_only" (before the first block): blocks of any node / point count, for femb_point_quantities only;
  *   "balance_rows" (before finalize): row schedule of the row-owner kernel -- 0 threads take nodes in node order,
  *       1 (default) nodes of every 256-node window are ordered by their number of adjacent elements when that saves
