@@ -163,6 +163,18 @@ static int launch_fan(const femb_plan* p, const DMat& D, const fan::Args& A, cud
         CUDA_TRY(cudaFuncSetAttribute(fan::k_assemble_fan<NN, WK, WR, CMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conf = smem;
     }
+    {   // Shared-memory carve-out: 85 % of what the register-limited number of warps would need -- L1 capacity for the node
+        // data the corners share is worth more than the last resident warps (sweep on one box: config 2 29.6 us at
+        // 60-72 %, 30.9 at 80-100 %, 31.0 at 55 %; config 4 219 us at 68-75 %, 237 at 80-100 %, 227 at 60 %).
+        static int carved[64] = {};
+        int& cv = carved[p->device & 63];
+        const int want = p->fanCarveout >= 0 ? p->fanCarveout
+                                             : std::min(100, (int)((fan::resident_warps<NN>() * (smem + 1024) * 85 + 228 * 1024 - 1) / (228 * 1024)));
+        if (cv != want + 1) {
+            CUDA_TRY(cudaFuncSetAttribute(fan::k_assemble_fan<NN, WK, WR, CMP>, cudaFuncAttributePreferredSharedMemoryCarveout, want));
+            cv = want + 1;
+        }
+    }
     fan::k_assemble_fan<NN, WK, WR, CMP><<<grid_for(p->numNodes, fan::BLOCK), fan::BLOCK, smem, st>>>(D, A);
     return 0;
 }

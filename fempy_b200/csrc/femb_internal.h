@@ -94,6 +94,7 @@ struct femb_plan {
     bool fanCompactAllowed = true;  // option "fan_compact" (tests): 0 keeps the wide fan records even when the differences fit
     int fanPrefetch = -1;        // option "fan_prefetch": L2 look-ahead of the fan kernel in 32-node warps (-1: a sixth of the resident wave, 0: off)
     bool pointsOnly = false;     // option "points_only": blocks of any size, femb_point_quantities only
+    int fanCarveout = -1;        // option "fan_carveout": shared-memory carve-out of the fan kernel in percent (-1: what the resident warps need)
     bool useFan = true;          // option "fan_rows": write-once fan kernel where it applies (else the accumulating row-owner kernel)
     int* d_blockAdj = nullptr;   // (numBlocks+1) x numNodes: start of each block's corners in a node's adjacency list (row-owner kernel)
     int* d_rowOrder = nullptr;   // plan-time temporary: balanced row order (plan.cu: k_row_order), node of every thread slot, -1 = padding

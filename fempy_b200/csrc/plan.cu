@@ -948,6 +948,9 @@ extern "C" int femb_plan_set_option(femb_plan* p, const char* name, int64_t valu
     } else if (!strcmp(name, "fan_prefetch")) {
         if (value < -1) return fail("femb_plan_set_option: fan_prefetch must be -1 (default), 0 (off) or a distance in 32-node warps");
         p->fanPrefetch = (int)value;
+    } else if (!strcmp(name, "fan_carveout")) {
+        if (value < -1 || value > 100) return fail("femb_plan_set_option: fan_carveout is a percentage (or -1 for the default)");
+        p->fanCarveout = (int)value;
     } else if (!strcmp(name, "fan_rows")) {
         if (value != 0 && value != 1) return fail("femb_plan_set_option: fan_rows must be 0 or 1");
         p->useFan = value != 0;

@@ -111,6 +111,8 @@ void femb_plan_destroy(femb_plan* plan);
  *       wide fan records even when node / element ids fit the compact forms (4 nodes: 24-bit differences to the owner;
  *       3 nodes: 8-byte chained records) (tests); "fan_prefetch": L2 look-ahead distance of the fan kernel in 32-node
  *       warps (-1 default: a sixth of the resident wave, 0 off; a hint only, results do not depend on it);
+ *       "fan_carveout": shared-memory carve-out of the fan kernel in percent (-1 default: 85 % of what the register-limited
+ *       warps would need; performance only);
  *   "points_only" (before the first block): blocks of any node / point count, for femb_point_quantities only;
  *   "balance_rows" (before finalize): row schedule of the row-owner kernel -- 0 threads take nodes in node order,
  *       1 (default) nodes of every 256-node window are ordered by their number of adjacent elements when that saves
