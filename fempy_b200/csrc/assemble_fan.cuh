@@ -80,6 +80,9 @@ __host__ __device__ constexpr int resident_warps() {
 }
 // write-out by one cp.async.bulk per warp from the unswizzled staging area (bit 0: 3-node elements, bit 1: 4-node
 // elements).  Measured: 4 nodes 32.3 -> 30.3 us at config 2, 2.34 -> 2.19 ms at config 5; 3 nodes 256 -> 265 us at config 4
+#ifndef FAN_QSTASH
+#define FAN_QSTASH 1
+#endif
 #ifndef FAN_BULK
 #define FAN_BULK 2
 #endif
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
                     fma(P1, xb, fma(R1, xf, -(Q1 * xc))), b0, b1, b2, b3);
             b0 += k0, b1 += k1, b2 += k2, b3 += k3;
             store((kwc >> 7) & 0x7f, b0, b1, b2, b3, q1);
+            if (FAN_QSTASH && WR && c == 0) acc[swz(ownStart + (int)(kwc & 0x7f))] = q1;
             apply_d(fma(Q0, yd, -fma(P0, ya, R0 * yf)), fma(Q0, xd, -fma(P0, xa, R0 * xf)), fma(Q1, yd, -fma(P1, ya, R1 * yf)),
                     fma(Q1, xd, -fma(P1, xa, R1 * xf)), b0, b1, b2, b3);
             store((kwc >> 14) & 0x7f, b0, b1, b2, b3, q2);
@@ -310,6 +314,7 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             apply_d(A0 * g01, A0 * g11, A1 * g01, A1 * g11, b0, b1, b2, b3);
             b0 += k0, b1 += k1, b2 += k2, b3 += k3;
             store((kwc >> 7) & 0x7f, b0, b1, b2, b3, q1);
+            if (FAN_QSTASH && WR && c == 0) acc[swz(ownStart + (int)(kwc & 0x7f))] = q1;
             apply_d(A0 * g02, A0 * g12, A1 * g02, A1 * g12, k0, k1, k2, k3);
         }
         if (!(kwc & (3u << 28))) {  // the fan ends here (open end or chain break): the carried block is final
@@ -321,7 +326,9 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
     }
     if (nc > 0) {
         if (lastFlags & (1u << 29)) {  // closed fan: the last corner continues into the first one's first neighbour
-            residual(k0, k1, k2, k3, WR ? __ldg(A.states + firstNode) : make_double2(0.0, 0.0));
+            // FAN_QSTASH: the state of the first corner's first neighbour waited in my own block's staging slot (free until
+            // the own block is stored below): no dependent global load in the epilogue
+            residual(k0, k1, k2, k3, !WR ? make_double2(0.0, 0.0) : FAN_QSTASH ? acc[swz(ownStart + (int)(lastFlags & 0x7f))] : __ldg(A.states + firstNode));
             if (WK) {
                 double2& s0 = acc[swz(ownStart + firstSlot)];
                 double2& s1 = acc[swz(ownStart + deg + firstSlot)];
