@@ -83,6 +83,9 @@ __host__ __device__ constexpr int resident_warps() {
 #ifndef FAN_QSTASH
 #define FAN_QSTASH 1
 #endif
+#ifndef FAN_QLAST
+#define FAN_QLAST 1
+#endif
 #ifndef FAN_BULK
 #define FAN_BULK 2
 #endif
@@ -244,11 +247,13 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             q1 = ld_early(A.states + n1);
             if (NN == 4) q2 = ld_early(A.states + n2);
         }
+        const unsigned kwc = kw;
+        lastFlags = kwc;
+        double2 qL = make_double2(0.0, 0.0);  // an ending fan's last neighbour state: requested here, not after the corner
+        if (FAN_QLAST && WR && !(kwc & (3u << 28))) qL = ld_early(A.states + nLast);
         int4 rec2 = make_int4(0, 0, 0, 0);
         int el2 = 0;
         if (c + 2 < nc) load_rec(c + 2, rec2, el2);
-        const unsigned kwc = kw;
-        lastFlags = kwc;
         if (NN == 3 && e < A.pfElemLimit) prefetch_l2(A.thick + e + A.pfElems);
         // the next corner's coordinates and thickness replace this corner's once the geometry has consumed them
         auto next_corner = [&]() {
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(BLOCK, resident_warps<NN>()) k_assemble_fan(co
             apply_d(A0 * g02, A0 * g12, A1 * g02, A1 * g12, k0, k1, k2, k3);
         }
         if (!(kwc & (3u << 28))) {  // the fan ends here (open end or chain break): the carried block is final
-            store((kwc >> (7 * (NN - 1))) & 0x7f, k0, k1, k2, k3, WR ? __ldg(A.states + nLast) : make_double2(0.0, 0.0));
+            store((kwc >> (7 * (NN - 1))) & 0x7f, k0, k1, k2, k3, !WR ? make_double2(0.0, 0.0) : FAN_QLAST ? qL : __ldg(A.states + nLast));
             k0 = k1 = k2 = k3 = 0.0;
         }
         rec1 = rec2;
